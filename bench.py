@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- GStencil/s of the LoRAStencil hot path on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # our CUDA path
+    python bench.py --impl reference --gpus 1 --steps K --warmup W # the reference's CPU stencil (test_cpu)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # slab-decomposed, one rank per GPU
+
+Workload (config.workload): BASELINE.json configs[1] -- `lorastencil_1d 1d2r 268435456 1000`: one STEP is
+the whole job, 1000 launches of the 9-tap 1-D operator over 2^28 points (per GPU: weak scaling, the
+global line is N x 2^28 points cut into slabs with a 4-element halo exchange per launch).
+
+Numbers on the JSON line:
+  value      cells x launches / second / 1e9 with the grid resident in HBM (CUDA events on the launch stream,
+             max over ranks).  K = 1 convention; the artifact's own printout multiplies by 2 for 1d2r
+             (src/1d/gpu_2r.cu:134) -- that figure is `value_artifact_units`.
+  e2e        the same job through the reference-facing operator `gpu_1d2r(in, out, params, times, n)` with
+             pinned HOST buffers: H2D of the padded line, 1000 launches, D2H, all inside the timed region.
+  roofline   dominant kernel (k_stencil1d): 16 B per cell per launch (one FP64 read + one write,
+             SURVEY.md section 8d) / its average launch duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the reference's own test_cpu (oracle/_ref, compiled from its main.cu) on the host cores,
+             timed on a bounded sample (a few launches over the same 2^28-point line).
+  shapes     the other seven shapes at their BASELINE sizes (device-resident, 1 GPU), same definitions.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+HALO = {1: (4,), 2: (4, 4), 3: (1, 2, 4)}
+ARTIFACT_K = {"1d1r": 3, "1d2r": 2, "star2d1r": 3, "box2d1r": 3, "star2d3r": 1, "box2d3r": 3, "box3d1r": 1, "star3d1r": 1}
+HEADLINE = ("1d2r", (1 << 28,), 1000)
+# BASELINE.json configs (b)-(d) on one GPU; launches per measurement kept short, the per-launch cost is constant
+SHAPE_TABLE = [("1d1r", (1 << 28,), 50), ("1d2r", (1 << 28,), 50), ("star2d1r", (10240, 10240), 100),
+               ("box2d1r", (10240, 10240), 100), ("star2d3r", (10240, 10240), 100), ("box2d3r", (10240, 10240), 100),
+               ("box3d1r", (512, 512, 512), 100), ("star3d1r", (512, 512, 512), 100)]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+                out = ""
+            self.lines = [l for l in out.splitlines() if l.strip()]
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v == "Active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU arm / cpu_baseline: the reference's verbatim test_cpu on all host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_runner(shape, dims):
+    """Returns (run_once, cores, kind): run_once() does ONE launch over the whole grid with the reference's
+    test_cpu (oracle/_ref) split over `cores` host threads along the outermost axis; falls back to the
+    OpenMP oracle port when oracle/_ref is absent."""
+    import oracle
+    d = oracle.dim_of(shape)
+    padded = oracle.padded_shape(shape, dims)
+    rng = np.random.default_rng(0)
+    mod = 10000 if d == 1 else 100
+    a = rng.integers(0, mod, size=padded).astype(np.float64)
+    out = np.zeros_like(a)
+    params = np.ascontiguousarray(oracle.reference_params(shape))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    h0 = oracle.HALO[d][0]
+    rest = int(np.prod(padded[1:])) if d > 1 else 1
+    if oracle.ref_available("cpu", d):
+        fn = oracle.ref_cpu_fn(d)
+        n0 = dims[0]
+        cuts = [n0 * i // cores for i in range(cores + 1)]
+
+        def piece(i):
+            lo, hi = cuts[i], cuts[i + 1]
+            if hi <= lo:
+                return
+            off = lo * rest * 8
+            fn(a.ctypes.data + off, out.ctypes.data + off, params.ctypes.data, hi - lo + 2 * h0,
+               *[int(x) for x in padded[1:]])
+
+        def run_once():
+            ts = [threading.Thread(target=piece, args=(i,)) for i in range(cores)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        return run_once, cores, "reference"
+    L = oracle.lib()
+    cores = L.oracle_max_threads()
+
+    def run_once():
+        oracle.step(shape, a, params)
+    return run_once, cores, "port"
+
+
+def time_cpu(shape, dims, min_seconds=8.0, max_launches=8):
+    run_once, cores, kind = cpu_reference_runner(shape, dims)
+    run_once()  # warm (page-faults the output)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        run_once()
+        n += 1
+        el = time.perf_counter() - t0
+        if el * cores >= min_seconds or n >= max_launches:
+            break
+    cells = float(np.prod(dims))
+    return {"value": cells * n / el / 1e9, "unit": "GStencil/s", "cores": cores, "kind": kind,
+            "sample": f"{n} launch(es) of {shape} over the full {'x'.join(map(str, dims))} grid "
+                      f"(of the job's launches), {el:.2f} s wall"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape, dims, times = HEADLINE
+    run_once, cores, kind = cpu_reference_runner(shape, dims)
+    for _ in range(args.warmup):
+        run_once()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_once()
+    el = time.perf_counter() - t0
+    cells = float(np.prod(dims))
+    v = cells * args.steps / el / 1e9
+    sample = f"each step = 1 launch of {shape} over the full {dims[0]}-point line (the job is {times} such launches)"
+    print(json.dumps({
+        "impl": "reference", "metric": "GStencil/s", "value": v, "unit": "GStencil/s (cells x launches / s / 1e9)",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"lorastencil_1d {shape} {dims[0]} {times} (BASELINE.json configs[1])", "shape": shape,
+                   "points_per_gpu": dims[0], "launches_per_job": times},
+        "cpu_baseline": {"value": v, "unit": "GStencil/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def device_fill(torch, shape_padded, mod, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    return torch.randint(0, mod, shape_padded, generator=g, device=device).double()
+
+
+def measure_shape(torch, ls, shape, dims, launches, hbm_gbs, reps=3):
+    """Device-resident GStencil/s of one shape on the current device (CUDA events, best of reps)."""
+    plan = ls.Plan(shape, dims)
+    d = len(dims)
+    b0 = device_fill(torch, plan.padded_shape, 10000 if d == 1 else 100, "cuda", 1)
+    b1 = plan.new_buffer()
+    plan.run(b0, b1, 3)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run(b0, b1, launches)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    cells = float(np.prod(dims))
+    per_launch_s = best / 1e3 / launches
+    gst = cells / per_launch_s / 1e9
+    ach = cells * 16 / per_launch_s / 1e9
+    desc = plan.describe
+    del plan, b0, b1
+    torch.cuda.empty_cache()
+    return {"shape": shape, "dims": list(dims), "launches": launches, "gstencils": gst,
+            "gstencils_artifact_units": gst * ARTIFACT_K[shape], "us_per_launch": per_launch_s * 1e6,
+            "hbm_gbs_algorithmic": ach, "roofline_frac": ach / hbm_gbs, "form": desc}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--times", type=int, default=HEADLINE[2], help="launches per step (default: the job's 1000)")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape table")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import lorastencil_b200 as ls
+    from lorastencil_b200 import ops
+    from lorastencil_b200.slab import SlabRunner
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    ops.set_verbose(False)
+    hbm_gbs, peak_src = peaks()
+    shape, dims, _ = HEADLINE
+    times = args.times
+    n = dims[0]
+    cells_per_gpu = float(n)
+
+    # ---- device-resident arm: slab runner (world == 1: a plain plan) ----
+    runner = SlabRunner(shape, (n * world,), device=dev)
+    runner.buf[0].copy_(device_fill(torch, runner.geo.local_padded, 10000, dev, 1234 + rank))
+    plan = runner.plan
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        runner.run(times)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    launches0 = plan.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            one_step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    gpu_launches = plan.launches - launches0
+    total_cells_launches = cells_per_gpu * world * times * args.steps
+    value = total_cells_launches / (ms / 1e3) / 1e9
+    main_launches = times * args.steps  # full-slab (world 1) or interior (world > 1) launches per rank
+    us_per_launch = ms * 1e3 / main_launches
+    achieved = cells_per_gpu * 16 / (us_per_launch * 1e-6) / 1e9
+
+    # ---- e2e: through the reference-facing operator with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        hin = torch.empty(n + 8, dtype=torch.float64).pin_memory()
+        hout = torch.empty(n + 8, dtype=torch.float64).pin_memory()
+        hin.copy_(torch.randint(0, 10000, (n + 8,)).double())
+        params = ls.reference_table(shape)
+        k_e2e = max(1, min(args.steps, 3))
+        if world == 1:
+            ops.gpu_1d2r(hin, hout, params, min(times, 10), n)  # warm: allocates the operator's device workspace
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                ops.gpu_1d2r(hin, hout, params, times, n)
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+        else:
+            def e2e_step():
+                runner.buf[0].copy_(hin, non_blocking=True)
+                runner.buf[1].zero_()
+                runner.launch = 0
+                res = runner.run(times)
+                hout.copy_(res, non_blocking=True)
+                torch.cuda.synchronize()
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(k_e2e):
+                e2e_step()
+            barrier()
+            el = time.perf_counter() - t0
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": cells_per_gpu * world * times * k_e2e / el / 1e9, "unit": "GStencil/s",
+               "h2d_bytes_per_step": (n + 8) * 8 * world, "d2h_bytes_per_step": (n + 7) * 8 * world,
+               "steps": k_e2e, "ms_per_step": el / k_e2e * 1e3,
+               "api": "lorastencil_b200.ops.gpu_1d2r -> lora_gpu_1d2r (C ABI), pinned host buffers" if world == 1 else
+                      "pinned host slab -> SlabRunner.run -> pinned host slab"}
+        del hin, hout
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "GStencil/s", "value": value, "unit": "GStencil/s (cells x launches / s / 1e9)",
+        "value_artifact_units": value * ARTIFACT_K[shape],
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"lorastencil_1d {shape} {n} {times} per GPU (BASELINE.json configs[1])",
+                   "shape": shape, "points_per_gpu": n, "launches_per_step": times,
+                   "decomposition": "single device" if world == 1 else f"{world} slabs, 4-element halo exchange per launch (NCCL send/recv)",
+                   "l2": "inputs (2.1 GB per buffer) larger than L2; no flush needed",
+                   "values": "reference weights: FP64 overflows to inf after ~217 launches exactly as in the reference run; timing only",
+                   "kernel_form": plan.describe},
+        "gpu_launches": gpu_launches,
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                     "traffic": None, "kernel": "k_stencil1d", "us_per_launch": us_per_launch,
+                     "algorithmic_bytes_per_launch": cells_per_gpu * 16, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = time_cpu(shape, dims)
+    if world == 1 and not args.no_shapes:
+        line["shapes"] = [measure_shape(torch, ls, s, d, l, hbm_gbs) for s, d, l in SHAPE_TABLE]
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

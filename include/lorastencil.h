@@ -1,0 +1,170 @@
+/*
+ * lorastencil.h -- C ABI of liblorastencil_b200.so, the B200-native (sm_100a) replacement for
+ * the LoRAStencil host operators.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Citations are relative to the reference tree (zondie17/LoRAStencil).
+ *
+ * Layer 1 (drop-in): lora_gpu_*  == the reference's gpu_* host operators
+ *     src/1d/1d_utils.h:45-47   gpu_1d1r, gpu_1d2r
+ *     src/2d/2d_utils.h:47-51   gpu_star_2d1r, gpu_star_2d3r, gpu_box_2d3r
+ *     src/3d/3d_utils.h:44-48   gpu_box_3d1r, gpu_star_3d1r
+ *   Same argument order and meaning, same buffer semantics (halo-padded row-major FP64 host
+ *   arrays, ping-pong over `times` launches, `out` = whole padded buffer `times % 2`), same
+ *   stdout banner, same fatal-error behaviour (message + exit(1)).  The library additionally
+ *   exports the reference's C++-mangled names (gpu_box_2d3r(...) etc., see
+ *   include/lorastencil_dropin.hpp) so the reference's own main.cu links against it unmodified.
+ *
+ * Layer 2 (device-resident plan API): what the benchmark, the multi-GPU slab driver and a
+ *   host application that keeps its grids in HBM use.  Returns error codes, never exits.
+ *
+ * Layer 3 (host-side low-rank decomposition): the C++ factorisation that replaces
+ *   src/2d/gpu.cu:280-350 (pyramidal rank-1 peel) and its siblings, exposed for inspection.
+ */
+#ifndef LORASTENCIL_H
+#define LORASTENCIL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- shapes: the CLI names of README.md:39-48 ---- */
+typedef enum {
+    LORA_1D1R = 0,
+    LORA_1D2R = 1,
+    LORA_STAR2D1R = 2,
+    LORA_BOX2D1R = 3,
+    LORA_STAR2D3R = 4,
+    LORA_BOX2D3R = 5,
+    LORA_BOX3D1R = 6,
+    LORA_STAR3D1R = 7,
+    LORA_NUM_SHAPES = 8
+} lora_shape_t;
+
+/* how `params` is interpreted when a plan is built */
+typedef enum {
+    /* exactly what the reference GPU operator does with `params`, quirks included:
+     * star2d1r / star3d1r ignore it (src/2d/gpu.cu:486-487, src/3d/gpu_star.cu:142-151),
+     * box3d1r reads params[0..2] only (src/3d/gpu_box.cu:161), box2d applies the three rank-1
+     * terms of its peel and drops the 1x1 remainder (src/2d/gpu.cu:349-358). */
+    LORA_WEIGHTS_REFERENCE = 0,
+    /* every one of the 9 / 49 / 27 weights is honoured (== the reference's test_cpu); the host
+     * decomposition picks the cheapest exact form (cross, pyramid, rank-1 + residual,
+     * separable, direct taps). */
+    LORA_WEIGHTS_GENERAL = 1
+} lora_weight_mode_t;
+
+/* error codes of layer 2/3 */
+enum {
+    LORA_OK = 0,
+    LORA_ERR_ARG = 1,      /* bad shape / size / null pointer / misaligned buffer */
+    LORA_ERR_CUDA = 2,     /* a CUDA runtime or driver call failed */
+    LORA_ERR_UNSUPPORTED = 3
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Layer 1: drop-in host operators (host buffers in, host buffers out)
+ * ------------------------------------------------------------------------------------------
+ * in / out: PADDED arrays  1-D n+8 | 2-D (m+8)x(n+8) | 3-D (h+2)x(m+4)x(n+8)  doubles.
+ * params:   9 | 49 | 27 doubles.   times: number of launches.   No size-multiple constraints
+ * (the reference needs n%1024, m%32, n%64, m%8: src/1d/gpu_1r.cu:112, src/2d/gpu.cu:402-403,
+ * src/3d/gpu_box.cu:201-202).  1-D copies back n+7 doubles like src/1d/gpu_1r.cu:134. */
+void lora_gpu_1d1r(const double *in, double *out, const double *params, int times, int input_n);
+void lora_gpu_1d2r(const double *in, double *out, const double *params, int times, int input_n);
+void lora_gpu_star_2d1r(const double *in, double *out, const double *params, int times, int input_m, int input_n);
+void lora_gpu_star_2d3r(const double *in, double *out, const double *params, int times, int input_m, int input_n);
+void lora_gpu_box_2d3r(const double *in, double *out, const double *params, int times, int input_m, int input_n);
+void lora_gpu_box_3d1r(const double *in, double *out, const double *params, int times, int input_h, int input_m, int input_n);
+void lora_gpu_star_3d1r(const double *in, double *out, const double *params, int times, int input_h, int input_m, int input_n);
+
+/* generic form of the seven above: shape selects the operator (box2d1r and box2d3r both run
+ * gpu_box_2d3r, src/2d/main.cu:276-279); dims = {n} | {m,n} | {h,m,n}.  Same fatal-error
+ * behaviour.  mode as in lora_weight_mode_t. */
+void lora_gpu_run_host(int shape, int mode, const double *in, double *out, const double *params, int times,
+                       const long long *dims);
+
+/* 1 (default): print the reference's banner "LoRAStencil(<dim> <shape>): / Time = N[ms] /
+ * GStencil/s = x" from the drop-in operators (src/2d/gpu.cu:415-419); 0: stay silent.
+ * Returns the previous value.  Also settable with the environment variable LORA_QUIET=1. */
+int lora_set_verbose(int on);
+
+/* milliseconds the last lora_gpu_* call spent in its launch loop (the reference's timed region:
+ * launches + device sync, src/2d/gpu.cu:408-414), and in the whole call (alloc + H2D + D2H too) */
+double lora_last_loop_ms(void);
+double lora_last_total_ms(void);
+
+/* free the device workspace the drop-in operators cache between calls */
+void lora_release_workspace(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Layer 2: device-resident plans
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lora_plan lora_plan_t;
+
+/* dims = interior sizes {n} | {m,n} | {h,m,n} of the grid THIS device holds (for a slab: the
+ * slab's interior).  params may be NULL = the reference CLI's table for `shape`. */
+int lora_plan_create(lora_plan_t **plan, int shape, int mode, const double *params, const long long *dims);
+void lora_plan_destroy(lora_plan_t *plan);
+
+/* number of doubles of one padded device buffer for this plan */
+long long lora_plan_padded_elems(const lora_plan_t *plan);
+
+/* One launch: read padded device buffer `src`, write the interior of `dst` for outermost-axis
+ * interior indices [lo, hi) (0 <= lo <= hi <= dims[0]); asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream).  Halo cells of dst are not touched
+ * (S2 of SURVEY.md section 8a). */
+int lora_plan_step(lora_plan_t *plan, const double *src, double *dst, long long lo, long long hi, void *stream);
+
+/* `times` launches ping-ponging buf0 -> buf1 -> buf0 ...; launch i reads buf[i%2].  The result
+ * is in buf[times%2].  Asynchronous on `stream`. */
+int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void *stream);
+
+/* how many kernel launches the plan has issued so far (bench.py's gpu_launches) */
+long long lora_plan_launch_count(const lora_plan_t *plan);
+
+/* textual description of the kernel form chosen by the host decomposition, e.g.
+ * "2d pyramid rank-3 (7/5/3) + centre 0"; owned by the plan */
+const char *lora_plan_describe(const lora_plan_t *plan);
+
+/* last error message of layer 2/3 on this thread ("" if none) */
+const char *lora_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Layer 3: host low-rank decomposition (inspection / tests)
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    LORA_FORM_TAPS9 = 0,      /* 1-D: 9 direct taps */
+    LORA_FORM_CROSS = 1,      /* 2-D star: column arm (with centre) + row arm (without) */
+    LORA_FORM_PYRAMID = 2,    /* 2-D box: sum of 3 rank-1 terms with support 7/5/3 + centre */
+    LORA_FORM_DIAMOND = 3,    /* 2-D: one rank-1 term of support 5 + 8 residual taps */
+    LORA_FORM_DIRECT49 = 4,   /* 2-D: all 49 taps */
+    LORA_FORM_SEP3 = 5,       /* 3-D box: one rank-1 term a (x) b (x) c */
+    LORA_FORM_STAR7 = 6,      /* 3-D star: 7 taps */
+    LORA_FORM_DIRECT27 = 7    /* 3-D: all 27 taps */
+};
+
+typedef struct {
+    int form;            /* LORA_FORM_* */
+    int nterms;          /* rank-1 terms in use (0..3) */
+    double vert[3][7];   /* term t, vertical (row-offset) profile, index = dr+3 */
+    double horiz[3][7];  /* term t, horizontal (col-offset) profile, index = dc+3 */
+    double centre;       /* extra weight on the centre tap (pyramid remainder) */
+    double residual[8];  /* DIAMOND: (0,-3),(0,+3),(-3,0),(+3,0),(-2,-2),(-2,+2),(+2,-2),(+2,+2) */
+    double recon_err;    /* max |sum of terms - effective weights| */
+    int macs_per_cell;   /* multiply-adds per output cell of the chosen form */
+} lora_decomp2d_t;
+
+/* factor a 7x7 weight table; shape picks the reference quirks when mode == REFERENCE */
+int lora_decompose_2d(int shape, int mode, const double *params49, lora_decomp2d_t *out);
+
+/* the weight table the reference CLI passes for `shape` (src/1d/main.cu:77-78, src/2d/main.cu:139-195,
+ * src/3d/main.cu:112-125): 9 / 49 / 27 doubles */
+int lora_reference_table(int shape, double *table_out);
+
+/* effective direct-tap weights (9 / 49 / 27 doubles) a plan built from (shape, mode, params)
+ * applies -- what the parity tests feed to the CPU oracle */
+int lora_effective_weights(int shape, int mode, const double *params, double *weights_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LORASTENCIL_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of include/lorastencil.h.  Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SHAPES = ("1d1r", "1d2r", "star2d1r", "box2d1r", "star2d3r", "box2d3r", "box3d1r", "star3d1r")
+SHAPE_IDS = {name: i for i, name in enumerate(SHAPES)}  # == lora_shape_t
+WEIGHTS_REFERENCE = 0
+WEIGHTS_GENERAL = 1
+
+# every symbol include/lorastencil.h declares (tests/test_abi.py checks the library exports them all)
+C_ABI_SYMBOLS = (
+    "lora_gpu_1d1r", "lora_gpu_1d2r", "lora_gpu_star_2d1r", "lora_gpu_star_2d3r", "lora_gpu_box_2d3r",
+    "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
+    "lora_last_total_ms", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
+    "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_launch_count", "lora_plan_describe",
+    "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
+)
+# the reference's own C++ symbols (include/lorastencil_dropin.hpp)
+CXX_DROPIN_SYMBOLS = (
+    "_Z8gpu_1d1rPKdPdS0_ii", "_Z8gpu_1d2rPKdPdS0_ii", "_Z13gpu_star_2d1rPKdPdS0_iii",
+    "_Z13gpu_star_2d3rPKdPdS0_iii", "_Z12gpu_box_2d3rPKdPdS0_iii", "_Z12gpu_box_3d1rPKdPdS0_iiii",
+    "_Z13gpu_star_3d1rPKdPdS0_iiii",
+)
+
+
+class LoraError(RuntimeError):
+    pass
+
+
+class Decomp2D(Structure):
+    _fields_ = [("form", c_int), ("nterms", c_int), ("vert", c_double * 7 * 3), ("horiz", c_double * 7 * 3),
+                ("centre", c_double), ("residual", c_double * 8), ("recon_err", c_double), ("macs_per_cell", c_int)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "lib", "liblorastencil_b200.so")
+
+
+def library_built() -> bool:
+    return os.path.exists(lib_path())
+
+
+def build(force: bool = False) -> None:
+    """Compile the CUDA library and the CLI drivers for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise LoraError("building liblorastencil_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not library_built():
+        raise LoraError(f"{lib_path()} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = ctypes.CDLL(lib_path())
+    dp = POINTER(c_double)
+    for name, nd in (("lora_gpu_1d1r", 1), ("lora_gpu_1d2r", 1), ("lora_gpu_star_2d1r", 2), ("lora_gpu_star_2d3r", 2),
+                     ("lora_gpu_box_2d3r", 2), ("lora_gpu_box_3d1r", 3), ("lora_gpu_star_3d1r", 3)):
+        f = getattr(L, name)
+        f.argtypes = [c_void_p, c_void_p, dp, c_int] + [c_int] * nd
+        f.restype = None
+    L.lora_gpu_run_host.argtypes = [c_int, c_int, c_void_p, c_void_p, dp, c_int, POINTER(c_longlong)]
+    L.lora_gpu_run_host.restype = None
+    L.lora_set_verbose.argtypes = [c_int]
+    L.lora_set_verbose.restype = c_int
+    L.lora_last_loop_ms.restype = c_double
+    L.lora_last_total_ms.restype = c_double
+    L.lora_release_workspace.restype = None
+    L.lora_plan_create.argtypes = [POINTER(c_void_p), c_int, c_int, dp, POINTER(c_longlong)]
+    L.lora_plan_create.restype = c_int
+    L.lora_plan_destroy.argtypes = [c_void_p]
+    L.lora_plan_destroy.restype = None
+    L.lora_plan_padded_elems.argtypes = [c_void_p]
+    L.lora_plan_padded_elems.restype = c_longlong
+    L.lora_plan_step.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p]
+    L.lora_plan_step.restype = c_int
+    L.lora_plan_run.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    L.lora_plan_run.restype = c_int
+    L.lora_plan_launch_count.argtypes = [c_void_p]
+    L.lora_plan_launch_count.restype = c_longlong
+    L.lora_plan_describe.argtypes = [c_void_p]
+    L.lora_plan_describe.restype = c_char_p
+    L.lora_last_error.restype = c_char_p
+    L.lora_decompose_2d.argtypes = [c_int, c_int, dp, POINTER(Decomp2D)]
+    L.lora_decompose_2d.restype = c_int
+    L.lora_reference_table.argtypes = [c_int, dp]
+    L.lora_reference_table.restype = c_int
+    L.lora_effective_weights.argtypes = [c_int, c_int, dp, dp]
+    L.lora_effective_weights.restype = c_int
+    _LIB = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise LoraError(f"{what}: error {rc}: {lib().lora_last_error().decode()}")

@@ -1,0 +1,211 @@
+// cli_main.cpp -- the three command-line drivers lorastencil_1d / lorastencil_2d / lorastencil_3d
+// (compile with -DLORA_CLI_DIM=1|2|3).  Same argv, same stdout/stderr lines and return codes as the
+// reference drivers:
+//   src/1d/main.cu:43-181   lorastencil_1d {1d1r|1d2r} n times
+//   src/2d/main.cu:97-337   lorastencil_2d {star2d1r|box2d1r|star2d3r|box2d3r} m n times
+//   src/3d/main.cu:71-253   lorastencil_3d {box3d1r|star3d1r} h m n times
+// Extras the reference ignores: a trailing "--check" (or building with -DCHECK_ERROR) runs the
+// reference's verification protocol -- one direct-tap CPU step against one GPU launch, every interior
+// cell whose absolute difference exceeds 1e-7 is printed, then "Correct!" (src/2d/main.cu:282-328);
+// the process additionally returns 2 when a mismatch was found.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lorastencil.h"
+
+#ifndef LORA_CLI_DIM
+#error "compile with -DLORA_CLI_DIM=1|2|3"
+#endif
+
+namespace {
+
+struct ShapeName {
+    const char *cli;   // argv[1]
+    const char *info;  // ShapeStr[] of the reference
+    int shape;
+};
+
+#if LORA_CLI_DIM == 1
+constexpr int kDim = 1;
+const ShapeName kShapes[] = {{"1d1r", "1d1r", LORA_1D1R}, {"1d2r", "1d2r", LORA_1D2R}};
+const char *kHelp =
+    "Program name: lorastencil_1d\n"
+    "Usage: lorastencil_1d shape input_size time_size\n"
+    "Shape: 1d1r or 1d2r\n";
+const int kHalo[3] = {4, 0, 0};
+const int kFillMod = 10000;  // src/1d/main.cu:108
+const int kNParams = 9;
+#elif LORA_CLI_DIM == 2
+constexpr int kDim = 2;
+const ShapeName kShapes[] = {{"box2d1r", "box_2d1r", LORA_BOX2D1R},
+                             {"star2d1r", "star_2d1r", LORA_STAR2D1R},
+                             {"star2d3r", "star_2d3r", LORA_STAR2D3R},
+                             {"box2d3r", "box_2d3r", LORA_BOX2D3R}};
+const char *kHelp =
+    "Program name: lorastencil_2d\n"
+    "Usage: lorastencil_2d shape input_size_of_first_dimension input_size_of_second_dimension time_size\n"
+    "Shape: box2d1r or star2d1r or box2d3r or star2d3r\n";
+const int kHalo[3] = {4, 4, 0};
+const int kFillMod = 100;  // src/2d/main.cu:235
+const int kNParams = 49;
+#else
+constexpr int kDim = 3;
+const ShapeName kShapes[] = {{"box3d1r", "box_3d1r", LORA_BOX3D1R}, {"star3d1r", "star_3d1r", LORA_STAR3D1R}};
+const char *kHelp =
+    "Program name: lorastencil_3d\n"
+    "Usage: lorastencil_3d shape input_size_of_first_dimension input_size_of_second_dimension "
+    "input_size_of_third_dimension time_size\n"
+    "Shape: box3d1r or star3d1r\n";
+const int kHalo[3] = {1, 2, 4};
+const int kFillMod = 100;  // src/3d/main.cu:167
+const int kNParams = 27;
+#endif
+
+void print_help() { printf("%s\n", kHelp); }
+
+// one direct-tap step over the interior (the protocol of test_cpu, written for any dimension)
+void cpu_step(const std::vector<double> &in, std::vector<double> &out, const double *w, const long long *pd) {
+#if LORA_CLI_DIM == 1
+    for (long long c = 4; c < pd[0] - 4; c++) {
+        double a = 0;
+        for (int k = 0; k < 9; k++) a += w[k] * in[c - 4 + k];
+        out[c] = a;
+    }
+#elif LORA_CLI_DIM == 2
+    for (long long r = 4; r < pd[0] - 4; r++)
+        for (long long c = 4; c < pd[1] - 4; c++) {
+            double a = 0;
+            for (int dr = -3; dr <= 3; dr++)
+                for (int dc = -3; dc <= 3; dc++) a += w[(dr + 3) * 7 + dc + 3] * in[(r + dr) * pd[1] + c + dc];
+            out[r * pd[1] + c] = a;
+        }
+#else
+    for (long long h = 1; h < pd[0] - 1; h++)
+        for (long long r = 2; r < pd[1] - 2; r++)
+            for (long long c = 4; c < pd[2] - 4; c++) {
+                double a = 0;
+                for (int dh = -1; dh <= 1; dh++)
+                    for (int dr = -1; dr <= 1; dr++)
+                        for (int dc = -1; dc <= 1; dc++)
+                            a += w[(dh + 1) * 9 + (dr + 1) * 3 + dc + 1] *
+                                 in[((h + dh) * pd[1] + r + dr) * pd[2] + c + dc];
+                out[(h * pd[1] + r) * pd[2] + c] = a;
+            }
+#endif
+}
+
+}  // namespace
+
+int main(int argc, char *argv[]) {
+    if (argc < kDim + 3) {
+        print_help();
+        return 1;
+    }
+    const std::string arg1 = argv[1];
+    const ShapeName *sn = nullptr;
+    for (const auto &s : kShapes)
+        if (arg1 == s.cli) sn = &s;
+    if (!sn) {
+        print_help();
+        return 1;
+    }
+
+    long long dims[3] = {0, 0, 0};
+    int times = 0;
+    try {
+        for (int i = 0; i < kDim; i++) dims[i] = std::stoi(argv[2 + i]);
+        times = std::stoi(argv[2 + kDim]);
+    } catch (const std::invalid_argument &) {
+        std::cerr << "Invalid argument: cannot convert the parameter(s) to integer.\n";
+        return 1;
+    } catch (const std::out_of_range &) {
+        std::cerr << "Argument out of range: the parameter(s) is(are) too large.\n";
+        return 1;
+    }
+    bool check = false;
+#if defined(CHECK_ERROR)
+    check = true;
+#endif
+    for (int i = kDim + 3; i < argc; i++)
+        if (std::strcmp(argv[i], "--check") == 0) check = true;
+
+#if LORA_CLI_DIM == 1
+    printf("INFO: shape = %s, n = %lld, times = %d\n", sn->info, dims[0], times);
+#elif LORA_CLI_DIM == 2
+    printf("INFO: shape = %s, m = %lld, n = %lld, times = %d\n", sn->info, dims[0], dims[1], times);
+#else
+    printf("INFO: shape = %s, h = %lld, m = %lld, n = %lld, times = %d\n", sn->info, dims[0], dims[1], dims[2],
+           times);
+#endif
+
+    double params[49];
+    lora_reference_table(sn->shape, params);
+
+    long long pd[3] = {1, 1, 1}, total = 1;
+    for (int i = 0; i < kDim; i++) {
+        if (dims[i] <= 0) {
+            std::cerr << "Argument out of range: sizes must be positive.\n";
+            return 1;
+        }
+        pd[i] = dims[i] + 2 * kHalo[i];
+        total *= pd[i];
+    }
+    std::vector<double> matrix((size_t)total + 1), output((size_t)total + 1, 0.0);
+    // FILL_RANDOM of the reference: unseeded rand() over the whole padded array, halo included
+    for (long long i = 0; i < total; i++) matrix[i] = (double)(rand() % kFillMod);
+
+    if (check) {
+        std::cout << arg1 << std::endl;
+#if LORA_CLI_DIM == 1
+        for (int i = 0; i < 9; i++) std::cout << params[i] << std::endl;
+#elif LORA_CLI_DIM == 2
+        for (int i = 0; i < 7; i++) {
+            for (int j = 0; j < 7; j++) std::cout << params[i * 7 + j] << " ";
+            std::cout << std::endl;
+        }
+#else
+        for (int h = 0; h < 3; h++) {
+            for (int r = 0; r < 3; r++) {
+                for (int c = 0; c < 3; c++) std::cout << params[h * 9 + r * 3 + c] << " ";
+                std::cout << std::endl;
+            }
+            std::cout << std::endl;
+        }
+#endif
+    }
+
+    lora_gpu_run_host(sn->shape, LORA_WEIGHTS_REFERENCE, matrix.data(), output.data(), params, times, dims);
+
+    int rc = 0;
+    if (check) {
+        printf("\nChecking Correctness... \n");
+        std::vector<double> naive((size_t)total + 1, 0.0), lora((size_t)total + 1, 0.0);
+        cpu_step(matrix, naive, params, pd);
+        lora_gpu_run_host(sn->shape, LORA_WEIGHTS_REFERENCE, matrix.data(), lora.data(), params, 1, dims);
+        printf("Comparing naive and lora\n");
+        long long bad = 0;
+        const long long lo[3] = {kHalo[0], kHalo[1], kHalo[2]};
+        for (long long a = lo[0]; a < pd[0] - lo[0]; a++)
+            for (long long b = (kDim > 1 ? lo[1] : 0); b < (kDim > 1 ? pd[1] - lo[1] : 1); b++)
+                for (long long c = (kDim > 2 ? lo[2] : 0); c < (kDim > 2 ? pd[2] - lo[2] : 1); c++) {
+                    const long long idx = (kDim == 1) ? a : (kDim == 2) ? a * pd[1] + b : (a * pd[1] + b) * pd[2] + c;
+                    if (std::fabs(naive[idx] - lora[idx]) > 1e-7) {
+                        if (bad < 100)
+                            printf("index = %lld, naive = %lf, lora = %lf\n", idx, naive[idx], lora[idx]);
+                        bad++;
+                    }
+                }
+        if (bad) {
+            printf("%lld mismatching cells\n", bad);
+            rc = 2;
+        }
+        printf("Correct!\n");
+    }
+    return rc;
+}

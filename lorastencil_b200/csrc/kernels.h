@@ -1,0 +1,90 @@
+// kernels.h -- host-visible launch interface of the sm_100a stencil kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace lora {
+
+// ---- tiling constants shared by host planning and device code ----
+constexpr int kWarpCols = 128;     // one warp owns 32 lanes x 4 consecutive columns
+constexpr int kWarpsPerCta = 4;     // 1-D / 2-D: warps are independent workers, the CTA is only a container
+constexpr int kBoxCols = 136;      // 128 + 4 halo columns each side (stencil radius <= 4, 32-byte aligned)
+constexpr int kRowsPerStage = 4;   // rows of one TMA box
+constexpr int kStages = 3;         // per-warp ring depth
+constexpr int kStageElems = kRowsPerStage * kBoxCols;            // 544 doubles = 4352 B (34 x 128 B)
+constexpr int kSmem12 = kWarpsPerCta * kStages * kStageElems * 8 + kWarpsPerCta * kStages * 8;
+
+// 3-D: CTA tile of 32 rows x 128 columns per plane, 8 warps x (4 rows x 128 cols); warp 0 lane 0 also drives TMA
+constexpr int k3TileRows = 32;
+constexpr int k3TileCols = 128;
+constexpr int k3BoxRows = k3TileRows + 2;
+constexpr int k3BoxCols = k3TileCols + 4;  // 2 halo columns each side keeps the box origin 16-byte aligned
+constexpr int k3Stages = 4;
+constexpr int k3StageBytes = ((k3BoxRows * k3BoxCols * 8 + 127) / 128) * 128;
+constexpr int k3Smem = k3Stages * k3StageBytes + 2 * k3Stages * 8;
+constexpr int k3Warps = 8;
+constexpr int k3Threads = 32 * k3Warps;
+
+struct Weights1D {
+    double w[9];
+};
+
+struct Weights2D {
+    double vert[3][7];
+    double horiz[3][7];
+    double centre;
+    double residual[8];
+};
+
+struct WeightsDirect49 {
+    double w[49];
+};
+
+struct Weights3D {
+    double a[3], b[3], c[3];  // SEP3
+    double star[7];           // STAR7: centre, n-1, n+1, m-1, m+1, h-1, h+1
+    double direct[27];        // DIRECT27
+};
+
+struct Geom1D {
+    const double *in;   // padded source
+    double *out;        // padded destination
+    long long n;        // interior length of the device array
+    long long lo, hi;   // interior range of this launch (lo even)
+    int rows_per_task;  // 128-element rows one warp sweeps
+    long long ntasks;
+    int vec4;           // 256-bit stores allowed (lo % 4 == 0 and 32-byte aligned base)
+};
+
+struct Geom2D {
+    double *out;
+    long long pitch;  // padded columns
+    int m, n;
+    int row_lo, row_hi;
+    int rows_per_chunk;
+    int nstrips;
+    int ntasks;
+    int vec4;  // 256-bit stores allowed (n % 4 == 0 and 32-byte aligned base)
+};
+
+struct Geom3D {
+    double *out;
+    long long row_pitch;    // padded columns
+    long long plane_pitch;  // padded rows * padded columns
+    int h, m, n;
+    int h_lo, h_hi;
+    int planes_per_chunk;
+    int tiles_m, tiles_n;
+    int vec4;
+};
+
+cudaError_t launch_1d(const Geom1D &g, const Weights1D &w, cudaStream_t s);
+cudaError_t launch_2d(int form, const CUtensorMap &tmap, const Geom2D &g, const Weights2D &w,
+                      const WeightsDirect49 &wd, cudaStream_t s);
+cudaError_t launch_3d(int form, const CUtensorMap &tmap, const Geom3D &g, const Weights3D &w, cudaStream_t s);
+cudaError_t kernels_init();     // opt in to large dynamic shared memory once per process/device
+cudaError_t kernels_init_1d();
+cudaError_t kernels_init_2d();
+cudaError_t kernels_init_3d();
+
+}  // namespace lora

@@ -1,0 +1,512 @@
+// plan.cu -- host side of liblorastencil_b200.so: plans, TMA descriptors, launch geometry, the
+// drop-in host operators and the C ABI declared in include/lorastencil.h.
+//
+// Reference counterparts: the gpu_* host operators
+//   src/1d/gpu_1r.cu:90-137, src/1d/gpu_2r.cu:91-137, src/2d/gpu.cu:276-557,
+//   src/3d/gpu_box.cu:143-226, src/3d/gpu_star.cu:136-195
+// (weight factorisation -> upload -> cudaMalloc x2 -> launch loop -> timing printout -> D2H).
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lorastencil.h"
+#include "../../include/lorastencil_dropin.hpp"
+#include "decompose.h"
+#include "kernels.h"
+
+using namespace lora;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(LORA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *lora_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+// driver entry point for TMA descriptors (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode() {
+    static encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_tiled_fn>(p);
+    });
+    return fn;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct lora_plan {
+    int shape = 0, mode = 0, dim = 0;
+    long long dims[3] = {0, 0, 0};    // interior
+    long long padded[3] = {0, 0, 0};  // with halos
+    long long elems = 0;
+    int form = 0;
+    Weights1D w1{};
+    Weights2D w2{};
+    WeightsDirect49 wd{};
+    Weights3D w3{};
+    std::string desc;
+    std::vector<std::pair<const void *, CUtensorMap>> maps;  // one TMA descriptor per source buffer
+    long long launches = 0;
+    int sm_count = 148;
+    int slots = 148 * 16;  // concurrently resident warp workers (1-D / 2-D) or CTAs (3-D)
+    int device = 0;
+};
+
+static std::once_flag g_init_once;
+static cudaError_t g_init_err = cudaSuccess;
+
+static int ensure_init() {
+    std::call_once(g_init_once, [] { g_init_err = kernels_init(); });
+    if (g_init_err != cudaSuccess)
+        return fail(LORA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(g_init_err));
+    return LORA_OK;
+}
+
+extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const double *params, const long long *dims) {
+    if (!out || !dims) return fail(LORA_ERR_ARG, "null argument");
+    const int dim = shape_dim(shape);
+    if (dim == 0) return fail(LORA_ERR_ARG, "unknown shape %d", shape);
+    if (mode != LORA_WEIGHTS_REFERENCE && mode != LORA_WEIGHTS_GENERAL) return fail(LORA_ERR_ARG, "bad mode %d", mode);
+    for (int i = 0; i < dim; i++)
+        if (dims[i] <= 0 || dims[i] > 0x7fffffffLL - 16) return fail(LORA_ERR_ARG, "bad size %lld", dims[i]);
+    int rc = ensure_init();
+    if (rc) return rc;
+
+    lora_plan *p = new lora_plan;
+    p->shape = shape;
+    p->mode = mode;
+    p->dim = dim;
+    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
+    p->elems = 1;
+    for (int i = 0; i < dim; i++) {
+        p->dims[i] = dims[i];
+        p->padded[i] = dims[i] + 2 * halo[dim][i];
+        p->elems *= p->padded[i];
+    }
+    double table[49];
+    if (!params) {
+        reference_table(shape, table);
+        params = table;
+    }
+    if (dim == 1) {
+        Decomp1D d;
+        decompose_1d(shape, mode, params, d);
+        std::memcpy(p->w1.w, d.w, sizeof d.w);
+        p->form = LORA_FORM_TAPS9;
+        p->desc = "1d 9 direct taps";
+    } else if (dim == 2) {
+        Decomp2D d;
+        decompose_2d(shape, mode, params, d);
+        std::memcpy(p->w2.vert, d.vert, sizeof d.vert);
+        std::memcpy(p->w2.horiz, d.horiz, sizeof d.horiz);
+        p->w2.centre = d.centre;
+        std::memcpy(p->w2.residual, d.residual, sizeof d.residual);
+        std::memcpy(p->wd.w, d.direct, sizeof d.direct);
+        p->form = d.form;
+        p->desc = d.desc;
+    } else {
+        Decomp3D d;
+        decompose_3d(shape, mode, params, d);
+        std::memcpy(p->w3.a, d.a, sizeof d.a);
+        std::memcpy(p->w3.b, d.b, sizeof d.b);
+        std::memcpy(p->w3.c, d.c, sizeof d.c);
+        std::memcpy(p->w3.star, d.star, sizeof d.star);
+        std::memcpy(p->w3.direct, d.direct, sizeof d.direct);
+        p->form = d.form;
+        p->desc = d.desc;
+    }
+    cudaGetDevice(&p->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+    const int warps_per_sm = (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
+    p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
+    *out = p;
+    return LORA_OK;
+}
+
+extern "C" void lora_plan_destroy(lora_plan_t *p) { delete p; }
+extern "C" long long lora_plan_padded_elems(const lora_plan_t *p) { return p ? p->elems : 0; }
+extern "C" long long lora_plan_launch_count(const lora_plan_t *p) { return p ? p->launches : 0; }
+extern "C" const char *lora_plan_describe(const lora_plan_t *p) { return p ? p->desc.c_str() : ""; }
+
+static int get_tmap(lora_plan *p, const double *src, const CUtensorMap **out) {
+    for (auto &kv : p->maps)
+        if (kv.first == src) {
+            *out = &kv.second;
+            return LORA_OK;
+        }
+    encode_tiled_fn enc = get_encode();
+    if (!enc) return fail(LORA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (reinterpret_cast<uintptr_t>(src) % 16) return fail(LORA_ERR_ARG, "source buffer must be 16-byte aligned");
+    CUtensorMap m;
+    CUresult r;
+    if (p->dim == 2) {
+        if (p->padded[1] % 2) return fail(LORA_ERR_UNSUPPORTED, "2-D TMA path needs an even number of columns");
+        cuuint64_t gdim[2] = {(cuuint64_t)p->padded[1], (cuuint64_t)p->padded[0]};
+        cuuint64_t gstr[1] = {(cuuint64_t)p->padded[1] * 8};
+        cuuint32_t box[2] = {(cuuint32_t)kBoxCols, (cuuint32_t)kRowsPerStage};
+        cuuint32_t es[2] = {1, 1};
+        r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(src), gdim, gstr, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        if (p->padded[2] % 2) return fail(LORA_ERR_UNSUPPORTED, "3-D TMA path needs an even number of columns");
+        cuuint64_t gdim[3] = {(cuuint64_t)p->padded[2], (cuuint64_t)p->padded[1], (cuuint64_t)p->padded[0]};
+        cuuint64_t gstr[2] = {(cuuint64_t)p->padded[2] * 8, (cuuint64_t)p->padded[2] * p->padded[1] * 8};
+        cuuint32_t box[3] = {(cuuint32_t)k3BoxCols, (cuuint32_t)k3BoxRows, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(src), gdim, gstr, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(LORA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    if (p->maps.size() >= 8) p->maps.erase(p->maps.begin());
+    p->maps.emplace_back(src, m);
+    *out = &p->maps.back().second;
+    return LORA_OK;
+}
+
+// rows (2-D), 128-element rows (1-D) or planes (3-D) per task: the smallest whole number of
+// "waves" k over `slots` concurrent workers whose tasks stay below `max_len`
+static long long pick_len(long long total, long long lanes, long long slots, long long max_len, long long min_len) {
+    if (total <= min_len) return total;
+    for (long long k = 1; k < 64; k++) {
+        long long q = (k * slots) / lanes;  // tasks along the swept axis
+        if (q < 1) q = 1;
+        long long len = (total + q - 1) / q;
+        if (len <= max_len) return len < min_len ? min_len : len;
+    }
+    return max_len;
+}
+
+extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
+                              void *stream) {
+    if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
+    if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
+    if (lo == hi) return LORA_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (p->dim == 1) {
+        if (lo % 2) return fail(LORA_ERR_ARG, "1-D range must start at an even index");
+        if (reinterpret_cast<uintptr_t>(src) % 16 || reinterpret_cast<uintptr_t>(dst) % 16)
+            return fail(LORA_ERR_ARG, "buffers must be 16-byte aligned");
+        Geom1D g;
+        g.in = src;
+        g.out = dst;
+        g.n = p->dims[0];
+        g.lo = lo;
+        g.hi = hi;
+        const long long rows = (hi - lo + kWarpCols - 1) / kWarpCols;
+        g.rows_per_task = (int)pick_len(rows, 1, p->slots, 256, 16);
+        g.ntasks = (rows + g.rows_per_task - 1) / g.rows_per_task;
+        g.vec4 = (lo % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+        e = launch_1d(g, p->w1, st);
+    } else if (p->dim == 2) {
+        const CUtensorMap *tm;
+        int rc = get_tmap(p, src, &tm);
+        if (rc) return rc;
+        Geom2D g;
+        g.out = dst;
+        g.pitch = p->padded[1];
+        g.m = (int)p->dims[0];
+        g.n = (int)p->dims[1];
+        g.row_lo = (int)lo;
+        g.row_hi = (int)hi;
+        g.nstrips = (g.n + kWarpCols - 1) / kWarpCols;
+        g.rows_per_chunk = (int)pick_len(hi - lo, g.nstrips, p->slots, 256, 32);
+        const int chunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
+        g.ntasks = chunks * g.nstrips;
+        g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+        e = launch_2d(p->form, *tm, g, p->w2, p->wd, st);
+    } else {
+        const CUtensorMap *tm;
+        int rc = get_tmap(p, src, &tm);
+        if (rc) return rc;
+        Geom3D g;
+        g.out = dst;
+        g.row_pitch = p->padded[2];
+        g.plane_pitch = p->padded[1] * p->padded[2];
+        g.h = (int)p->dims[0];
+        g.m = (int)p->dims[1];
+        g.n = (int)p->dims[2];
+        g.h_lo = (int)lo;
+        g.h_hi = (int)hi;
+        g.tiles_m = (g.m + k3TileRows - 1) / k3TileRows;
+        g.tiles_n = (g.n + k3TileCols - 1) / k3TileCols;
+        g.planes_per_chunk = (int)pick_len(hi - lo, (long long)g.tiles_m * g.tiles_n, p->slots, 64, 8);
+        g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+        e = launch_3d(p->form, *tm, g, p->w3, st);
+    }
+    if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    p->launches++;
+    return LORA_OK;
+}
+
+extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int times, void *stream) {
+    if (!p || !buf0 || !buf1) return fail(LORA_ERR_ARG, "null argument");
+    double *buf[2] = {buf0, buf1};
+    for (int i = 0; i < times; i++) {
+        int rc = lora_plan_step(p, buf[i % 2], buf[(i + 1) % 2], 0, p->dims[0], stream);
+        if (rc) return rc;
+    }
+    return LORA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// layer 3
+// ---------------------------------------------------------------------------------------------
+extern "C" int lora_decompose_2d(int shape, int mode, const double *params49, lora_decomp2d_t *out) {
+    if (!params49 || !out) return fail(LORA_ERR_ARG, "null argument");
+    Decomp2D d;
+    if (!decompose_2d(shape, mode, params49, d)) return fail(LORA_ERR_ARG, "shape %d is not 2-D", shape);
+    out->form = d.form;
+    out->nterms = d.nterms;
+    std::memcpy(out->vert, d.vert, sizeof d.vert);
+    std::memcpy(out->horiz, d.horiz, sizeof d.horiz);
+    out->centre = d.centre;
+    std::memcpy(out->residual, d.residual, sizeof d.residual);
+    out->recon_err = d.recon_err;
+    out->macs_per_cell = d.macs;
+    return LORA_OK;
+}
+
+extern "C" int lora_reference_table(int shape, double *table_out) {
+    if (!table_out || shape_dim(shape) == 0) return fail(LORA_ERR_ARG, "bad argument");
+    reference_table(shape, table_out);
+    return LORA_OK;
+}
+
+extern "C" int lora_effective_weights(int shape, int mode, const double *params, double *w) {
+    if (!w) return fail(LORA_ERR_ARG, "null argument");
+    double table[49];
+    if (!params) {
+        if (shape_dim(shape) == 0) return fail(LORA_ERR_ARG, "unknown shape %d", shape);
+        reference_table(shape, table);
+        params = table;
+    }
+    switch (shape_dim(shape)) {
+        case 1: {
+            Decomp1D d;
+            decompose_1d(shape, mode, params, d);
+            std::memcpy(w, d.w, sizeof d.w);
+            return LORA_OK;
+        }
+        case 2: {
+            Decomp2D d;
+            decompose_2d(shape, mode, params, d);
+            std::memcpy(w, d.effective, sizeof d.effective);
+            return LORA_OK;
+        }
+        case 3: {
+            Decomp3D d;
+            decompose_3d(shape, mode, params, d);
+            std::memcpy(w, d.effective, sizeof d.effective);
+            return LORA_OK;
+        }
+        default:
+            return fail(LORA_ERR_ARG, "unknown shape %d", shape);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// layer 1: drop-in host operators
+// ---------------------------------------------------------------------------------------------
+static int g_verbose = -1;
+static double g_loop_ms = 0, g_total_ms = 0;
+static std::mutex g_ws_mutex;
+static double *g_ws[2] = {nullptr, nullptr};
+static size_t g_ws_bytes = 0;
+static int g_ws_device = -1;
+
+extern "C" int lora_set_verbose(int on) {
+    if (g_verbose < 0) {
+        const char *q = getenv("LORA_QUIET");
+        g_verbose = (q && q[0] && q[0] != '0') ? 0 : 1;
+    }
+    int prev = g_verbose;
+    g_verbose = on ? 1 : 0;
+    return prev;
+}
+static bool verbose() {
+    if (g_verbose < 0) {
+        const char *q = getenv("LORA_QUIET");
+        g_verbose = (q && q[0] && q[0] != '0') ? 0 : 1;
+    }
+    return g_verbose != 0;
+}
+
+extern "C" double lora_last_loop_ms(void) { return g_loop_ms; }
+extern "C" double lora_last_total_ms(void) { return g_total_ms; }
+
+extern "C" void lora_release_workspace(void) {
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    for (auto &b : g_ws) {
+        if (b) cudaFree(b);
+        b = nullptr;
+    }
+    g_ws_bytes = 0;
+    g_ws_device = -1;
+}
+
+// the reference's CUDA_CHECK: report and exit(1) (src/2d/2d_utils.h:22-36)
+[[noreturn]] static void die_cuda(cudaError_t e, const char *what, int line) {
+    printf("CUDA Error:\n");
+    printf("    File:       %s\n", __FILE__);
+    printf("    Line:       %d\n", line);
+    printf("    Error code: %d\n", (int)e);
+    printf("    Error text: %s (%s)\n", cudaGetErrorString(e), what);
+    fflush(stdout);
+    exit(1);
+}
+#define CU_DIE(call)                                          \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) die_cuda(e__, #call, __LINE__); \
+    } while (0)
+
+[[noreturn]] static void die_plan(const char *what) {
+    printf("LoRAStencil error: %s: %s\n", what, lora_last_error());
+    fflush(stdout);
+    exit(1);
+}
+
+extern "C" void lora_gpu_run_host(int shape, int mode, const double *in, double *out, const double *params, int times,
+                                  const long long *dims) {
+    using clk = std::chrono::steady_clock;
+    const clk::time_point t_begin = clk::now();
+    lora_plan *p = nullptr;
+    if (lora_plan_create(&p, shape, mode, params, dims) != LORA_OK) die_plan("plan");
+    const size_t bytes = (size_t)p->elems * sizeof(double);
+
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    int dev = 0;
+    CU_DIE(cudaGetDevice(&dev));
+    if (g_ws_bytes < bytes || g_ws_device != dev) {
+        for (auto &b : g_ws) {
+            if (b) cudaFree(b);
+            b = nullptr;
+        }
+        CU_DIE(cudaMalloc(&g_ws[0], bytes));
+        CU_DIE(cudaMalloc(&g_ws[1], bytes));
+        g_ws_bytes = bytes;
+        g_ws_device = dev;
+    }
+    // S2: buffer 0 <- the whole padded input (halo included), buffer 1 <- zeros (src/2d/gpu.cu:396-400)
+    CU_DIE(cudaMemcpy(g_ws[0], in, bytes, cudaMemcpyHostToDevice));
+    CU_DIE(cudaMemset(g_ws[1], 0, bytes));
+    CU_DIE(cudaDeviceSynchronize());
+
+    // timed region of the reference: launch loop + device sync (src/2d/gpu.cu:408-414)
+    const clk::time_point t0 = clk::now();
+    if (lora_plan_run(p, g_ws[0], g_ws[1], times, nullptr) != LORA_OK) die_plan("launch");
+    CU_DIE(cudaDeviceSynchronize());
+    const clk::time_point t1 = clk::now();
+    const long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    g_loop_ms = us / 1e3;
+    if (verbose()) {
+        double cells = 1;
+        for (int i = 0; i < p->dim; i++) cells *= (double)p->dims[i];
+        printf("LoRAStencil(%s): \n", shape_banner(shape));
+        printf("Time = %lld[ms]\n", (long long)std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count());
+        printf("GStencil/s = %f\n", cells * times * shape_artifact_k(shape) / (us / 1e6) / 1e9);
+        fflush(stdout);
+    }
+    // S3: the whole padded buffer times%2 comes back; 1-D leaves the last double alone (src/1d/gpu_1r.cu:134)
+    const size_t back = (p->dim == 1) ? bytes - sizeof(double) : bytes;
+    CU_DIE(cudaMemcpy(out, g_ws[times % 2 == 0 ? 0 : 1], back, cudaMemcpyDeviceToHost));
+    lora_plan_destroy(p);
+    g_total_ms = std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t_begin).count() / 1e3;
+}
+
+extern "C" void lora_gpu_1d1r(const double *in, double *out, const double *params, int times, int n) {
+    const long long d[1] = {n};
+    lora_gpu_run_host(LORA_1D1R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+extern "C" void lora_gpu_1d2r(const double *in, double *out, const double *params, int times, int n) {
+    const long long d[1] = {n};
+    lora_gpu_run_host(LORA_1D2R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+extern "C" void lora_gpu_star_2d1r(const double *in, double *out, const double *params, int times, int m, int n) {
+    const long long d[2] = {m, n};
+    lora_gpu_run_host(LORA_STAR2D1R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+extern "C" void lora_gpu_star_2d3r(const double *in, double *out, const double *params, int times, int m, int n) {
+    const long long d[2] = {m, n};
+    lora_gpu_run_host(LORA_STAR2D3R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+extern "C" void lora_gpu_box_2d3r(const double *in, double *out, const double *params, int times, int m, int n) {
+    const long long d[2] = {m, n};
+    lora_gpu_run_host(LORA_BOX2D3R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+extern "C" void lora_gpu_box_3d1r(const double *in, double *out, const double *params, int times, int h, int m, int n) {
+    const long long d[3] = {h, m, n};
+    lora_gpu_run_host(LORA_BOX3D1R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+extern "C" void lora_gpu_star_3d1r(const double *in, double *out, const double *params, int times, int h, int m, int n) {
+    const long long d[3] = {h, m, n};
+    lora_gpu_run_host(LORA_STAR3D1R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+
+// the reference's own C++ symbols (include/lorastencil_dropin.hpp)
+void gpu_1d1r(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ params,
+              const int time, const int input_n) {
+    lora_gpu_1d1r(in, out, params, time, input_n);
+}
+void gpu_1d2r(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ params,
+              const int time, const int input_n) {
+    lora_gpu_1d2r(in, out, params, time, input_n);
+}
+void gpu_star_2d1r(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ params,
+                   const int times, const int input_m, const int input_n) {
+    lora_gpu_star_2d1r(in, out, params, times, input_m, input_n);
+}
+void gpu_star_2d3r(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ params,
+                   const int times, const int input_m, const int input_n) {
+    lora_gpu_star_2d3r(in, out, params, times, input_m, input_n);
+}
+void gpu_box_2d3r(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ params,
+                  const int times, const int input_m, const int input_n) {
+    lora_gpu_box_2d3r(in, out, params, times, input_m, input_n);
+}
+void gpu_box_3d1r(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ params,
+                  const int times, const int input_h, const int input_m, const int input_n) {
+    lora_gpu_box_3d1r(in, out, params, times, input_h, input_m, input_n);
+}
+void gpu_star_3d1r(const double *__restrict__ in, double *__restrict__ out, const double *__restrict__ params,
+                   const int times, const int input_h, const int input_m, const int input_n) {
+    lora_gpu_star_3d1r(in, out, params, times, input_h, input_m, input_n);
+}

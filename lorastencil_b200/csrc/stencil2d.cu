@@ -1,0 +1,243 @@
+// stencil2d.cu -- 2-D low-rank stencil kernels for sm_100a.
+//
+// Replaces kernel2d_box2d3r / kernel2d_star2d3r / kernel2d_star2d1r of the reference
+// (src/2d/gpu.cu:31-273).  Same mathematics -- the 7x7 table applied as a sum of rank-1 terms
+// (vertical profile (x) horizontal profile), a cross, or one rank-1 term + residual taps -- but a
+// different machine mapping:
+//
+//   * every warp is an independent worker: it owns a strip of 128 columns and sweeps a chunk of rows
+//     top to bottom.  Lane l owns 4 consecutive columns.
+//   * input rows reach shared memory through the warp's private TMA ring (cp.async.bulk.tensor.2d,
+//     boxes of 136 columns x 4 rows, 3 stages, one mbarrier per stage); no CTA-wide barrier exists.
+//   * per input row a lane reads its 12-double window with six 128-bit LDS, forms the horizontal
+//     profile sums h_t (FP64 FMA, weights straight from the constant bank) and PUSHES u_t[dr] * h_t
+//     into seven per-column register accumulators (one per pending output row).  The oldest
+//     accumulator is complete after every row and leaves with one 256-bit store.  The accumulator
+//     ring is rotated by unrolling the row loop 7x, so no register moves are issued.
+//
+// MACs per cell: pyramid 31, cross 13, diamond 18, direct 49 (reference: 108 / 32 / 36+8 DMMA MACs).
+// FP64 DMMA (mma.sync m8n8k4, the only FP64 tensor shape on sm_100a) is not used here: the operands
+// are banded Toeplitz matrices (<= 7/16 dense), so the tensor pipe would spend >2x the FP64 work of
+// the FMA form; see DESIGN.md and profiles/ for the measured pipe rates.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/lorastencil.h"
+
+namespace lora {
+
+namespace {
+
+constexpr int NACC = 7;
+
+// x[4 + q + dc] is the input at (own column q) + dc; accumulator (3 - dr + PH) % 7 belongs to the
+// output row that sees this input row at row offset dr.
+template <int FORM, int PH>
+__device__ __forceinline__ void push_row(const double (&x)[12], double (&A)[NACC][4], const Weights2D &w,
+                                         const WeightsDirect49 &wd) {
+#define ACC(dr) A[((3 - (dr)) + PH) % NACC]
+    if constexpr (FORM == LORA_FORM_PYRAMID) {
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int rad = 3 - t;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double h = w.horiz[t][3 - rad] * x[4 + q - rad];
+#pragma unroll
+                for (int dc = -rad + 1; dc <= rad; dc++) h = fma(w.horiz[t][3 + dc], x[4 + q + dc], h);
+#pragma unroll
+                for (int dr = -rad; dr <= rad; dr++) ACC(dr)[q] = fma(w.vert[t][3 + dr], h, ACC(dr)[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) ACC(0)[q] = fma(w.centre, x[4 + q], ACC(0)[q]);
+    } else if constexpr (FORM == LORA_FORM_CROSS) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int dr = -3; dr <= 3; dr++) ACC(dr)[q] = fma(w.vert[0][3 + dr], x[4 + q], ACC(dr)[q]);
+            double h = w.horiz[1][0] * x[4 + q - 3];
+#pragma unroll
+            for (int dc = -2; dc <= 3; dc++)
+                if (dc != 0) h = fma(w.horiz[1][3 + dc], x[4 + q + dc], h);
+            ACC(0)[q] += h;
+        }
+    } else if constexpr (FORM == LORA_FORM_DIAMOND) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double h = w.horiz[0][1] * x[4 + q - 2];
+#pragma unroll
+            for (int dc = -1; dc <= 2; dc++) h = fma(w.horiz[0][3 + dc], x[4 + q + dc], h);
+#pragma unroll
+            for (int dr = -2; dr <= 2; dr++) ACC(dr)[q] = fma(w.vert[0][3 + dr], h, ACC(dr)[q]);
+            ACC(0)[q] = fma(w.residual[0], x[4 + q - 3], ACC(0)[q]);
+            ACC(0)[q] = fma(w.residual[1], x[4 + q + 3], ACC(0)[q]);
+            ACC(-3)[q] = fma(w.residual[2], x[4 + q], ACC(-3)[q]);
+            ACC(3)[q] = fma(w.residual[3], x[4 + q], ACC(3)[q]);
+            ACC(-2)[q] = fma(w.residual[4], x[4 + q - 2], ACC(-2)[q]);
+            ACC(-2)[q] = fma(w.residual[5], x[4 + q + 2], ACC(-2)[q]);
+            ACC(2)[q] = fma(w.residual[6], x[4 + q - 2], ACC(2)[q]);
+            ACC(2)[q] = fma(w.residual[7], x[4 + q + 2], ACC(2)[q]);
+        }
+    } else {  // DIRECT49
+#pragma unroll
+        for (int dr = -3; dr <= 3; dr++)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int dc = -3; dc <= 3; dc++)
+                    ACC(dr)[q] = fma(wd.w[(dr + 3) * 7 + dc + 3], x[4 + q + dc], ACC(dr)[q]);
+    }
+#undef ACC
+}
+
+struct Sweep2D {
+    const CUtensorMap *tmap;
+    double *ring;
+    uint64_t *bars;
+    double *orow;  // next output row, this lane's first column
+    long long pitch;
+    int nin, nst, boxcol, row0_padded, lane, ncols_left;  // ncols_left = n - c0 (how many of the 4 columns exist)
+    bool vec4;
+};
+
+// one input row: wait for its stage if it opens one, read the window, push, retire the oldest
+// accumulator, refill the ring if the row closes a stage
+template <int FORM, int PH>
+__device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4], const Weights2D &w,
+                                          const WeightsDirect49 &wd) {
+    const int st = i / kRowsPerStage, rr = i % kRowsPerStage, slot = st % kStages;
+    if (rr == 0) mbar_wait(&s.bars[slot], (st / kStages) & 1);
+    const double2 *rowp = reinterpret_cast<const double2 *>(s.ring + slot * kStageElems + rr * kBoxCols + 4 * s.lane);
+    double x[12];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const double2 v = rowp[k];
+        x[2 * k] = v.x;
+        x[2 * k + 1] = v.y;
+    }
+    push_row<FORM, PH>(x, A, w, wd);
+
+    double(&done)[4] = A[PH % NACC];  // logical accumulator 0: output row i - 6 of the chunk
+    if (i >= 6) {
+        if (s.ncols_left >= 4) {
+            if (s.vec4) {
+                st_global_v4(s.orow, done[0], done[1], done[2], done[3]);
+            } else {
+                st_global_v2(s.orow, done[0], done[1]);
+                st_global_v2(s.orow + 2, done[2], done[3]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (q < s.ncols_left) s.orow[q] = done[q];
+        }
+        s.orow += s.pitch;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) done[q] = 0.0;  // becomes logical accumulator 6 of the next row
+
+    if (rr == kRowsPerStage - 1 || i == s.nin - 1) {
+        __syncwarp();  // every lane has consumed this stage
+        if (s.lane == 0 && st + kStages < s.nst) {
+            mbar_arrive_expect_tx(&s.bars[slot], kStageElems * 8);
+            tma_load_2d(s.ring + slot * kStageElems, s.tmap, s.boxcol, s.row0_padded + (st + kStages) * kRowsPerStage,
+                        &s.bars[slot]);
+        }
+    }
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (FORM == LORA_FORM_PYRAMID || FORM == LORA_FORM_DIRECT49) ? 3 : 4)
+k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2D g,
+            const __grid_constant__ Weights2D w, const __grid_constant__ WeightsDirect49 wd) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task = blockIdx.x * kWarpsPerCta + warp;
+    if (task >= g.ntasks) return;  // warps never synchronise with each other
+
+    const int strip = task % g.nstrips, chunk = task / g.nstrips;
+    const int r0 = g.row_lo + chunk * g.rows_per_chunk;  // first interior row of this chunk
+    const int R = min(g.rows_per_chunk, g.row_hi - r0);
+    const int c0 = strip * kWarpCols + 4 * lane;         // first interior column of this lane
+
+    Sweep2D s;
+    s.tmap = &tmap;
+    s.ring = reinterpret_cast<double *>(smem_raw) + warp * (kStages * kStageElems);
+    s.bars = reinterpret_cast<uint64_t *>(smem_raw + kWarpsPerCta * kStages * kStageElems * 8) + warp * kStages;
+    s.nin = R + 6;  // input rows r0-3 .. r0+R+2  ==  padded rows r0+1 .. r0+R+6
+    s.nst = (s.nin + kRowsPerStage - 1) / kRowsPerStage;
+    s.boxcol = strip * kWarpCols;  // padded column of the box origin = interior column - 4
+    s.row0_padded = r0 + 1;
+    s.lane = lane;
+    s.ncols_left = g.n - c0;
+    s.vec4 = g.vec4 != 0;
+    s.pitch = g.pitch;
+    s.orow = g.out + (long long)(r0 + 4) * g.pitch + 4 + c0;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kStages; k++) mbar_init(&s.bars[k], 1);
+        fence_barrier_init();
+#pragma unroll
+        for (int k = 0; k < kStages; k++)
+            if (k < s.nst) {
+                mbar_arrive_expect_tx(&s.bars[k], kStageElems * 8);
+                tma_load_2d(s.ring + k * kStageElems, &tmap, s.boxcol, s.row0_padded + k * kRowsPerStage, &s.bars[k]);
+            }
+    }
+    __syncwarp();
+
+    double A[NACC][4];
+#pragma unroll
+    for (int j = 0; j < NACC; j++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) A[j][q] = 0.0;
+
+    for (int base = 0; base < s.nin; base += NACC) {
+        if (base + 0 < s.nin) row_phase<FORM, 0>(base + 0, s, A, w, wd);
+        if (base + 1 < s.nin) row_phase<FORM, 1>(base + 1, s, A, w, wd);
+        if (base + 2 < s.nin) row_phase<FORM, 2>(base + 2, s, A, w, wd);
+        if (base + 3 < s.nin) row_phase<FORM, 3>(base + 3, s, A, w, wd);
+        if (base + 4 < s.nin) row_phase<FORM, 4>(base + 4, s, A, w, wd);
+        if (base + 5 < s.nin) row_phase<FORM, 5>(base + 5, s, A, w, wd);
+        if (base + 6 < s.nin) row_phase<FORM, 6>(base + 6, s, A, w, wd);
+    }
+}
+
+template <int FORM>
+cudaError_t launch_form(const CUtensorMap &tmap, const Geom2D &g, const Weights2D &w, const WeightsDirect49 &wd,
+                        cudaStream_t st) {
+    if (g.ntasks <= 0) return cudaSuccess;
+    const int ctas = (g.ntasks + kWarpsPerCta - 1) / kWarpsPerCta;
+    k_stencil2d<FORM><<<ctas, 32 * kWarpsPerCta, kSmem12, st>>>(tmap, g, w, wd);
+    return cudaGetLastError();
+}
+
+template <int FORM>
+cudaError_t opt_in() {
+    return cudaFuncSetAttribute(k_stencil2d<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem12);
+}
+
+}  // namespace
+
+cudaError_t kernels_init_2d() {
+    cudaError_t e;
+    if ((e = opt_in<LORA_FORM_PYRAMID>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_CROSS>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_DIAMOND>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_DIRECT49>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_2d(int form, const CUtensorMap &tmap, const Geom2D &g, const Weights2D &w,
+                      const WeightsDirect49 &wd, cudaStream_t s) {
+    switch (form) {
+        case LORA_FORM_PYRAMID: return launch_form<LORA_FORM_PYRAMID>(tmap, g, w, wd, s);
+        case LORA_FORM_CROSS: return launch_form<LORA_FORM_CROSS>(tmap, g, w, wd, s);
+        case LORA_FORM_DIAMOND: return launch_form<LORA_FORM_DIAMOND>(tmap, g, w, wd, s);
+        case LORA_FORM_DIRECT49: return launch_form<LORA_FORM_DIRECT49>(tmap, g, w, wd, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace lora

@@ -1,0 +1,115 @@
+"""Device-resident plans (layer 2 of include/lorastencil.h) on torch CUDA tensors."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_longlong, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+HALO = {1: (4,), 2: (4, 4), 3: (1, 2, 4)}  # S1: src/1d/main.cu:96, src/2d/main.cu:217-218, src/3d/main.cu:21-23
+FORM_NAMES = {0: "taps9", 1: "cross", 2: "pyramid", 3: "diamond", 4: "direct49", 5: "sep3", 6: "star7", 7: "direct27"}
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(POINTER(c_double))
+
+
+def reference_table(shape: str) -> np.ndarray:
+    """The weight table the reference CLI passes for ``shape``."""
+    sid = _lib.SHAPE_IDS[shape]
+    n = 9 if sid < 2 else (49 if sid < 6 else 27)
+    out = np.zeros(n, dtype=np.float64)
+    _lib.check(_lib.lib().lora_reference_table(sid, _dp(out)), "lora_reference_table")
+    return out
+
+
+def effective_weights(shape: str, mode: int = _lib.WEIGHTS_REFERENCE, params=None) -> np.ndarray:
+    """Direct-tap weights a plan built from (shape, mode, params) applies."""
+    sid = _lib.SHAPE_IDS[shape]
+    n = 9 if sid < 2 else (49 if sid < 6 else 27)
+    out = np.zeros(n, dtype=np.float64)
+    p = None if params is None else np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
+    _lib.check(_lib.lib().lora_effective_weights(sid, int(mode), None if p is None else _dp(p), _dp(out)),
+               "lora_effective_weights")
+    return out
+
+
+def decompose_2d(shape: str, params, mode: int = _lib.WEIGHTS_GENERAL) -> dict:
+    """Host low-rank decomposition of a 7x7 table (layer 3)."""
+    d = _lib.Decomp2D()
+    p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
+    _lib.check(_lib.lib().lora_decompose_2d(_lib.SHAPE_IDS[shape], int(mode), _dp(p), byref(d)), "lora_decompose_2d")
+    return {"form": FORM_NAMES[d.form], "nterms": d.nterms,
+            "vert": np.array([[d.vert[t][k] for k in range(7)] for t in range(3)]),
+            "horiz": np.array([[d.horiz[t][k] for k in range(7)] for t in range(3)]),
+            "centre": d.centre, "residual": np.array(list(d.residual)), "recon_err": d.recon_err,
+            "macs_per_cell": d.macs_per_cell}
+
+
+class Plan:
+    """A device-resident stencil plan: weights factored on the host once, launches on CUDA tensors.
+
+    ``dims`` are the interior sizes of the grid this device holds.  Buffers are float64 CUDA tensors
+    with the padded shape ``padded_shape`` (allocate with ``new_buffer``)."""
+
+    def __init__(self, shape: str, dims, params=None, mode: int = _lib.WEIGHTS_REFERENCE):
+        self.shape = shape
+        self.dims = tuple(int(d) for d in dims)
+        self.dim = len(self.dims)
+        self.padded_shape = tuple(d + 2 * h for d, h in zip(self.dims, HALO[self.dim]))
+        self._h = c_void_p()
+        p = None if params is None else np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
+        d = (c_longlong * 3)(*self.dims, *([0] * (3 - self.dim)))
+        _lib.check(_lib.lib().lora_plan_create(byref(self._h), _lib.SHAPE_IDS[shape], int(mode),
+                                               None if p is None else _dp(p), d), "lora_plan_create")
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().lora_plan_destroy(self._h)
+                self._h = c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def describe(self) -> str:
+        return _lib.lib().lora_plan_describe(self._h).decode()
+
+    @property
+    def launches(self) -> int:
+        return int(_lib.lib().lora_plan_launch_count(self._h))
+
+    @property
+    def cells(self) -> int:
+        return int(np.prod(self.dims))
+
+    def new_buffer(self, device="cuda", zero: bool = True):
+        import torch
+        return (torch.zeros if zero else torch.empty)(self.padded_shape, dtype=torch.float64, device=device)
+
+    def _check_buf(self, t):
+        if not t.is_cuda or t.dtype.__str__() != "torch.float64" or not t.is_contiguous() or \
+                tuple(t.shape) != self.padded_shape:
+            raise TypeError(f"expected a contiguous float64 CUDA tensor of shape {self.padded_shape}")
+
+    def step(self, src, dst, lo: int = 0, hi: int | None = None, stream=None):
+        """One launch: dst[interior, outermost index in [lo, hi)] = stencil(src).  Asynchronous."""
+        import torch
+        self._check_buf(src)
+        self._check_buf(dst)
+        hi = self.dims[0] if hi is None else hi
+        s = torch.cuda.current_stream(src.device) if stream is None else stream
+        _lib.check(_lib.lib().lora_plan_step(self._h, c_void_p(src.data_ptr()), c_void_p(dst.data_ptr()), int(lo), int(hi),
+                                             c_void_p(s.cuda_stream)), "lora_plan_step")
+
+    def run(self, buf0, buf1, times: int, stream=None):
+        """``times`` launches, launch i reads buf[i%2]; returns the tensor holding the result."""
+        import torch
+        self._check_buf(buf0)
+        self._check_buf(buf1)
+        s = torch.cuda.current_stream(buf0.device) if stream is None else stream
+        _lib.check(_lib.lib().lora_plan_run(self._h, c_void_p(buf0.data_ptr()), c_void_p(buf1.data_ptr()), int(times),
+                                            c_void_p(s.cuda_stream)), "lora_plan_run")
+        return buf0 if times % 2 == 0 else buf1

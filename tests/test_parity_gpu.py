@@ -1,0 +1,203 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bar: bit-exact (==) while every intermediate stays an exact integer below 2^53 (integer inputs and
+weights, the first few launches); afterwards max relative error <= 1e-12 (BASELINE.json north_star).
+The oracle is fed `effective_weights` = the weights the reference GPU operator applies."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import lorastencil_b200 as ls
+import oracle
+from lorastencil_b200 import ops
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "single_step.json")))
+RTOL = 1e-12  # north_star: max relative error <= 1e-12 for FP64
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _quiet():
+    prev = ops.set_verbose(False)
+    yield
+    ops.set_verbose(prev)
+
+
+def interior(shape, dims):
+    halo = oracle.HALO[oracle.dim_of(shape)]
+    return tuple(slice(h, h + x) for h, x in zip(halo, dims))
+
+
+def max_rel_err(got, ref):
+    scale = np.abs(ref).max()
+    return 0.0 if scale == 0 else float(np.abs(got - ref).max() / scale)
+
+
+def run_dropin(shape, a, params, times, dims, fill=-7.0):
+    out = np.full_like(a, fill)
+    ops.BY_SHAPE[shape](a, out, params, times, *dims)
+    return out
+
+
+@pytest.mark.parametrize("g", GOLDEN, ids=lambda g: f"{g['shape']}-{'x'.join(map(str, g['dims']))}")
+def test_golden_single_step(g):
+    """One launch on the reference's own input reproduces the reference test_cpu golden values."""
+    shape, dims = g["shape"], tuple(g["dims"])
+    a = oracle.fill_rand(shape, dims)
+    out = run_dropin(shape, a, oracle.reference_params(shape), 1, dims)
+    inner = np.ascontiguousarray(out[interior(shape, dims)])
+    assert float(inner.sum()) == g["interior_sum"]
+    assert hashlib.sha256(inner.tobytes()).hexdigest() == g["interior_sha256"]
+
+
+CASES = [
+    ("1d1r", (1024,)), ("1d2r", (1024,)), ("1d2r", (130,)), ("1d1r", (7,)), ("1d2r", (100003,)), ("1d2r", (1 << 20,)),
+    ("box2d1r", (64, 64)), ("box2d3r", (32, 64)), ("box2d3r", (50, 70)), ("box2d1r", (1, 2)), ("box2d3r", (300, 258)),
+    ("star2d3r", (64, 64)), ("star2d3r", (33, 130)), ("star2d1r", (64, 64)), ("star2d1r", (40, 36)),
+    ("box2d1r", (1024, 1024)),
+    ("box3d1r", (16, 16, 64)), ("box3d1r", (5, 9, 30)), ("box3d1r", (70, 40, 136)), ("box3d1r", (1, 1, 2)),
+    ("star3d1r", (16, 16, 64)), ("star3d1r", (7, 33, 132)), ("star3d1r", (64, 64, 64)),
+]
+
+
+@pytest.mark.parametrize("shape,dims", CASES, ids=lambda v: v if isinstance(v, str) else "x".join(map(str, v)))
+def test_multi_step_bit_exact_then_1e12(shape, dims):
+    """S1-S4 over several launches, full padded output (halo alternation included)."""
+    a = oracle.fill_rand(shape, dims)
+    p = oracle.reference_params(shape)
+    eff = ls.effective_weights(shape, ls.WEIGHTS_REFERENCE, p)
+    assert np.array_equal(eff, oracle.effective_params(shape, p))
+    exact_upto = {"1d1r": 8, "1d2r": 8, "box2d1r": 5, "box2d3r": 5, "star2d1r": 6, "star2d3r": 9,
+                  "box3d1r": 8, "star3d1r": 15}[shape]
+    for times in (0, 1, 2, 3, 4, 10):
+        out = run_dropin(shape, a, p, times, dims)
+        ref = np.full_like(a, -7.0)
+        oracle.run(shape, a, eff, times, out=ref)
+        if times <= exact_upto:
+            assert np.array_equal(out, ref), (shape, dims, times)
+        else:
+            assert max_rel_err(out, ref) <= RTOL, (shape, dims, times)
+        if oracle.dim_of(shape) == 1:
+            assert out[-1] == -7.0  # S3: 1-D copies back cols-1 doubles
+
+
+@pytest.mark.parametrize("shape,dims", [("1d2r", (4096,)), ("box2d3r", (96, 128)), ("star2d3r", (64, 192)),
+                                        ("star2d1r", (64, 64)), ("box3d1r", (12, 32, 128)), ("star3d1r", (9, 40, 64))])
+def test_float_data_long_run_relative_error(shape, dims):
+    """Non-integer data, 40 launches (values grow by the weight sum each launch): <= 1e-12 relative."""
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-1, 1, oracle.padded_shape(shape, dims))
+    p = oracle.reference_params(shape)
+    eff = oracle.effective_params(shape, p)
+    for times in (1, 7, 40):
+        out = run_dropin(shape, a, p, times, dims, fill=0.0)
+        ref = oracle.run(shape, a, eff, times)
+        assert max_rel_err(out, ref) <= RTOL, (shape, times, max_rel_err(out, ref))
+
+
+def test_general_mode_honours_every_weight():
+    """LORA_WEIGHTS_GENERAL == the reference's test_cpu for arbitrary tables: pyramid with a centre
+    remainder, asymmetric pyramid, full-rank (direct taps), general cross / diamond, 3-D forms."""
+    rng = np.random.default_rng(13)
+    dims2, dims3 = (70, 200), (9, 40, 136)
+    a2 = rng.uniform(-1, 1, oracle.padded_shape("box2d3r", dims2))
+    a3 = rng.uniform(-1, 1, oracle.padded_shape("box3d1r", dims3))
+    tables2 = []
+    W = np.zeros((7, 7))
+    for t in range(3):
+        u, v = np.zeros(7), np.zeros(7)
+        u[t:7 - t] = rng.uniform(0.5, 1.5, 7 - 2 * t)
+        v[t:7 - t] = rng.uniform(0.5, 1.5, 7 - 2 * t)
+        W += np.outer(u, v)
+    W[3, 3] += 0.37
+    tables2.append(("pyramid", W.ravel()))
+    tables2.append(("direct49", rng.standard_normal(49)))
+    cross = np.zeros((7, 7))
+    cross[:, 3] = rng.standard_normal(7)
+    cross[3, :] = rng.standard_normal(7)
+    tables2.append(("cross", cross.ravel()))
+    dia = oracle.reference_params("star2d1r").reshape(7, 7).copy()
+    dia[3, 0] = 0.25
+    dia[1, 1] = -3.0
+    tables2.append(("diamond", dia.ravel()))
+    for form, w in tables2:
+        assert ls.decompose_2d("box2d3r", w)["form"] == form
+        out = np.zeros_like(a2)
+        ops.run_host("box2d3r", a2, out, w, 3, dims2, mode=ls.WEIGHTS_GENERAL)
+        assert max_rel_err(out, oracle.run(2, a2, w, 3)) <= RTOL, form
+    tables3 = [np.einsum("i,j,k->ijk", *[rng.uniform(0.5, 1.5, 3) for _ in range(3)]).ravel(), rng.standard_normal(27)]
+    st = np.zeros(27)
+    st[[13, 12, 14, 10, 16, 4, 22]] = rng.standard_normal(7)
+    tables3.append(st)
+    for w in tables3:
+        out = np.zeros_like(a3)
+        ops.run_host("box3d1r", a3, out, w, 3, dims3, mode=ls.WEIGHTS_GENERAL)
+        assert max_rel_err(out, oracle.run(3, a3, w, 3)) <= RTOL
+    w1 = rng.standard_normal(9)
+    a1 = rng.uniform(-1, 1, (5000 + 8,))
+    out = np.zeros_like(a1)
+    ops.run_host("1d2r", a1, out, w1, 5, (5000,), mode=ls.WEIGHTS_GENERAL)
+    assert max_rel_err(out[:-1], oracle.run(1, a1, w1, 5)[:-1]) <= RTOL
+
+
+def test_plan_api_partial_ranges_and_device_buffers():
+    """Layer 2: launches over sub-ranges of the outermost axis compose to the full step, halo cells of
+    the destination are left alone, and the result of `run` sits in buf[times % 2]."""
+    import torch
+    for shape, dims, cuts in (("1d2r", (8192,), (0, 1024, 5000, 8192)), ("box2d3r", (100, 256), (0, 3, 64, 100)),
+                              ("star2d1r", (64, 128), (0, 32, 64)), ("box3d1r", (20, 32, 128), (0, 1, 9, 20)),
+                              ("star3d1r", (10, 33, 64), (0, 5, 10))):
+        a = oracle.fill_rand(shape, dims)
+        plan = ls.Plan(shape, dims)
+        src = torch.from_numpy(a).cuda()
+        dst = torch.full(plan.padded_shape, -3.0, dtype=torch.float64, device="cuda")
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            plan.step(src, dst, lo, hi)
+        torch.cuda.synchronize()
+        ref = np.full_like(a, -3.0)
+        inner = interior(shape, dims)
+        ref[inner] = oracle.step(shape, a, oracle.effective_params(shape))[inner]
+        assert np.array_equal(dst.cpu().numpy(), ref), shape
+        b0, b1 = torch.from_numpy(a).cuda(), plan.new_buffer()
+        res = plan.run(b0, b1, 3)
+        torch.cuda.synchronize()
+        assert res is b1
+        full = oracle.run(shape, a, oracle.effective_params(shape), 3)
+        got = res.cpu().numpy()
+        if oracle.dim_of(shape) == 1:
+            assert np.array_equal(got[:-1], full[:-1])
+        else:
+            assert np.array_equal(got, full)
+        assert plan.launches == len(cuts) - 1 + 3
+
+
+def test_linearity_and_shift_invariance_at_scale():
+    """Size-independent properties at a BASELINE-sized grid (box2d3r 10240 x 10240 would need minutes of
+    oracle time): stencil(a + 2b) == stencil(a) + 2 stencil(b) exactly for integer data, and a grid of
+    ones maps to the weight sum everywhere away from the zero halo."""
+    import torch
+    shape, dims = "box2d3r", (2048, 10240)
+    plan = ls.Plan(shape, dims)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(0, 100, plan.padded_shape, generator=g, device="cuda").double()
+    b = torch.randint(0, 100, plan.padded_shape, generator=g, device="cuda").double()
+    outs = []
+    for x in (a, b, a + 2 * b):
+        o = plan.new_buffer()
+        plan.step(x, o)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[2], outs[0] + 2 * outs[1])
+    ones = torch.ones(plan.padded_shape, dtype=torch.float64, device="cuda")
+    o = plan.new_buffer()
+    plan.step(ones, o)
+    torch.cuda.synchronize()
+    assert torch.all(o[4:-4, 4:-4] == float(oracle.reference_params(shape).sum()))
+    # spot-check rows of the big grid against the oracle on a slab cut out of it
+    r0 = 1000
+    slab = a[r0:r0 + 8 + 16].cpu().numpy()
+    ref = oracle.step(2, np.ascontiguousarray(slab), oracle.effective_params(shape))
+    assert np.array_equal(outs[0][r0 + 4:r0 + 4 + 16].cpu().numpy()[:, 4:-4], ref[4:-4, 4:-4])
