@@ -316,7 +316,9 @@ def main():
                 ops.gpu_1d2r(hin, hout, params, times, n)
             torch.cuda.synchronize()
             el = time.perf_counter() - t0
+            e2e_detail = {"launch_loop_ms_last_call": ops.last_loop_ms(), "whole_call_ms_last_call": ops.last_total_ms()}
         else:
+            e2e_detail = {}
             def e2e_step():
                 runner.buf[0].copy_(hin, non_blocking=True)
                 runner.buf[1].zero_()
@@ -338,7 +340,7 @@ def main():
                "h2d_bytes_per_step": (n + 8) * 8 * world, "d2h_bytes_per_step": (n + 7) * 8 * world,
                "steps": k_e2e, "ms_per_step": el / k_e2e * 1e3,
                "api": "lorastencil_b200.ops.gpu_1d2r -> lora_gpu_1d2r (C ABI), pinned host buffers" if world == 1 else
-                      "pinned host slab -> SlabRunner.run -> pinned host slab"}
+                      "pinned host slab -> SlabRunner.run -> pinned host slab", **e2e_detail}
         del hin, hout
 
     if rank != 0:

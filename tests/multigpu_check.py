@@ -1,0 +1,56 @@
+"""Multi-GPU parity check, run under torchrun with one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py
+
+Every rank runs its slab through lorastencil_b200.slab.SlabRunner (CUDA kernels + NCCL halo exchange);
+rank 0 additionally runs the whole grid on its own GPU with a plain Plan and compares BITWISE.
+Exit code 0 = all cases identical."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import lorastencil_b200 as ls  # noqa: E402
+from lorastencil_b200.slab import SlabRunner  # noqa: E402
+
+CASES = [("1d2r", (1 << 20,), 7), ("1d1r", (100000,), 4), ("box2d1r", (512, 640), 6), ("star2d3r", (300, 258), 5),
+         ("star2d1r", (256, 256), 5), ("box3d1r", (64, 64, 128), 5), ("star3d1r", (33, 40, 136), 4)]
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    bad = 0
+    for shape, dims, times in CASES:
+        runner = SlabRunner(shape, dims, device=dev)
+        rng = np.random.default_rng(42)
+        d = len(dims)
+        padded = tuple(x + 2 * h for x, h in zip(dims, ls.plan.HALO[d]))
+        a = rng.integers(0, 100, size=padded).astype(np.float64)
+        runner.load_global(a)
+        runner.run(times)
+        torch.cuda.synchronize()
+        got = runner.gather_global(a.shape)
+        if rank == 0:
+            plan = ls.Plan(shape, dims)
+            b0, b1 = torch.from_numpy(a).to(dev), plan.new_buffer(dev)
+            ref = plan.run(b0, b1, times).cpu().numpy()
+            ok = np.array_equal(got, ref)
+            print(f"[{world} GPUs] {shape} {dims} x{times}: {'identical' if ok else 'MISMATCH'}", flush=True)
+            bad += 0 if ok else 1
+    flag = torch.tensor([bad], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -201,3 +201,17 @@ def test_linearity_and_shift_invariance_at_scale():
     slab = a[r0:r0 + 8 + 16].cpu().numpy()
     ref = oracle.step(2, np.ascontiguousarray(slab), oracle.effective_params(shape))
     assert np.array_equal(outs[0][r0 + 4:r0 + 4 + 16].cpu().numpy()[:, 4:-4], ref[4:-4, 4:-4])
+
+
+def test_two_gpu_slabs_identical_to_one_gpu():
+    """N > 1 on real GPUs (skipped on a 1-GPU box; tests/test_slab_gloo.py covers the logic on CPU)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(os.path.dirname(__file__), "multigpu_check.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

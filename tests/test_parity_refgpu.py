@@ -21,12 +21,17 @@ def test_same_results_as_reference_gpu_operator(shape, dims, capfd):
     try:
         a = oracle.fill_rand(shape, dims)
         p = oracle.reference_params(shape)
-        for times in (1, 2, 3, 6):
+        # integer data: both sides are exact while values stay below 2^53
+        exact_upto = {"1d1r": 8, "1d2r": 8, "box2d1r": 5, "box2d3r": 5, "star2d1r": 6, "star2d3r": 9,
+                      "box3d1r": 8, "star3d1r": 15}[shape]
+        for times in (1, 2, 3, 5, 6, 12):
             ref = oracle.ref_gpu_run(shape, a, p, times)
             out = np.zeros_like(a)
             ops.BY_SHAPE[shape](a, out, p, times, *dims)
-            # integer data: both sides are exact while values stay below 2^53
-            assert np.array_equal(out, ref), (shape, times)
+            if times <= exact_upto:
+                assert np.array_equal(out, ref), (shape, times)
+            else:
+                assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max(), (shape, times)
         rng = np.random.default_rng(2)
         b = rng.uniform(-1, 1, a.shape)
         for times in (1, 5):
