@@ -118,6 +118,22 @@ int lora_plan_step(lora_plan_t *plan, const double *src, double *dst, long long 
  * is in buf[times%2].  Asynchronous on `stream`. */
 int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void *stream);
 
+/* Temporal blocking (new; the reference launches one kernel per time step).  lora_plan_run fuses up to
+ * `tb` consecutive launches into one sweep that keeps the intermediate grids on chip; results are
+ * bit-identical to unfused launches, halo semantics (S2) included.  Default: 4 for the 1-D shapes (or the
+ * environment variable LORA_TB), 1 for 2-D / 3-D (not implemented there yet: the call clamps).  */
+int lora_plan_set_temporal_block(lora_plan_t *plan, int tb);
+int lora_plan_temporal_block(const lora_plan_t *plan);
+
+/* One FUSED launch of `tb` time steps over interior range [lo, hi) (1-D only, lo % 4 == 0): reads
+ * src[lo - 4 tb, hi + 4 tb) clipped to the array, writes dst[lo, hi).  `launches_before` = time steps
+ * already applied to src (its parity selects the halo each level sees).  virt_lo / virt_hi: that end of
+ * the array is an end of the global line, whose halo cells are virtual -- caller's halo (read from the
+ * padded buffer `halo_src`) at even times, zero at odd times; with 0 the side is an inter-slab boundary
+ * whose halo / ghost cells hold real neighbour data in src. */
+int lora_plan_step_fused(lora_plan_t *plan, const double *src, double *dst, const double *halo_src, long long lo,
+                         long long hi, int tb, int launches_before, int virt_lo, int virt_hi, void *stream);
+
 /* how many kernel launches the plan has issued so far (bench.py's gpu_launches) */
 long long lora_plan_launch_count(const lora_plan_t *plan);
 

@@ -19,7 +19,8 @@ C_ABI_SYMBOLS = (
     "lora_gpu_1d1r", "lora_gpu_1d2r", "lora_gpu_star_2d1r", "lora_gpu_star_2d3r", "lora_gpu_box_2d3r",
     "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
     "lora_last_total_ms", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
-    "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_launch_count", "lora_plan_describe",
+    "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_set_temporal_block",
+    "lora_plan_temporal_block", "lora_plan_step_fused", "lora_plan_launch_count", "lora_plan_describe",
     "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
 )
 # the reference's own C++ symbols (include/lorastencil_dropin.hpp)
@@ -87,6 +88,13 @@ def lib() -> ctypes.CDLL:
     L.lora_plan_step.restype = c_int
     L.lora_plan_run.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     L.lora_plan_run.restype = c_int
+    L.lora_plan_set_temporal_block.argtypes = [c_void_p, c_int]
+    L.lora_plan_set_temporal_block.restype = c_int
+    L.lora_plan_temporal_block.argtypes = [c_void_p]
+    L.lora_plan_temporal_block.restype = c_int
+    L.lora_plan_step_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int,
+                                       c_int, c_int, c_void_p]
+    L.lora_plan_step_fused.restype = c_int
     L.lora_plan_launch_count.argtypes = [c_void_p]
     L.lora_plan_launch_count.restype = c_longlong
     L.lora_plan_describe.argtypes = [c_void_p]

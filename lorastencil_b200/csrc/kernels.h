@@ -13,6 +13,8 @@ constexpr int kRowsPerStage = 4;   // rows of one TMA box
 constexpr int kStages = 3;         // per-warp ring depth
 constexpr int kStageElems = kRowsPerStage * kBoxCols;            // 544 doubles = 4352 B (34 x 128 B)
 constexpr int kSmem12 = kWarpsPerCta * kStages * kStageElems * 8 + kWarpsPerCta * kStages * 8;
+constexpr int kMaxTb1 = 4;          // deepest temporal block of the 1-D kernel
+constexpr int kSmem1Tb = kSmem12 + kWarpsPerCta * kMaxTb1 * 2 * 8 * 8;  // + per-warp, per-level row hand-over mailboxes
 
 // 3-D: CTA tile of 32 rows x 128 columns per plane, 8 warps x (4 rows x 128 cols); warp 0 lane 0 also drives TMA
 constexpr int k3TileRows = 32;
@@ -56,6 +58,20 @@ struct Geom1D {
     int vec4;           // 256-bit stores allowed (lo % 4 == 0 and 32-byte aligned base)
 };
 
+// temporally blocked 1-D sweep (stencil1d_tb.cu): TB launches fused, rows of 256 cells
+struct Geom1DTB {
+    const double *in;        // padded source (level 0)
+    double *out;             // padded destination (level TB)
+    const double *halo_src;  // padded buffer whose halo cells hold the caller's halo (buffer 0 of the ping-pong)
+    long long n;             // interior length of the device array
+    long long lo, hi;        // interior range written by this launch (lo % 4 == 0)
+    int rows_per_task;       // 256-cell rows one warp sweeps
+    long long ntasks;
+    int par0;                // parity of the launch count before level 0 (0: level 0 sees the caller's halo)
+    int virt_left, virt_right;  // this end of the array is an end of the global line: halo cells are virtual
+    int vec4;
+};
+
 struct Geom2D {
     double *out;
     long long pitch;  // padded columns
@@ -79,11 +95,13 @@ struct Geom3D {
 };
 
 cudaError_t launch_1d(const Geom1D &g, const Weights1D &w, cudaStream_t s);
+cudaError_t launch_1d_tb(int tb, const Geom1DTB &g, const Weights1D &w, cudaStream_t s);
 cudaError_t launch_2d(int form, const CUtensorMap &tmap, const Geom2D &g, const Weights2D &w,
                       const WeightsDirect49 &wd, cudaStream_t s);
 cudaError_t launch_3d(int form, const CUtensorMap &tmap, const Geom3D &g, const Weights3D &w, cudaStream_t s);
 cudaError_t kernels_init();     // opt in to large dynamic shared memory once per process/device
 cudaError_t kernels_init_1d();
+cudaError_t kernels_init_1d_tb();
 cudaError_t kernels_init_2d();
 cudaError_t kernels_init_3d();
 

@@ -84,6 +84,7 @@ struct lora_plan {
     int sm_count = 148;
     int slots = 148 * 16;  // concurrently resident warp workers (1-D / 2-D) or CTAs (3-D)
     int device = 0;
+    int max_tb = 1;        // deepest temporal block lora_plan_run may fuse (1 = one launch per time step)
 };
 
 static std::once_flag g_init_once;
@@ -154,6 +155,13 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
     const int warps_per_sm = (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
+    if (dim == 1) {
+        p->max_tb = kMaxTb1;
+        if (const char *e = getenv("LORA_TB")) {
+            const int v = atoi(e);
+            if (v >= 1) p->max_tb = v < kMaxTb1 ? v : kMaxTb1;
+        }
+    }
     *out = p;
     return LORA_OK;
 }
@@ -276,9 +284,83 @@ extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, lo
     return LORA_OK;
 }
 
+extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
+    if (!p || tb < 1) return fail(LORA_ERR_ARG, "bad argument");
+    const int cap = (p->dim == 1) ? kMaxTb1 : 1;
+    p->max_tb = tb < cap ? tb : cap;
+    return LORA_OK;
+}
+
+extern "C" int lora_plan_temporal_block(const lora_plan_t *p) { return p ? p->max_tb : 0; }
+
+extern "C" int lora_plan_step_fused(lora_plan_t *p, const double *src, double *dst, const double *halo_src,
+                                    long long lo, long long hi, int tb, int launches_before, int virt_lo, int virt_hi,
+                                    void *stream) {
+    if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
+    if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D shapes");
+    if (tb < 1 || tb > kMaxTb1) return fail(LORA_ERR_ARG, "temporal block must be 1..%d", kMaxTb1);
+    if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
+    if ((virt_lo || virt_hi) && !halo_src) return fail(LORA_ERR_ARG, "virtual halo needs halo_src");
+    if (lo == hi) return LORA_OK;
+    if (lo % 4) return fail(LORA_ERR_ARG, "1-D fused range must start at a multiple of 4");
+    if (reinterpret_cast<uintptr_t>(src) % 16 || reinterpret_cast<uintptr_t>(dst) % 16)
+        return fail(LORA_ERR_ARG, "buffers must be 16-byte aligned");
+    Geom1DTB g;
+    g.in = src;
+    g.out = dst;
+    g.halo_src = halo_src ? halo_src : src;
+    g.n = p->dims[0];
+    g.lo = lo;
+    g.hi = hi;
+    const long long rows = (hi - lo + 255) / 256;
+    g.rows_per_task = (int)pick_len(rows, 1, p->slots, 128, 8);
+    g.ntasks = (rows + g.rows_per_task - 1) / g.rows_per_task;
+    g.par0 = launches_before & 1;
+    g.virt_left = virt_lo ? 1 : 0;
+    g.virt_right = virt_hi ? 1 : 0;
+    g.vec4 = reinterpret_cast<uintptr_t>(dst) % 32 == 0;
+    cudaError_t e = launch_1d_tb(tb, g, p->w1, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    p->launches++;
+    return LORA_OK;
+}
+
+// Temporal blocks for `times` launches: as many blocks of max_tb as fit, the remainder, and -- because the
+// result has to land in buf[times % 2] like the reference's ping-pong (S3) -- one block split in two when
+// the number of fused launches would have the wrong parity.
+static std::vector<int> temporal_schedule(int times, int max_tb) {
+    std::vector<int> tbs;
+    for (int left = times; left > 0;) {
+        const int t = left < max_tb ? left : max_tb;
+        tbs.push_back(t);
+        left -= t;
+    }
+    if ((tbs.size() & 1) != (size_t)(times & 1)) {
+        for (size_t i = tbs.size(); i-- > 0;)
+            if (tbs[i] >= 2) {
+                const int a = tbs[i] / 2, b = tbs[i] - a;
+                tbs[i] = b;
+                tbs.insert(tbs.begin() + i, a);
+                break;
+            }
+    }
+    return tbs;
+}
+
 extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int times, void *stream) {
     if (!p || !buf0 || !buf1) return fail(LORA_ERR_ARG, "null argument");
     double *buf[2] = {buf0, buf1};
+    if (p->dim == 1 && p->max_tb > 1 && times > 1) {
+        // fused: launch k reads buf[k%2]; the halo every level sees is virtual (caller's halo lives in buf0)
+        const std::vector<int> tbs = temporal_schedule(times, p->max_tb);
+        int done = 0;
+        for (size_t k = 0; k < tbs.size(); k++) {
+            int rc = lora_plan_step_fused(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tbs[k], done, 1, 1, stream);
+            if (rc) return rc;
+            done += tbs[k];
+        }
+        return LORA_OK;
+    }
     for (int i = 0; i < times; i++) {
         int rc = lora_plan_step(p, buf[i % 2], buf[(i + 1) % 2], 0, p->dims[0], stream);
         if (rc) return rc;

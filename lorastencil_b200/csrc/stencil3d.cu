@@ -270,6 +270,7 @@ cudaError_t launch_3d(int form, const CUtensorMap &tmap, const Geom3D &g, const 
 cudaError_t kernels_init() {
     cudaError_t e;
     if ((e = kernels_init_1d()) != cudaSuccess) return e;
+    if ((e = kernels_init_1d_tb()) != cudaSuccess) return e;
     if ((e = kernels_init_2d()) != cudaSuccess) return e;
     return kernels_init_3d();
 }

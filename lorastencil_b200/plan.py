@@ -82,6 +82,24 @@ class Plan:
         return int(_lib.lib().lora_plan_launch_count(self._h))
 
     @property
+    def temporal_block(self) -> int:
+        """Deepest temporal block `run` fuses (1 = one kernel launch per time step)."""
+        return int(_lib.lib().lora_plan_temporal_block(self._h))
+
+    @temporal_block.setter
+    def temporal_block(self, tb: int):
+        _lib.check(_lib.lib().lora_plan_set_temporal_block(self._h, int(tb)), "lora_plan_set_temporal_block")
+
+    def step_fused(self, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream=None):
+        """One fused launch of `tb` time steps (1-D): see lora_plan_step_fused in include/lorastencil.h."""
+        import torch
+        s = torch.cuda.current_stream(src.device) if stream is None else stream
+        _lib.check(_lib.lib().lora_plan_step_fused(
+            self._h, c_void_p(src.data_ptr()), c_void_p(dst.data_ptr()),
+            c_void_p(halo_src.data_ptr()) if halo_src is not None else None, int(lo), int(hi), int(tb),
+            int(launches_before), int(bool(virt_lo)), int(bool(virt_hi)), c_void_p(s.cuda_stream)), "lora_plan_step_fused")
+
+    @property
     def cells(self) -> int:
         return int(np.prod(self.dims))
 

@@ -171,7 +171,8 @@ def test_plan_api_partial_ranges_and_device_buffers():
             assert np.array_equal(got[:-1], full[:-1])
         else:
             assert np.array_equal(got, full)
-        assert plan.launches == len(cuts) - 1 + 3
+        # 1-D fuses the 3 launches of `run` into one temporally blocked sweep; 2-D / 3-D launch once per step
+        assert plan.launches == len(cuts) - 1 + (1 if oracle.dim_of(shape) == 1 else 3)
 
 
 def test_linearity_and_shift_invariance_at_scale():
@@ -201,6 +202,62 @@ def test_linearity_and_shift_invariance_at_scale():
     slab = a[r0:r0 + 8 + 16].cpu().numpy()
     ref = oracle.step(2, np.ascontiguousarray(slab), oracle.effective_params(shape))
     assert np.array_equal(outs[0][r0 + 4:r0 + 4 + 16].cpu().numpy()[:, 4:-4], ref[4:-4, 4:-4])
+
+
+@pytest.mark.parametrize("n", [7, 130, 1000, 4096, 100003, 1 << 20])
+def test_temporal_blocking_1d_equals_unfused_launches(n):
+    """Fused sweeps of 2/3/4 launches (intermediate levels in registers, virtual alternating halo) give the
+    same bits as one launch per step and as the oracle, for every launch count parity and ragged sizes."""
+    import torch
+    shape = "1d2r"
+    a = oracle.fill_rand(shape, (n,))
+    rng = np.random.default_rng(n)
+    af = rng.uniform(-1, 1, a.shape)
+    eff = oracle.effective_params(shape)
+    plan = ls.Plan(shape, (n,))
+    assert plan.temporal_block == 4
+    for data, exact_upto in ((a, 8), (af, 0)):
+        for times in (1, 2, 3, 4, 5, 6, 7, 8, 9, 13, 40):
+            ref = oracle.run(shape, data, eff, times)[:-1]
+            results = []
+            for tb in (1, 2, 3, 4):
+                plan.temporal_block = tb
+                b0, b1 = torch.from_numpy(data).cuda(), plan.new_buffer()
+                res = plan.run(b0, b1, times)
+                torch.cuda.synchronize()
+                assert res is (b0 if times % 2 == 0 else b1)
+                results.append(res.cpu().numpy()[:-1])
+            for r in results[1:]:
+                assert np.array_equal(r, results[0]), (n, times)  # same operation order => same bits
+            if times <= exact_upto:
+                assert np.array_equal(results[0], ref), (n, times)
+            else:
+                assert max_rel_err(results[0], ref) <= RTOL, (n, times)
+
+
+def test_fused_step_sub_ranges_with_real_halo_data():
+    """lora_plan_step_fused on interior sub-ranges with virt flags off (the inter-slab case): the fused launch
+    equals tb single launches wherever the dependency cone stays inside the data that was provided."""
+    import torch
+    n, tb = 20000, 3
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 100, (n + 8,)).astype(np.float64)  # integers: 3 steps stay exact on both sides
+    eff = oracle.effective_params("1d1r")
+    plan = ls.Plan("1d1r", (n,))
+    src = torch.from_numpy(a).cuda()
+    dst = torch.full((n + 8,), -5.0, dtype=torch.float64, device="cuda")
+    lo, hi = 4096, 12000
+    plan.step_fused(src, dst, None, lo, hi, tb, 0, False, False)
+    torch.cuda.synchronize()
+    # reference: tb plain steps of the whole line with its physical halo kept fixed (never re-zeroed):
+    ref = a.copy()
+    for _ in range(tb):
+        nxt = ref.copy()
+        nxt[4:-4] = oracle.step(1, ref, eff)[4:-4]
+        ref = nxt
+    got = dst.cpu().numpy()
+    assert np.array_equal(got[4 + lo:4 + hi], ref[4 + lo:4 + hi])
+    assert np.all(got[:4 + lo] == -5.0) and np.all(got[4 + hi:] == -5.0)
 
 
 def test_two_gpu_slabs_identical_to_one_gpu():
