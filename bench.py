@@ -279,7 +279,7 @@ def main():
     for _ in range(args.warmup):
         one_step()
     barrier()
-    launches0 = plan.launches
+    launches0, sweeps0 = plan.launches, runner.launch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
@@ -298,7 +298,7 @@ def main():
     value = total_cells_launches / (ms / 1e3) / 1e9
     # dominant kernel: the full-slab (world 1) or interior (world > 1) sweep; with temporal blocking one launch
     # advances `tb` time steps, so its algorithmic bytes are 16 B x cells x tb
-    main_launches = gpu_launches if world == 1 else gpu_launches // 3
+    main_launches = gpu_launches if world == 1 else (runner.launch - sweeps0)
     steps_per_launch = times * args.steps / main_launches
     us_per_launch = ms * 1e3 / main_launches
     achieved = cells_per_gpu * 16 * steps_per_launch / (us_per_launch * 1e-6) / 1e9
@@ -306,9 +306,10 @@ def main():
     # ---- e2e: through the reference-facing operator with pinned host buffers ----
     e2e = None
     if not args.no_e2e:
-        hin = torch.empty(n + 8, dtype=torch.float64).pin_memory()
-        hout = torch.empty(n + 8, dtype=torch.float64).pin_memory()
-        hin.copy_(torch.randint(0, 10000, (n + 8,)).double())
+        nloc = runner.geo.local_padded[0]  # n + 8 on one device; slab + halo / ghost cells on a rank of N
+        hin = torch.empty(nloc, dtype=torch.float64).pin_memory()
+        hout = torch.empty(nloc, dtype=torch.float64).pin_memory()
+        hin.copy_(torch.randint(0, 10000, (nloc,)).double())
         params = ls.reference_table(shape)
         k_e2e = max(1, min(args.steps, 3))
         if world == 1:
@@ -325,7 +326,7 @@ def main():
             def e2e_step():
                 runner.buf[0].copy_(hin, non_blocking=True)
                 runner.buf[1].zero_()
-                runner.launch = 0
+                runner.launch = runner.time = 0
                 res = runner.run(times)
                 hout.copy_(res, non_blocking=True)
                 torch.cuda.synchronize()
@@ -340,7 +341,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
         e2e = {"value": cells_per_gpu * world * times * k_e2e / el / 1e9, "unit": "GStencil/s",
-               "h2d_bytes_per_step": (n + 8) * 8 * world, "d2h_bytes_per_step": (n + 7) * 8 * world,
+               "h2d_bytes_per_step": nloc * 8 * world, "d2h_bytes_per_step": (nloc - (1 if world == 1 else 0)) * 8 * world,
                "steps": k_e2e, "ms_per_step": el / k_e2e * 1e3,
                "api": "lorastencil_b200.ops.gpu_1d2r -> lora_gpu_1d2r (C ABI), pinned host buffers" if world == 1 else
                       "pinned host slab -> SlabRunner.run -> pinned host slab", **e2e_detail}
@@ -359,15 +360,17 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"lorastencil_1d {shape} {n} {times} per GPU (BASELINE.json configs[1])",
                    "shape": shape, "points_per_gpu": n, "launches_per_step": times,
-                   "decomposition": "single device" if world == 1 else f"{world} slabs, 4-element halo exchange per launch (NCCL send/recv)",
+                   "decomposition": "single device" if world == 1 else
+                   f"{world} slabs, {4 * runner.max_tb}-element ghost-zone exchange per temporal block of {runner.max_tb} launches "
+                   "(NCCL send/recv on a side stream, edge bands first)",
                    "l2": "inputs (2.1 GB per buffer) larger than L2; no flush needed",
                    "values": "reference weights: FP64 overflows to inf after ~217 launches exactly as in the reference run; timing only",
-                   "kernel_form": plan.describe, "temporal_block": plan.temporal_block},
+                   "kernel_form": plan.describe, "temporal_block": runner.max_tb},
         "gpu_launches": gpu_launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": None,
-                     "kernel": f"k_stencil1d_tb<{plan.temporal_block}>" if (world == 1 and plan.temporal_block > 1) else "k_stencil1d",
+                     "kernel": f"k_stencil1d_tb<{runner.max_tb}>" if runner.max_tb > 1 else "k_stencil1d",
                      "us_per_launch": us_per_launch,
                      "algorithmic_bytes_per_launch": cells_per_gpu * 16 * steps_per_launch,
                      "time_steps_per_launch": steps_per_launch, "peak_source": peak_src,

@@ -59,3 +59,24 @@ def test_banner_matches_reference(capfd):
     assert our_lines[0] == ref_lines[0] == "LoRAStencil(2D box_2d3r): "
     assert our_lines[1].startswith("Time = ") and our_lines[1].endswith("[ms]")
     assert our_lines[2].startswith("GStencil/s = ")
+
+
+@pytest.mark.parametrize("dim,args", [(1, ["1d1r", "10240", "3"]), (1, ["1d2r", "4096", "1"]),
+                                      (2, ["box2d1r", "1024", "1024", "10"]), (2, ["box2d3r", "64", "128", "2"]),
+                                      (2, ["star2d1r", "96", "64", "3"]), (2, ["star2d3r", "32", "192", "1"]),
+                                      (3, ["box3d1r", "16", "16", "64", "2"]), (3, ["star3d1r", "8", "24", "128", "3"])])
+def test_reference_driver_links_against_our_library_and_passes_its_own_check(dim, args):
+    """The reference's UNMODIFIED main.cu (compiled with -DCHECK_ERROR by oracle/Makefile, linked against
+    liblorastencil_b200.so instead of its gpu_*.cu) runs its own verification loop -- test_cpu vs one launch,
+    every interior cell whose |difference| > 1e-7 is printed (src/2d/main.cu:282-328) -- and prints none."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(oracle.__file__), "_ref", f"refmain_{dim}d")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/refmain_* not built")
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    assert "Comparing naive and lora" in out and "Correct!" in out
+    assert "naive = " not in out, out[-2000:]           # no mismatch lines
+    assert out.count("GStencil/s = ") == 2              # timed run + the times=1 verification run

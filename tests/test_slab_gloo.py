@@ -25,6 +25,11 @@ def test_geometry_covers_the_axis_without_overlap():
         assert gs[0].prev is None and gs[-1].next is None and gs[0].next == 1
         for g in gs:
             assert g.local_padded[0] == g.hi - g.lo + 2 * g.halo
+    # ghost zones (1-D temporal blocking): 16 cells towards neighbours, the 4-cell halo towards the ends
+    gs = [SlabGeometry((4096,), 3, r, 16, ghost=16) for r in range(3)]
+    assert [(g.wl, g.wr) for g in gs] == [(4, 16), (16, 16), (16, 4)]
+    assert [g.off for g in gs] == [0, 12, 12]
+    assert gs[1].local_padded[0] == gs[1].slab + 32 and gs[0].local_padded[0] == gs[0].slab + 20
     with pytest.raises(ValueError):
         SlabGeometry((6, 64), 4, 0)
 
@@ -37,7 +42,25 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, dims, times, ret):
+def _oracle_fused_fn(eff):
+    """CPU stand-in for Plan.step_fused (lora_plan_step_fused): tb oracle steps with the virtual halo."""
+    def fused(src, dst, halo_src, lo, hi, tb, t0, virt_lo, virt_hi, stream=None):
+        cur = src.numpy().copy()
+        H = halo_src.numpy()
+        for s in range(tb):
+            use_h = (t0 + s) % 2 == 0
+            if virt_lo:
+                cur[:4] = H[:4] if use_h else 0.0
+            if virt_hi:
+                cur[-4:] = H[-4:] if use_h else 0.0
+            nxt = cur.copy()
+            nxt[4:-4] = oracle.step(1, cur, eff)[4:-4]
+            cur = nxt
+        dst.numpy()[4 + lo:4 + hi] = cur[4 + lo:4 + hi]
+    return fused
+
+
+def _worker(rank, world, port, shape, dims, times, ret, fused=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -52,7 +75,9 @@ def _worker(rank, world, port, shape, dims, times, ret):
             dst.numpy()[sl] = full[sl]
 
         a = oracle.fill_rand(shape, dims)  # every rank generates the same global input
-        runner = SlabRunner(shape, dims, step_fn=step_fn)
+        runner = SlabRunner(shape, dims, step_fn=step_fn, fused_fn=_oracle_fused_fn(eff) if fused else None,
+                            temporal_block=4 if fused else None)
+        assert runner.max_tb == (4 if fused else 1)
         runner.load_global(a)
         runner.run(times)
         got = runner.gather_global(a.shape)
@@ -64,14 +89,25 @@ def _worker(rank, world, port, shape, dims, times, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shape,dims,world,times", [
-    ("1d2r", (4096,), 2, 3), ("box2d3r", (48, 64), 2, 4), ("star2d1r", (40, 36), 3, 3),
-    ("box3d1r", (12, 8, 64), 2, 3), ("star3d1r", (9, 5, 30), 3, 2), ("box2d1r", (32, 64), 2, 1)])
-def test_slab_run_equals_single_domain(shape, dims, world, times):
+def test_temporal_schedule_lands_in_the_reference_buffer():
+    from lorastencil_b200.slab import temporal_schedule
+    for max_tb in (1, 2, 3, 4):
+        for times in range(0, 60):
+            tbs = temporal_schedule(times, max_tb)
+            assert sum(tbs) == times and all(1 <= t <= max_tb for t in tbs)
+            assert len(tbs) % 2 == times % 2  # result in buf[times % 2] (S3)
+    assert temporal_schedule(1000, 4) == [4] * 250
+
+
+@pytest.mark.parametrize("shape,dims,world,times,fused", [
+    ("1d2r", (4096,), 2, 3, False), ("box2d3r", (48, 64), 2, 4, False), ("star2d1r", (40, 36), 3, 3, False),
+    ("box3d1r", (12, 8, 64), 2, 3, False), ("star3d1r", (9, 5, 30), 3, 2, False), ("box2d1r", (32, 64), 2, 1, False),
+    ("1d2r", (4096,), 2, 7, True), ("1d1r", (1000,), 3, 10, True)])
+def test_slab_run_equals_single_domain(shape, dims, world, times, fused):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, dims, times, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, dims, times, ret, fused)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
