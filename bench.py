@@ -238,6 +238,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    # libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout, so everything
+    # else goes to stderr and the JSON line is written to the saved descriptor
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -384,7 +388,8 @@ def main():
         line["cpu_baseline"] = time_cpu(shape, dims)
     if world == 1 and not args.no_shapes:
         line["shapes"] = [measure_shape(torch, ls, s, d, l, hbm_gbs) for s, d, l in SHAPE_TABLE]
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -14,7 +14,11 @@ constexpr int kStages = 3;         // per-warp ring depth
 constexpr int kStageElems = kRowsPerStage * kBoxCols;            // 544 doubles = 4352 B (34 x 128 B)
 constexpr int kSmem12 = kWarpsPerCta * kStages * kStageElems * 8 + kWarpsPerCta * kStages * 8;
 constexpr int kMaxTb1 = 4;          // deepest temporal block of the 1-D kernel
-constexpr int kSmem1Tb = kSmem12 + kWarpsPerCta * kMaxTb1 * 2 * 8 * 8;  // + per-warp, per-level row hand-over mailboxes
+// per-warp shared memory of the temporally blocked 1-D kernel: 3 x 4 KB TMA load ring, 2 x 2 KB output staging
+// rows (TMA store), per-level row hand-over mailboxes (4 levels x 2 parities x 64 B), 3 mbarriers
+constexpr int kTbRing = 3 * 4096, kTbOut = 2 * 2048, kTbMail = kMaxTb1 * 2 * 64, kTbBars = 64;
+constexpr int kTbWarpSmem = kTbRing + kTbOut + kTbMail + kTbBars;
+constexpr int kSmem1Tb = kWarpsPerCta * kTbWarpSmem;
 
 // 3-D: CTA tile of 32 rows x 128 columns per plane, 8 warps x (4 rows x 128 cols); warp 0 lane 0 also drives TMA
 constexpr int k3TileRows = 32;

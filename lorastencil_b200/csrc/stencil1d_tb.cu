@@ -10,8 +10,14 @@
 //     lane l-1's 8 cells followed by its own 8 cells, so one level costs 8 FP64 warp shuffles (16 SHFL.32)
 //     + 72 DFMA per lane, no shared-memory round trip, and a row never needs data from the row after it;
 //   * lane 0 takes lane 31's cells of the previous row from a 64-byte per-level mailbox in shared memory;
-//   * level 0 arrives through the warp's private TMA ring (cp.async.bulk, 2 rows = 4 KB per stage), level
-//     TB leaves with 256-bit stores, 32-byte aligned because B = s0 + 4 TB makes the final skew vanish.
+//   * level 0 arrives through the warp's private TMA ring (cp.async.bulk, 2 rows = 4 KB per stage); level TB
+//     leaves through a 2 KB staging row and a TMA store (cp.async.bulk shared -> global), row-aligned because
+//     B = s0 + 4 TB makes the final skew vanish;
+//   * a lane's 8 cells are 64 contiguous bytes, i.e. a 64-byte lane stride in shared memory, which is a 4-way
+//     bank conflict for plain 128-bit accesses.  Lanes therefore touch their four 16-byte pieces in a rotated
+//     order (piece (k + lane/2) mod 4 in instruction k): every quarter-warp then covers all 8 bank groups, the
+//     access is conflict-free, and a 2-level select network un-rotates the registers (ALU pipe, which is idle).
+//     The LSU data pipe is this kernel's bottleneck (profiles/), so wavefronts are what is being saved.
 //
 // Reference semantics (S2) under fusion: launch i of the reference sees the caller's
 // halo when i is even and zeros when i is odd.  Inside a fused sweep the halo cells of every level are
@@ -27,6 +33,50 @@ namespace {
 constexpr int kTbRow = 256;                 // cells per row
 constexpr int kTbStageRows = 2;             // rows per bulk copy
 constexpr int kTbStage = kTbStageRows * kTbRow;  // 512 doubles <= kStageElems
+
+// piece order used by lane `lane` for its k-th 128-bit access to a 64-byte chunk: conflict-free in shared memory
+__device__ __forceinline__ int rot_of(int lane) { return (lane >> 1) & 3; }
+
+// out[j] = in[(j - rot) & 3] for 16-byte pieces (2-level barrel of selects)
+__device__ __forceinline__ void unrotate(const double2 (&in)[4], int rot, double2 (&out)[4]) {
+    double2 a[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        a[j].x = (rot & 1) ? in[(j + 3) & 3].x : in[j].x;
+        a[j].y = (rot & 1) ? in[(j + 3) & 3].y : in[j].y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        out[j].x = (rot & 2) ? a[(j + 2) & 3].x : a[j].x;
+        out[j].y = (rot & 2) ? a[(j + 2) & 3].y : a[j].y;
+    }
+}
+
+// lane's 8 cells (64 contiguous bytes at chunk) -> registers, conflict-free
+__device__ __forceinline__ void load_rotated(const double *chunk, int lane, double (&cur)[8]) {
+    const int rot = rot_of(lane);
+    double2 r[4], pc[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) r[k] = *reinterpret_cast<const double2 *>(chunk + 2 * ((k + rot) & 3));
+    unrotate(r, rot, pc);  // r[k] holds piece (k + rot) & 3  =>  piece j = r[(j - rot) & 3]
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        cur[2 * j] = pc[j].x;
+        cur[2 * j + 1] = pc[j].y;
+    }
+}
+
+// registers -> lane's 64-byte chunk of the staging row, conflict-free
+__device__ __forceinline__ void store_rotated(double *chunk, int lane, const double (&cur)[8]) {
+    const int rot = rot_of(lane);
+    double2 pc[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) pc[j] = make_double2(cur[2 * j], cur[2 * j + 1]);
+    // instruction k writes piece (k + rot) & 3: q[k] = pc[(k + rot) & 3] = pc[(k - (4 - rot)) & 3]
+    unrotate(pc, (4 - rot) & 3, q);
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<double2 *>(chunk + 2 * ((k + rot) & 3)) = q[k];
+}
 
 // virtual halo of one level: cells -4..-1 and n..n+3 take (level time even ? caller's halo : 0)
 __device__ __forceinline__ void fix_halo(double (&v)[8], long long p, int level, const Geom1DTB &g) {
@@ -44,12 +94,7 @@ __device__ __forceinline__ void fix_halo(double (&v)[8], long long p, int level,
 template <int TB, bool FIX>
 __device__ __forceinline__ void sweep_row(const double *rowp, double *mailbox, int i, int lane, long long p,
                                           const Geom1DTB &g, const Weights1D &w, double (&cur)[8]) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const double2 v = reinterpret_cast<const double2 *>(rowp)[k];
-        cur[2 * k] = v.x;
-        cur[2 * k + 1] = v.y;
-    }
+    load_rotated(rowp, lane, cur);
     if (FIX) fix_halo(cur, p, 0, g);
 #pragma unroll
     for (int s = 1; s <= TB; s++) {
@@ -85,17 +130,18 @@ __device__ __forceinline__ void sweep_row(const double *rowp, double *mailbox, i
 }
 
 template <int TB>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 4)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 3)
 k_stencil1d_tb(const __grid_constant__ Geom1DTB g, const __grid_constant__ Weights1D w) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (task >= g.ntasks) return;
 
-    double *ring = reinterpret_cast<double *>(smem_raw) + warp * (kStages * kStageElems);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kWarpsPerCta * kStages * kStageElems * 8) + warp * kStages;
-    // mailbox[level][row parity][8]: lane 31's cells of the previous row
-    double *mailbox = reinterpret_cast<double *>(smem_raw + kSmem12) + warp * (4 * 2 * 8);
+    unsigned char *wsm = smem_raw + warp * kTbWarpSmem;
+    double *ring = reinterpret_cast<double *>(wsm);                            // 3 stages x 512 doubles
+    double *outbuf = reinterpret_cast<double *>(wsm + kTbRing);                // 2 staging rows x 256 doubles
+    double *mailbox = reinterpret_cast<double *>(wsm + kTbRing + kTbOut);      // [level][row parity][8]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + kTbRing + kTbOut + kTbMail);
 
     const long long s0 = g.lo + task * (long long)g.rows_per_task * kTbRow;  // first output cell (interior coords)
     const long long len = min((long long)g.rows_per_task * kTbRow, g.hi - s0);
@@ -116,8 +162,8 @@ k_stencil1d_tb(const __grid_constant__ Geom1DTB g, const __grid_constant__ Weigh
         const long long even = cnt & ~1LL;
         mbar_arrive_expect_tx(&bars[slot], (uint32_t)(even * 8));
         if (even > 0)
-            tma_load_1d(ring + slot * kStageElems + skip, g.in + start + skip, (uint32_t)(even * 8), &bars[slot]);
-        if (cnt != even) ring[slot * kStageElems + skip + even] = g.in[start + skip + even];
+            tma_load_1d(ring + slot * kTbStage + skip, g.in + start + skip, (uint32_t)(even * 8), &bars[slot]);
+        if (cnt != even) ring[slot * kTbStage + skip + even] = g.in[start + skip + even];
     };
 
     if (lane == 0) {
@@ -134,7 +180,7 @@ k_stencil1d_tb(const __grid_constant__ Geom1DTB g, const __grid_constant__ Weigh
     for (int i = 0; i < niter; i++) {
         const int st = i / kTbStageRows, rr = i % kTbStageRows, slot = st % kStages;
         if (rr == 0) mbar_wait(&bars[slot], (st / kStages) & 1);
-        const double *rowp = ring + slot * kStageElems + rr * kTbRow + 8 * lane;
+        const double *rowp = ring + slot * kTbStage + rr * kTbRow + 8 * lane;
         const long long p0 = task_start + (long long)i * kTbRow;  // interior coordinate of lane 0's first level-0 cell
         // rows whose skewed levels can touch a virtual halo zone take the (rare) patched path; warp-uniform
         const bool edge = (g.virt_left && p0 - 4 * TB < 0) || (g.virt_right && p0 + kTbRow > g.n);
@@ -147,17 +193,22 @@ k_stencil1d_tb(const __grid_constant__ Geom1DTB g, const __grid_constant__ Weigh
 
         // level TB, row j = i - 1: cells s0 + 256 j + 8 lane .. +7
         if (i >= 1) {
-            const long long p = p0 + 8 * lane - 4 * TB;
-            double *o = g.out + 4 + p;
-            if (p + 7 < end) {
-                if (g.vec4) {
-                    st_global_v4(o, cur[0], cur[1], cur[2], cur[3]);
-                    st_global_v4(o + 4, cur[4], cur[5], cur[6], cur[7]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; q += 2) st_global_v2(o + q, cur[q], cur[q + 1]);
+            const long long prow = p0 - 4 * TB;  // first cell of the output row
+            if (prow + kTbRow <= end) {
+                // whole row: stage it (conflict-free STS) and let the TMA write the 2 KB line segment
+                double *stage = outbuf + (i & 1) * kTbRow;
+                if (lane == 0) tma_store_wait_read<1>();  // the store issued from this staging row two rows ago has drained
+                __syncwarp();
+                store_rotated(stage + 8 * lane, lane, cur);
+                fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_1d(g.out + 4 + prow, stage, kTbRow * 8);
+                    tma_store_commit();
                 }
             } else {
+                const long long p = prow + 8 * lane;
+                double *o = g.out + 4 + p;
 #pragma unroll
                 for (int q = 0; q < 8; q++)
                     if (p + q < end) o[q] = cur[q];
@@ -167,6 +218,7 @@ k_stencil1d_tb(const __grid_constant__ Geom1DTB g, const __grid_constant__ Weigh
             if (lane == 0 && st + kStages < nst) issue(st + kStages, slot);
         }
     }
+    if (lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last TMA stores
 }
 
 template <int TB>

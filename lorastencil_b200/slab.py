@@ -63,9 +63,8 @@ class SlabGeometry:
         self.world, self.rank = world, rank
         self.halo = HALO[self.dim][0]
         n0 = self.dims[0]
-        per = -(-n0 // world)
-        per = -(-per // align) * align
-        self.bounds = [min(n0, r * per) for r in range(world + 1)]
+        units = -(-n0 // align)  # balanced split in units of `align` cells (the last unit may be partial)
+        self.bounds = [min(n0, align * (units * r // world)) for r in range(world + 1)]
         self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
         self.prev = rank - 1 if rank > 0 else None
         self.next = rank + 1 if rank < world - 1 else None
