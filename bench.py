@@ -317,7 +317,7 @@ def main():
         params = ls.reference_table(shape)
         k_e2e = max(1, min(args.steps, 3))
         if world == 1:
-            ops.gpu_1d2r(hin, hout, params, min(times, 10), n)  # warm: allocates the operator's device workspace
+            ops.gpu_1d2r(hin, hout, params, times, n)  # warm: allocates the operator's device workspace
             barrier()
             t0 = time.perf_counter()
             for _ in range(k_e2e):
@@ -374,7 +374,7 @@ def main():
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": None,
-                     "kernel": f"k_stencil1d_tb<{runner.max_tb}>" if runner.max_tb > 1 else "k_stencil1d",
+                     "kernel": f"k_stencil1d_tb (tb = {runner.max_tb})" if runner.max_tb > 1 else "k_stencil1d",
                      "us_per_launch": us_per_launch,
                      "algorithmic_bytes_per_launch": cells_per_gpu * 16 * steps_per_launch,
                      "time_steps_per_launch": steps_per_launch, "peak_source": peak_src,

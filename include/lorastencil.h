@@ -92,6 +92,14 @@ int lora_set_verbose(int on);
 double lora_last_loop_ms(void);
 double lora_last_total_ms(void);
 
+/* The 1-D drop-in operators overlap their copies with their launches: a cell after `times` launches depends on
+ * 4 * times cells either side only, so a long line is cut into chunks with ghost margins of that width; every
+ * chunk runs all its launches on its own while the next chunk's H2D copy and the previous chunk's D2H copy are
+ * in flight (bit-identical results; lora_last_loop_ms is then the sum of the chunks' launch loops).  Returns how
+ * many chunks the last lora_gpu_* call used (1 = plain H2D -> launches -> D2H).  Environment: LORA_CHUNKS=0
+ * disables the overlap, LORA_CHUNKS=k forces k chunks. */
+int lora_last_chunks(void);
+
 /* free the device workspace the drop-in operators cache between calls */
 void lora_release_workspace(void);
 
@@ -120,12 +128,12 @@ int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void
 
 /* Temporal blocking (new; the reference launches one kernel per time step).  lora_plan_run fuses up to
  * `tb` consecutive launches into one sweep that keeps the intermediate grids on chip; results are
- * bit-identical to unfused launches, halo semantics (S2) included.  Default: 4 for the 1-D shapes (or the
- * environment variable LORA_TB), 1 for 2-D / 3-D (not implemented there yet: the call clamps).  */
+ * bit-identical to unfused launches, halo semantics (S2) included.  Default: 15 (the maximum) for the 1-D
+ * shapes (or the environment variable LORA_TB), 1 for 2-D / 3-D (not implemented there yet: the call clamps).  */
 int lora_plan_set_temporal_block(lora_plan_t *plan, int tb);
 int lora_plan_temporal_block(const lora_plan_t *plan);
 
-/* One FUSED launch of `tb` time steps over interior range [lo, hi) (1-D only, lo % 4 == 0): reads
+/* One FUSED launch of `tb` (1..15) time steps over interior range [lo, hi) (1-D only): reads
  * src[lo - 4 tb, hi + 4 tb) clipped to the array, writes dst[lo, hi).  `launches_before` = time steps
  * already applied to src (its parity selects the halo each level sees).  virt_lo / virt_hi: that end of
  * the array is an end of the global line, whose halo cells are virtual -- caller's halo (read from the

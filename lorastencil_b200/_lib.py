@@ -18,7 +18,7 @@ WEIGHTS_GENERAL = 1
 C_ABI_SYMBOLS = (
     "lora_gpu_1d1r", "lora_gpu_1d2r", "lora_gpu_star_2d1r", "lora_gpu_star_2d3r", "lora_gpu_box_2d3r",
     "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
-    "lora_last_total_ms", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
+    "lora_last_total_ms", "lora_last_chunks", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
     "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_set_temporal_block",
     "lora_plan_temporal_block", "lora_plan_step_fused", "lora_plan_launch_count", "lora_plan_describe",
     "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
@@ -41,7 +41,8 @@ class Decomp2D(Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "lib", "liblorastencil_b200.so")
+    """The in-tree library; LORASTENCIL_LIB may name another build of it (kernel tuning experiments)."""
+    return os.environ.get("LORASTENCIL_LIB") or os.path.join(_HERE, "lib", "liblorastencil_b200.so")
 
 
 def library_built() -> bool:
@@ -77,6 +78,7 @@ def lib() -> ctypes.CDLL:
     L.lora_set_verbose.restype = c_int
     L.lora_last_loop_ms.restype = c_double
     L.lora_last_total_ms.restype = c_double
+    L.lora_last_chunks.restype = c_int
     L.lora_release_workspace.restype = None
     L.lora_plan_create.argtypes = [POINTER(c_void_p), c_int, c_int, dp, POINTER(c_longlong)]
     L.lora_plan_create.restype = c_int

@@ -13,12 +13,35 @@ constexpr int kRowsPerStage = 4;   // rows of one TMA box
 constexpr int kStages = 3;         // per-warp ring depth
 constexpr int kStageElems = kRowsPerStage * kBoxCols;            // 544 doubles = 4352 B (34 x 128 B)
 constexpr int kSmem12 = kWarpsPerCta * kStages * kStageElems * 8 + kWarpsPerCta * kStages * 8;
-constexpr int kMaxTb1 = 4;          // deepest temporal block of the 1-D kernel
-// per-warp shared memory of the temporally blocked 1-D kernel: 3 x 4 KB TMA load ring, 2 x 2 KB output staging
-// rows (TMA store), per-level row hand-over mailboxes (4 levels x 2 parities x 64 B), 3 mbarriers
-constexpr int kTbRing = 3 * 4096, kTbOut = 2 * 2048, kTbMail = kMaxTb1 * 2 * 64, kTbBars = 64;
-constexpr int kTbWarpSmem = kTbRing + kTbOut + kTbMail + kTbBars;
+// ---- temporally blocked 1-D kernel (stencil1d_tb.cu) ----
+// Rows of 512 cells (lane = 16 cells = 128 B).  Per-warp shared memory: kTbStages x 4 KB TMA load ring +
+// kTbOutBufs x 4 KB output staging rows (both 128B-swizzled, 1024-byte aligned), per-level mailboxes
+// (kMaxTb1 levels x 2 row parities x 64 B), mbarriers; rounded to a multiple of 1024.  The defaults put 4 CTAs x
+// 4 warps on an SM (4 x (56 KB + 1 KB reserved) = 228 KB); the macros exist for tuning experiments only.
+#ifndef LORA_TB_STAGES
+#define LORA_TB_STAGES 2
+#endif
+#ifndef LORA_TB_OUTBUFS
+#define LORA_TB_OUTBUFS 1
+#endif
+#ifndef LORA_TB_CTAS
+#define LORA_TB_CTAS 4
+#endif
+#ifndef LORA_TB_MAX
+#define LORA_TB_MAX 15
+#endif
+constexpr int kMaxTb1 = LORA_TB_MAX;         // deepest temporal block of the 1-D kernel
+constexpr int kDefaultTb1 = 15;              // what lora_plan_run fuses unless told otherwise (LORA_TB / set_temporal_block)
+constexpr int kTbCellsPerLane = 16;
+constexpr int kTbRowCells = 32 * kTbCellsPerLane;
+constexpr int kTbStages = LORA_TB_STAGES;    // TMA load ring depth (rows in flight per warp)
+constexpr int kTbOutBufs = LORA_TB_OUTBUFS;  // output staging rows per warp
+constexpr int kTbCtasPerSm = LORA_TB_CTAS;   // resident CTAs (of kWarpsPerCta warps) per SM the kernel is built for
+constexpr int kTbRing = kTbStages * kTbRowCells * 8, kTbOut = kTbOutBufs * kTbRowCells * 8, kTbMail = kMaxTb1 * 2 * 64,
+              kTbBars = 64;
+constexpr int kTbWarpSmem = ((kTbRing + kTbOut + kTbMail + kTbBars + 1023) / 1024) * 1024;
 constexpr int kSmem1Tb = kWarpsPerCta * kTbWarpSmem;
+static_assert(kTbStages * 8 <= kTbBars, "mbarrier area too small");
 
 // 3-D: CTA tile of 32 rows x 128 columns per plane, 8 warps x (4 rows x 128 cols); warp 0 lane 0 also drives TMA
 constexpr int k3TileRows = 32;
@@ -62,18 +85,23 @@ struct Geom1D {
     int vec4;           // 256-bit stores allowed (lo % 4 == 0 and 32-byte aligned base)
 };
 
-// temporally blocked 1-D sweep (stencil1d_tb.cu): TB launches fused, rows of 256 cells
+// temporally blocked 1-D sweep (stencil1d_tb.cu): TB launches fused.  X = PADDED coordinates (interior cell i = X 4 + i)
 struct Geom1DTB {
     const double *in;        // padded source (level 0)
     double *out;             // padded destination (level TB)
     const double *halo_src;  // padded buffer whose halo cells hold the caller's halo (buffer 0 of the ping-pong)
     long long n;             // interior length of the device array
-    long long lo, hi;        // interior range written by this launch (lo % 4 == 0)
-    int rows_per_task;       // 256-cell rows one warp sweeps
+    long long xlo, xhi;      // cells written by this launch: X in [xlo, xhi)
+    long long rho0, nrows;   // output rows (row r = cells [512 r - 4 TB, +512)) that intersect [xlo, xhi)
+    int tb;                  // time steps fused by this launch (1..kMaxTb1)
+    int rows_per_task;       // rows one warp sweeps
     long long ntasks;
     int par0;                // parity of the launch count before level 0 (0: level 0 sees the caller's halo)
     int virt_left, virt_right;  // this end of the array is an end of the global line: halo cells are virtual
-    int vec4;
+    int use_tma;             // 0: array too small for the tensor maps, everything goes through plain accesses
+    long long xcov;          // level-0 cells X >= xcov are not covered by the load map
+    long long out_off;       // the store map starts at cell out_off (= -4 TB mod 16) ...
+    long long out_rows;      // ... and covers out_rows rows of 16 cells
 };
 
 struct Geom2D {
@@ -99,7 +127,8 @@ struct Geom3D {
 };
 
 cudaError_t launch_1d(const Geom1D &g, const Weights1D &w, cudaStream_t s);
-cudaError_t launch_1d_tb(int tb, const Geom1DTB &g, const Weights1D &w, cudaStream_t s);
+cudaError_t launch_1d_tb(const CUtensorMap &imap, const CUtensorMap &omap, const Geom1DTB &g, const Weights1D &w,
+                         cudaStream_t s);
 cudaError_t launch_2d(int form, const CUtensorMap &tmap, const Geom2D &g, const Weights2D &w,
                       const WeightsDirect49 &wd, cudaStream_t s);
 cudaError_t launch_3d(int form, const CUtensorMap &tmap, const Geom3D &g, const Weights3D &w, cudaStream_t s);

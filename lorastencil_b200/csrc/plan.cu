@@ -80,6 +80,12 @@ struct lora_plan {
     Weights3D w3{};
     std::string desc;
     std::vector<std::pair<const void *, CUtensorMap>> maps;  // one TMA descriptor per source buffer
+    struct Map1D {
+        const void *ptr;
+        long long off;
+        CUtensorMap map;
+    };
+    std::vector<Map1D> maps1d;  // 1-D line viewed as rows of 16 doubles starting at cell `off`, 128B swizzle
     long long launches = 0;
     int sm_count = 148;
     int slots = 148 * 16;  // concurrently resident warp workers (1-D / 2-D) or CTAs (3-D)
@@ -151,12 +157,12 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         p->desc = d.desc;
     }
     cudaGetDevice(&p->device);
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, p->device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && sms > 0) p->sm_count = sms;
     const int warps_per_sm = (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
     if (dim == 1) {
-        p->max_tb = kMaxTb1;
+        p->max_tb = kDefaultTb1;
         if (const char *e = getenv("LORA_TB")) {
             const int v = atoi(e);
             if (v >= 1) p->max_tb = v < kMaxTb1 ? v : kMaxTb1;
@@ -205,6 +211,33 @@ static int get_tmap(lora_plan *p, const double *src, const CUtensorMap **out) {
     if (p->maps.size() >= 8) p->maps.erase(p->maps.begin());
     p->maps.emplace_back(src, m);
     *out = &p->maps.back().second;
+    return LORA_OK;
+}
+
+// 1-D temporal blocking: the padded line from cell `off` on as a (rows x 16) tensor, boxes of 32 rows = 512 cells
+// = one warp row, 128-byte swizzle (stencil1d_tb.cu).  Used for loads (off 0) and stores (off = -4 tb mod 16).
+static int get_tmap1d(lora_plan *p, const double *ptr, long long off, long long rows, CUtensorMap *out) {
+    for (auto &m : p->maps1d)
+        if (m.ptr == ptr && m.off == off) {
+            *out = m.map;
+            return LORA_OK;
+        }
+    encode_tiled_fn enc = get_encode();
+    if (!enc) return fail(LORA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    lora_plan::Map1D m;
+    m.ptr = ptr;
+    m.off = off;
+    cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {128};
+    cuuint32_t box[2] = {16, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(ptr + off), gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LORA_ERR_CUDA, "cuTensorMapEncodeTiled (1-D line) failed with CUresult %d", (int)r);
+    if (p->maps1d.size() >= 24) p->maps1d.erase(p->maps1d.begin());
+    p->maps1d.push_back(m);
+    *out = m.map;
     return LORA_OK;
 }
 
@@ -302,24 +335,40 @@ extern "C" int lora_plan_step_fused(lora_plan_t *p, const double *src, double *d
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if ((virt_lo || virt_hi) && !halo_src) return fail(LORA_ERR_ARG, "virtual halo needs halo_src");
     if (lo == hi) return LORA_OK;
-    if (lo % 4) return fail(LORA_ERR_ARG, "1-D fused range must start at a multiple of 4");
     if (reinterpret_cast<uintptr_t>(src) % 16 || reinterpret_cast<uintptr_t>(dst) % 16)
         return fail(LORA_ERR_ARG, "buffers must be 16-byte aligned");
-    Geom1DTB g;
+    const long long P = p->dims[0] + 8;  // padded length
+    Geom1DTB g{};
     g.in = src;
     g.out = dst;
     g.halo_src = halo_src ? halo_src : src;
     g.n = p->dims[0];
-    g.lo = lo;
-    g.hi = hi;
-    const long long rows = (hi - lo + 255) / 256;
-    g.rows_per_task = (int)pick_len(rows, 1, p->slots, 128, 8);
-    g.ntasks = (rows + g.rows_per_task - 1) / g.rows_per_task;
+    g.xlo = 4 + lo;
+    g.xhi = 4 + hi;
+    // output row r (level tb) covers padded cells [512 r - 4 tb, 512 r - 4 tb + 512)
+    g.rho0 = (g.xlo + 4 * tb) / kTbRowCells;
+    g.nrows = (g.xhi - 1 + 4 * tb) / kTbRowCells - g.rho0 + 1;
+    g.rows_per_task = (int)pick_len(g.nrows, 1, (long long)p->sm_count * kTbCtasPerSm * kWarpsPerCta, 128, 8);
+    g.ntasks = (g.nrows + g.rows_per_task - 1) / g.rows_per_task;
+    g.tb = tb;
     g.par0 = launches_before & 1;
     g.virt_left = virt_lo ? 1 : 0;
     g.virt_right = virt_hi ? 1 : 0;
-    g.vec4 = reinterpret_cast<uintptr_t>(dst) % 32 == 0;
-    cudaError_t e = launch_1d_tb(tb, g, p->w1, static_cast<cudaStream_t>(stream));
+    g.out_off = (16 - (4 * tb) % 16) % 16;
+    const long long in_rows = P / 16, out_rows = (P - g.out_off) / 16;
+    g.use_tma = (in_rows >= 1 && out_rows >= 1) ? 1 : 0;
+    g.xcov = g.use_tma ? in_rows * 16 : 0;
+    g.out_rows = out_rows;
+    CUtensorMap imap, omap;
+    std::memset(&imap, 0, sizeof imap);
+    std::memset(&omap, 0, sizeof omap);
+    if (g.use_tma) {
+        int rc = get_tmap1d(p, src, 0, in_rows, &imap);
+        if (rc) return rc;
+        rc = get_tmap1d(p, dst, g.out_off, out_rows, &omap);
+        if (rc) return rc;
+    }
+    cudaError_t e = launch_1d_tb(imap, omap, g, p->w1, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     p->launches++;
     return LORA_OK;
@@ -347,20 +396,25 @@ static std::vector<int> temporal_schedule(int times, int max_tb) {
     return tbs;
 }
 
+// `times` launches of a 1-D plan as fused sweeps: launch k reads buf[k%2]; the halo every level sees on a virtual
+// side is the caller's halo (it lives in buf0, whose halo nothing writes) at even times and zero at odd times
+static int run_fused_1d(lora_plan *p, double *buf0, double *buf1, int times, int virt_lo, int virt_hi, void *stream) {
+    double *buf[2] = {buf0, buf1};
+    const std::vector<int> tbs = temporal_schedule(times, p->max_tb);
+    int done = 0;
+    for (size_t k = 0; k < tbs.size(); k++) {
+        int rc = lora_plan_step_fused(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tbs[k], done, virt_lo, virt_hi,
+                                      stream);
+        if (rc) return rc;
+        done += tbs[k];
+    }
+    return LORA_OK;
+}
+
 extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int times, void *stream) {
     if (!p || !buf0 || !buf1) return fail(LORA_ERR_ARG, "null argument");
+    if (p->dim == 1 && p->max_tb > 1 && times > 1) return run_fused_1d(p, buf0, buf1, times, 1, 1, stream);
     double *buf[2] = {buf0, buf1};
-    if (p->dim == 1 && p->max_tb > 1 && times > 1) {
-        // fused: launch k reads buf[k%2]; the halo every level sees is virtual (caller's halo lives in buf0)
-        const std::vector<int> tbs = temporal_schedule(times, p->max_tb);
-        int done = 0;
-        for (size_t k = 0; k < tbs.size(); k++) {
-            int rc = lora_plan_step_fused(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tbs[k], done, 1, 1, stream);
-            if (rc) return rc;
-            done += tbs[k];
-        }
-        return LORA_OK;
-    }
     for (int i = 0; i < times; i++) {
         int rc = lora_plan_step(p, buf[i % 2], buf[(i + 1) % 2], 0, p->dims[0], stream);
         if (rc) return rc;
@@ -429,8 +483,9 @@ extern "C" int lora_effective_weights(int shape, int mode, const double *params,
 // ---------------------------------------------------------------------------------------------
 static int g_verbose = -1;
 static double g_loop_ms = 0, g_total_ms = 0;
+static int g_chunks = 1;  // chunks the last drop-in call was cut into (1-D copy/compute overlap)
 static std::mutex g_ws_mutex;
-static double *g_ws[2] = {nullptr, nullptr};
+static std::vector<double *> g_ws;  // device workspace the drop-in operators cache between calls (equal-sized buffers)
 static size_t g_ws_bytes = 0;
 static int g_ws_device = -1;
 
@@ -453,15 +508,19 @@ static bool verbose() {
 
 extern "C" double lora_last_loop_ms(void) { return g_loop_ms; }
 extern "C" double lora_last_total_ms(void) { return g_total_ms; }
+extern "C" int lora_last_chunks(void) { return g_chunks; }
+
+static void ws_free_locked() {
+    for (double *b : g_ws)
+        if (b) cudaFree(b);
+    g_ws.clear();
+    g_ws_bytes = 0;
+    g_ws_device = -1;
+}
 
 extern "C" void lora_release_workspace(void) {
     std::lock_guard<std::mutex> lk(g_ws_mutex);
-    for (auto &b : g_ws) {
-        if (b) cudaFree(b);
-        b = nullptr;
-    }
-    g_ws_bytes = 0;
-    g_ws_device = -1;
+    ws_free_locked();
 }
 
 // the reference's CUDA_CHECK: report and exit(1) (src/2d/2d_utils.h:22-36)
@@ -486,27 +545,153 @@ extern "C" void lora_release_workspace(void) {
     exit(1);
 }
 
+// at least `count` cached device buffers of at least `bytes` each on the current device (caller holds g_ws_mutex)
+static void ws_reserve(size_t count, size_t bytes) {
+    int dev = 0;
+    CU_DIE(cudaGetDevice(&dev));
+    if (g_ws_device != dev || g_ws_bytes < bytes) ws_free_locked();
+    if (g_ws.empty()) {
+        g_ws_bytes = bytes + bytes / 8;  // slack: a slightly larger follow-up call does not reallocate everything
+        g_ws_device = dev;
+    }
+    while (g_ws.size() < count) {
+        double *b = nullptr;
+        CU_DIE(cudaMalloc(&b, g_ws_bytes));
+        g_ws.push_back(b);
+    }
+}
+
+static void print_banner(int shape, int dim, const long long *dims, int times, double loop_us) {
+    double cells = 1;
+    for (int i = 0; i < dim; i++) cells *= (double)dims[i];
+    printf("LoRAStencil(%s): \n", shape_banner(shape));
+    printf("Time = %lld[ms]\n", (long long)(loop_us / 1e3));
+    printf("GStencil/s = %f\n", cells * times * shape_artifact_k(shape) / (loop_us / 1e6) / 1e9);
+    fflush(stdout);
+}
+
+// 1-D host operator, chunked and copy-overlapped.  A cell's value after `times` launches depends on 4 * times
+// cells either side only, so a long line is cut into K chunks that each carry a ghost margin of G = 4 * times
+// cells and run ALL their launches independently (bit-identical: the same operations on the same operands).
+// Chunk c+2's H2D copy, the launches of chunks c and c+1 and chunk c-1's D2H copy then overlap instead of
+// H2D -> launches -> D2H running back to back.  The ghost margins cost 2 G / chunk of redundant work (0.02 % for
+// 2^28 points x 1000 launches).  Sides that are ends of the line keep the reference's halo semantics (S2) through
+// the kernel's virtual halo.  Returns false when chunking does not pay (short line, wide cone): the caller then
+// takes the plain path.  LORA_CHUNKS=0 disables, LORA_CHUNKS=k forces k chunks.
+static bool run_host_1d_chunked(int shape, int mode, const double *in, double *out, const double *params, int times,
+                                long long n) {
+    const long long G = 4LL * times;
+    long long K = n / (16LL << 20);  // chunks of >= 16 M cells keep the sweeps efficient; 8-16 chunks measured best
+    if (K > 12) K = 12;
+    bool forced = false;
+    if (const char *e = getenv("LORA_CHUNKS")) {
+        K = atoll(e);
+        forced = true;
+    }
+    if (times < 1 || K < 2 || K > n) return false;
+    const long long C = ((n + K - 1) / K + 511) / 512 * 512;  // chunk length, whole kernel rows
+    if (!forced && G > C / 16) return false;
+    K = (n + C - 1) / C;
+    if (K < 2) return false;
+
+    // Two chunks compute at a time (two launch streams): the tail of one chunk's sweep, where SMs run dry, is
+    // back-filled by the other chunk's CTAs.  Buffer pairs in flight: two computing, one loading, one draining.
+    constexpr int NCS = 2, NP = NCS + 2;
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    ws_reserve(2 * NP, (size_t)(C + 2 * G + 8) * sizeof(double));
+    cudaStream_t s_in, s_out, s_comp[NCS];
+    CU_DIE(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    CU_DIE(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (auto &st : s_comp) CU_DIE(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> in_done(K), comp_done(K), out_done(K);
+    std::vector<lora_plan *> plans(K, nullptr);
+    for (long long c = 0; c < K; c++) {
+        CU_DIE(cudaEventCreateWithFlags(&in_done[c], cudaEventDisableTiming));
+        CU_DIE(cudaEventCreateWithFlags(&comp_done[c], cudaEventDisableTiming));
+        CU_DIE(cudaEventCreateWithFlags(&out_done[c], cudaEventDisableTiming));
+    }
+    cudaEvent_t t_first, t_last;
+    CU_DIE(cudaEventCreate(&t_first));
+    CU_DIE(cudaEventCreate(&t_last));
+    for (long long c = 0; c < K; c++) {
+        const long long lo = c * C, hi = (lo + C < n) ? lo + C : n;
+        const long long gl = G < lo ? G : lo, gr = G < n - hi ? G : n - hi;
+        const long long nloc = (hi + gr) - (lo - gl);        // interior length of the chunk's own padded array
+        const int virt_lo = (lo - gl == 0), virt_hi = (hi + gr == n);
+        double *b0 = g_ws[2 * (c % NP)], *b1 = g_ws[2 * (c % NP) + 1];
+        const size_t bytes = (size_t)(nloc + 8) * sizeof(double);
+        cudaStream_t sc = s_comp[c % NCS];
+        if (c >= NP) CU_DIE(cudaStreamWaitEvent(s_in, out_done[c - NP], 0));  // the pair's previous tenant has drained
+        // S2 per chunk: buffer 0 <- the padded input segment, buffer 1 <- zeros
+        CU_DIE(cudaMemcpyAsync(b0, in + (lo - gl), bytes, cudaMemcpyHostToDevice, s_in));
+        CU_DIE(cudaMemsetAsync(b1, 0, bytes, s_in));
+        CU_DIE(cudaEventRecord(in_done[c], s_in));
+
+        const long long d[1] = {nloc};
+        if (lora_plan_create(&plans[c], shape, mode, params, d) != LORA_OK) die_plan("plan");
+        CU_DIE(cudaStreamWaitEvent(sc, in_done[c], 0));
+        if (c == 0) CU_DIE(cudaEventRecord(t_first, sc));
+        if (run_fused_1d(plans[c], b0, b1, times, virt_lo, virt_hi, sc) != LORA_OK) die_plan("launch");
+        CU_DIE(cudaEventRecord(comp_done[c], sc));
+
+        // S3: the chunk's own cells of buffer times%2; the first / last chunk also return the line's halo cells
+        // (the reference copies back n + 7 doubles, src/1d/gpu_1r.cu:134)
+        const double *res = (times % 2 == 0) ? b0 : b1;
+        long long src_off = 4 + gl, dst_off = 4 + lo, cnt = hi - lo;
+        if (c == 0) {
+            src_off -= 4;
+            dst_off -= 4;
+            cnt += 4;
+        }
+        if (c == K - 1) cnt += 3;
+        CU_DIE(cudaStreamWaitEvent(s_out, comp_done[c], 0));
+        if (c == K - 1) {
+            if (K >= 2) CU_DIE(cudaStreamWaitEvent(s_out, comp_done[K - 2], 0));
+            CU_DIE(cudaEventRecord(t_last, s_out));  // every chunk's launches have finished
+        }
+        CU_DIE(cudaMemcpyAsync(out + dst_off, res + src_off, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        CU_DIE(cudaEventRecord(out_done[c], s_out));
+    }
+    CU_DIE(cudaStreamSynchronize(s_out));
+    for (auto &st : s_comp) CU_DIE(cudaStreamSynchronize(st));
+    CU_DIE(cudaStreamSynchronize(s_in));
+    // the reference's timed region is its launch loop (src/1d/gpu_1r.cu:118-126): here first launch -> last launch
+    // done, which also contains whatever time the launches spent waiting for a chunk's H2D copy
+    float ms = 0;
+    CU_DIE(cudaEventElapsedTime(&ms, t_first, t_last));
+    for (long long c = 0; c < K; c++) {
+        lora_plan_destroy(plans[c]);
+        cudaEventDestroy(in_done[c]);
+        cudaEventDestroy(comp_done[c]);
+        cudaEventDestroy(out_done[c]);
+    }
+    cudaEventDestroy(t_first);
+    cudaEventDestroy(t_last);
+    cudaStreamDestroy(s_in);
+    cudaStreamDestroy(s_out);
+    for (auto &st : s_comp) cudaStreamDestroy(st);
+    g_loop_ms = ms;
+    g_chunks = (int)K;
+    return true;
+}
+
 extern "C" void lora_gpu_run_host(int shape, int mode, const double *in, double *out, const double *params, int times,
                                   const long long *dims) {
     using clk = std::chrono::steady_clock;
     const clk::time_point t_begin = clk::now();
+    g_chunks = 1;
+    if (shape_dim(shape) == 1 && dims && dims[0] > 0 && in && out &&
+        run_host_1d_chunked(shape, mode, in, out, params, times, dims[0])) {
+        if (verbose()) print_banner(shape, 1, dims, times, g_loop_ms * 1e3);
+        g_total_ms = std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t_begin).count() / 1e3;
+        return;
+    }
     lora_plan *p = nullptr;
     if (lora_plan_create(&p, shape, mode, params, dims) != LORA_OK) die_plan("plan");
     const size_t bytes = (size_t)p->elems * sizeof(double);
 
     std::lock_guard<std::mutex> lk(g_ws_mutex);
-    int dev = 0;
-    CU_DIE(cudaGetDevice(&dev));
-    if (g_ws_bytes < bytes || g_ws_device != dev) {
-        for (auto &b : g_ws) {
-            if (b) cudaFree(b);
-            b = nullptr;
-        }
-        CU_DIE(cudaMalloc(&g_ws[0], bytes));
-        CU_DIE(cudaMalloc(&g_ws[1], bytes));
-        g_ws_bytes = bytes;
-        g_ws_device = dev;
-    }
+    ws_reserve(2, bytes);
     // S2: buffer 0 <- the whole padded input (halo included), buffer 1 <- zeros (src/2d/gpu.cu:396-400)
     CU_DIE(cudaMemcpy(g_ws[0], in, bytes, cudaMemcpyHostToDevice));
     CU_DIE(cudaMemset(g_ws[1], 0, bytes));
@@ -519,14 +704,7 @@ extern "C" void lora_gpu_run_host(int shape, int mode, const double *in, double 
     const clk::time_point t1 = clk::now();
     const long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
     g_loop_ms = us / 1e3;
-    if (verbose()) {
-        double cells = 1;
-        for (int i = 0; i < p->dim; i++) cells *= (double)p->dims[i];
-        printf("LoRAStencil(%s): \n", shape_banner(shape));
-        printf("Time = %lld[ms]\n", (long long)std::chrono::duration_cast<std::chrono::milliseconds>(t1 - t0).count());
-        printf("GStencil/s = %f\n", cells * times * shape_artifact_k(shape) / (us / 1e6) / 1e9);
-        fflush(stdout);
-    }
+    if (verbose()) print_banner(shape, p->dim, p->dims, times, (double)us);
     // S3: the whole padded buffer times%2 comes back; 1-D leaves the last double alone (src/1d/gpu_1r.cu:134)
     const size_t back = (p->dim == 1) ? bytes - sizeof(double) : bytes;
     CU_DIE(cudaMemcpy(out, g_ws[times % 2 == 0 ? 0 : 1], back, cudaMemcpyDeviceToHost));

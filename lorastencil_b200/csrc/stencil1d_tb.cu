@@ -3,21 +3,25 @@
 // living in registers only.  New functionality: the reference has no temporal blocking (it only counts
 // its composite 9-tap kernels as 3 / 2 steps, src/1d/gpu_1r.cu:132).
 //
-// Mapping (one warp = one independent worker, as in stencil1d.cu):
-//   * the line is cut into rows of 256 cells, lane l owns 8 consecutive cells of a row;
-//   * level s (the grid after s of the TB launches) is held SKEWED: row j of level s covers cells
-//     [B + 256 j - 4 s, +256).  With that skew the 16-cell window a lane needs from level s-1 is exactly
-//     lane l-1's 8 cells followed by its own 8 cells, so one level costs 8 FP64 warp shuffles (16 SHFL.32)
-//     + 72 DFMA per lane, no shared-memory round trip, and a row never needs data from the row after it;
-//   * lane 0 takes lane 31's cells of the previous row from a 64-byte per-level mailbox in shared memory;
-//   * level 0 arrives through the warp's private TMA ring (cp.async.bulk, 2 rows = 4 KB per stage); level TB
-//     leaves through a 2 KB staging row and a TMA store (cp.async.bulk shared -> global), row-aligned because
-//     B = s0 + 4 TB makes the final skew vanish;
-//   * a lane's 8 cells are 64 contiguous bytes, i.e. a 64-byte lane stride in shared memory, which is a 4-way
-//     bank conflict for plain 128-bit accesses.  Lanes therefore touch their four 16-byte pieces in a rotated
-//     order (piece (k + lane/2) mod 4 in instruction k): every quarter-warp then covers all 8 bank groups, the
-//     access is conflict-free, and a 2-level select network un-rotates the registers (ALU pipe, which is idle).
-//     The LSU data pipe is this kernel's bottleneck (profiles/), so wavefronts are what is being saved.
+// The kernel is built to be bound by the FP64 pipe (9 DFMA per cell per level is the floor for general
+// weights), i.e. everything else has to cost (much) less than one issue slot per DFMA:
+//
+//   * one warp = one independent worker with a private TMA ring; the line is cut, in PADDED coordinates X,
+//     into rows of 512 cells [512 r, 512 r + 512), lane l owns 16 consecutive cells (128 bytes) of a row;
+//   * level s (the line after s of the TB launches) is held SKEWED by -4 s cells: the 24-cell window a
+//     lane needs from level s-1 is lane l-1's last 8 cells followed by its own 16, so a level costs 8 FP64
+//     warp shuffles (16 SHFL.32) against 144 DFMA per lane, never a shared-memory round trip, and a row
+//     never needs the row after it.  The shuffle is circular: lane 0 receives lane 31's cells, which are
+//     what it needs one row LATER -- it parks them in a private 64-byte mailbox per level and row parity (one
+//     thread writes and reads it, so there is no cross-lane synchronisation);
+//   * level 0 arrives by cp.async.bulk.tensor.2d through a tensor map that views the line as rows of 16
+//     doubles with the 128-byte hardware swizzle: a lane's 128 contiguous bytes are then read with eight
+//     conflict-free 128-bit LDS (16-byte chunk k sits at chunk k ^ (lane & 7)) -- no padding, no register
+//     un-shuffling;
+//   * level TB leaves through a swizzled 4 KB staging row and a tensor-map TMA store.  The skew moves the
+//     output row to X - 4 TB, so the store map's base is shifted by (-4 TB mod 16) cells; whatever the maps
+//     cannot reach (the first / last few cells of the array, partial rows of a sub-range) goes through plain
+//     predicated global accesses on the rare edge path.
 //
 // Reference semantics (S2) under fusion: launch i of the reference sees the caller's
 // halo when i is even and zeros when i is odd.  Inside a fused sweep the halo cells of every level are
@@ -30,228 +34,181 @@ namespace lora {
 
 namespace {
 
-constexpr int kTbRow = 256;                 // cells per row
-constexpr int kTbStageRows = 2;             // rows per bulk copy
-constexpr int kTbStage = kTbStageRows * kTbRow;  // 512 doubles <= kStageElems
+constexpr int kCpl = kTbCellsPerLane;  // 16
+constexpr int kRow = kTbRowCells;      // 512
+constexpr unsigned kFull = 0xffffffffu;
 
-// piece order used by lane `lane` for its k-th 128-bit access to a 64-byte chunk: conflict-free in shared memory
-__device__ __forceinline__ int rot_of(int lane) { return (lane >> 1) & 3; }
-
-// out[j] = in[(j - rot) & 3] for 16-byte pieces (2-level barrel of selects)
-__device__ __forceinline__ void unrotate(const double2 (&in)[4], int rot, double2 (&out)[4]) {
-    double2 a[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        a[j].x = (rot & 1) ? in[(j + 3) & 3].x : in[j].x;
-        a[j].y = (rot & 1) ? in[(j + 3) & 3].y : in[j].y;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        out[j].x = (rot & 2) ? a[(j + 2) & 3].x : a[j].x;
-        out[j].y = (rot & 2) ? a[(j + 2) & 3].y : a[j].y;
-    }
-}
-
-// lane's 8 cells (64 contiguous bytes at chunk) -> registers, conflict-free
-__device__ __forceinline__ void load_rotated(const double *chunk, int lane, double (&cur)[8]) {
-    const int rot = rot_of(lane);
-    double2 r[4], pc[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) r[k] = *reinterpret_cast<const double2 *>(chunk + 2 * ((k + rot) & 3));
-    unrotate(r, rot, pc);  // r[k] holds piece (k + rot) & 3  =>  piece j = r[(j - rot) & 3]
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        cur[2 * j] = pc[j].x;
-        cur[2 * j + 1] = pc[j].y;
-    }
-}
-
-// registers -> lane's 64-byte chunk of the staging row, conflict-free
-__device__ __forceinline__ void store_rotated(double *chunk, int lane, const double (&cur)[8]) {
-    const int rot = rot_of(lane);
-    double2 pc[4], q[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) pc[j] = make_double2(cur[2 * j], cur[2 * j + 1]);
-    // instruction k writes piece (k + rot) & 3: q[k] = pc[(k + rot) & 3] = pc[(k - (4 - rot)) & 3]
-    unrotate(pc, (4 - rot) & 3, q);
-#pragma unroll
-    for (int k = 0; k < 4; k++) *reinterpret_cast<double2 *>(chunk + 2 * ((k + rot) & 3)) = q[k];
-}
-
-// virtual halo of one level: cells -4..-1 and n..n+3 take (level time even ? caller's halo : 0)
-__device__ __forceinline__ void fix_halo(double (&v)[8], long long p, int level, const Geom1DTB &g) {
+// virtual halo of one level: padded cells 0..3 and n+4..n+7 take (level time even ? caller's halo : 0)
+__device__ __forceinline__ void fix_halo(double (&v)[kCpl], long long X, int level, const Geom1DTB &g) {
     const bool use_h = ((g.par0 + level) & 1) == 0;
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const long long x = p + q;
-        const bool in_left = g.virt_left && x >= -4 && x < 0;
-        const bool in_right = g.virt_right && x >= g.n && x < g.n + 4;
-        if (in_left || in_right) v[q] = use_h ? g.halo_src[x + 4] : 0.0;
+    for (int q = 0; q < kCpl; q++) {
+        const long long x = X + q;
+        const bool in_left = g.virt_left && x >= 0 && x < 4;
+        const bool in_right = g.virt_right && x >= g.n + 4 && x < g.n + 8;
+        if (in_left || in_right) v[q] = use_h ? g.halo_src[x] : 0.0;
     }
 }
 
-// one row through all TB levels.  `p` = interior coordinate of this lane's first level-0 cell.
-template <int TB, bool FIX>
-__device__ __forceinline__ void sweep_row(const double *rowp, double *mailbox, int i, int lane, long long p,
-                                          const Geom1DTB &g, const Weights1D &w, double (&cur)[8]) {
-    load_rotated(rowp, lane, cur);
-    if (FIX) fix_halo(cur, p, 0, g);
+// One row through all TB levels.  X = padded coordinate of this lane's first level-0 cell; on return cur[]
+// holds level TB of the cells X - 4 TB .. X - 4 TB + 15.
+template <bool FIX>
+__device__ __forceinline__ void sweep_row(const unsigned char *stage, double *mailbox, int par, int lane, long long X,
+                                          const Geom1DTB &g, const Weights1D &w, double (&cur)[kCpl]) {
+    {
+        const unsigned char *rowp = stage + lane * 128;
+        const int sw = lane & 7;
 #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double2 v = *reinterpret_cast<const double2 *>(rowp + ((k ^ sw) << 4));
+            cur[2 * k] = v.x;
+            cur[2 * k + 1] = v.y;
+        }
+    }
+    if (FIX) {
+        // cells the load map does not cover (the tail of the array; everything when there is no map)
+#pragma unroll
+        for (int q = 0; q < kCpl; q++) {
+            const long long x = X + q;
+            if (x >= g.xcov || x < 0) cur[q] = (x >= 0 && x < g.n + 8) ? g.in[x] : 0.0;
+        }
+        fix_halo(cur, X, 0, g);
+    }
+    const int src_lane = (lane + 31) & 31;
+    const int TB = g.tb;
+    // the level loop is deliberately NOT unrolled: one level is ~200 instructions, a fully unrolled row would
+    // not fit the instruction cache (measured: 1349 -> 1431 GStencil/s at TB = 8 when rolled)
+#pragma unroll 1
     for (int s = 1; s <= TB; s++) {
-        // mailbox[level][row parity][8]: lane 31 posts its cells for lane 0 of the next row
-        double *mb_wr = mailbox + ((s - 1) * 2 + (i & 1)) * 8;
-        const double *mb_rd = mailbox + ((s - 1) * 2 + ((i + 1) & 1)) * 8;
-        if (lane == 31) {
+        double win[kCpl + 8];
 #pragma unroll
-            for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2 *>(mb_wr + q) = make_double2(cur[q], cur[q + 1]);
+        for (int q = 0; q < 8; q++) win[q] = __shfl_sync(kFull, cur[kCpl - 8 + q], src_lane);
+        if (lane == 0) {
+            // lane 31's cells belong to the NEXT row's lane 0: park them, take what was parked one row ago
+            // (two mailboxes per level alternate by row parity, so the load can land in the window registers)
+            double *mb_wr = mailbox + ((s - 1) * 2 + par) * 8;
+            const double *mb_rd = mailbox + ((s - 1) * 2 + (par ^ 1)) * 8;
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2 *>(mb_wr + q) = make_double2(win[q], win[q + 1]);
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(mb_rd + q);
+                win[q] = t.x;
+                win[q + 1] = t.y;
+            }
         }
-        double win[16];
 #pragma unroll
-        for (int q = 0; q < 8; q += 2) {
-            const double2 m = *reinterpret_cast<const double2 *>(mb_rd + q);  // broadcast read, used by lane 0 only
-            const double a = __shfl_up_sync(0xffffffffu, cur[q], 1);
-            const double b = __shfl_up_sync(0xffffffffu, cur[q + 1], 1);
-            win[q] = lane == 0 ? m.x : a;
-            win[q + 1] = lane == 0 ? m.y : b;
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) win[8 + q] = cur[q];
+        for (int q = 0; q < kCpl; q++) win[8 + q] = cur[q];
         // level s, cell q sits at (level s-1 position of win[0]) + 4 + q: taps win[q .. q+8]
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+        for (int q = 0; q < kCpl; q++) {
             double a = w.w[0] * win[q];
 #pragma unroll
             for (int k = 1; k < 9; k++) a = fma(w.w[k], win[q + k], a);
             cur[q] = a;
         }
-        p -= 4;
-        if (FIX && s < TB) fix_halo(cur, p, s, g);
+        X -= 4;
+        if (FIX && s < TB) fix_halo(cur, X, s, g);
     }
 }
 
-template <int TB>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 3)
-k_stencil1d_tb(const __grid_constant__ Geom1DTB g, const __grid_constant__ Weights1D w) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, kTbCtasPerSm)
+k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__ CUtensorMap omap,
+               const __grid_constant__ Geom1DTB g, const __grid_constant__ Weights1D w) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (task >= g.ntasks) return;
+    if (task >= g.ntasks) return;  // warps never synchronise with each other
+    const int TB = g.tb;
 
     unsigned char *wsm = smem_raw + warp * kTbWarpSmem;
-    double *ring = reinterpret_cast<double *>(wsm);                            // 3 stages x 512 doubles
-    double *outbuf = reinterpret_cast<double *>(wsm + kTbRing);                // 2 staging rows x 256 doubles
+    unsigned char *ring = wsm;                                                 // kTbStages x 4 KB, swizzled rows
+    unsigned char *outbuf = wsm + kTbRing;                                     // 2 staging rows x 4 KB, swizzled
     double *mailbox = reinterpret_cast<double *>(wsm + kTbRing + kTbOut);      // [level][row parity][8]
     uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + kTbRing + kTbOut + kTbMail);
 
-    const long long s0 = g.lo + task * (long long)g.rows_per_task * kTbRow;  // first output cell (interior coords)
-    const long long len = min((long long)g.rows_per_task * kTbRow, g.hi - s0);
-    const int J = (int)((len + kTbRow - 1) / kTbRow);  // output rows; iteration i handles row j = i - 1
-    const int niter = J + 1;
-    const int nst = (niter + kTbStageRows - 1) / kTbStageRows;
-    const long long task_start = s0 + 4 * TB - kTbRow;  // interior coordinate of level-0 row -1, lane 0
-    const long long padded_len = g.n + 8;
+    const long long rfirst = g.rho0 + task * (long long)g.rows_per_task;       // first output row of the task
+    const int J = (int)min((long long)g.rows_per_task, g.rho0 + g.nrows - rfirst);
+    const int niter = J + 1;  // iteration 0 is the warm-up row rfirst - 1: it only fills the mailboxes
 
     auto issue = [&](int k, int slot) {
-        const long long start = task_start + 4 + (long long)k * kTbStage;  // padded index of the stage
-        const long long skip = start < 0 ? -start : 0;                     // cells left of the array: never needed
-        const long long cnt = min((long long)kTbStage, padded_len - start) - skip;
-        if (cnt <= 0) {
+        if (g.use_tma) {
+            mbar_arrive_expect_tx(&bars[slot], kRow * 8);
+            tma_load_2d(ring + slot * (kRow * 8), &imap, 0, (int)(32 * (rfirst - 1 + k)), &bars[slot]);
+        } else {
             mbar_arrive(&bars[slot]);
-            return;
         }
-        const long long even = cnt & ~1LL;
-        mbar_arrive_expect_tx(&bars[slot], (uint32_t)(even * 8));
-        if (even > 0)
-            tma_load_1d(ring + slot * kTbStage + skip, g.in + start + skip, (uint32_t)(even * 8), &bars[slot]);
-        if (cnt != even) ring[slot * kTbStage + skip + even] = g.in[start + skip + even];
     };
 
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < kStages; k++) mbar_init(&bars[k], 1);
+        for (int k = 0; k < kTbStages; k++) mbar_init(&bars[k], 1);
         fence_barrier_init();
 #pragma unroll
-        for (int k = 0; k < kStages; k++)
-            if (k < nst) issue(k, k);
+        for (int k = 0; k < kTbStages; k++)
+            if (k < niter) issue(k, k);
     }
     __syncwarp();
 
-    const long long end = s0 + len;
     for (int i = 0; i < niter; i++) {
-        const int st = i / kTbStageRows, rr = i % kTbStageRows, slot = st % kStages;
-        if (rr == 0) mbar_wait(&bars[slot], (st / kStages) & 1);
-        const double *rowp = ring + slot * kTbStage + rr * kTbRow + 8 * lane;
-        const long long p0 = task_start + (long long)i * kTbRow;  // interior coordinate of lane 0's first level-0 cell
-        // rows whose skewed levels can touch a virtual halo zone take the (rare) patched path; warp-uniform
-        const bool edge = (g.virt_left && p0 - 4 * TB < 0) || (g.virt_right && p0 + kTbRow > g.n);
-        double cur[8];
+        const int slot = i % kTbStages;
+        mbar_wait(&bars[slot], (i / kTbStages) & 1);
+        const long long X0 = (rfirst - 1 + i) * (long long)kRow;  // padded coordinate of lane 0's first level-0 cell
+        // rows with cells the load map cannot reach, or whose skewed levels touch a virtual halo zone, take the
+        // (rare) patched path; warp-uniform
+        const bool edge = (X0 + kRow >= g.xcov) || (g.virt_left && X0 - 4 * (TB - 1) < 4) ||
+                          (g.virt_right && X0 + kRow > g.n + 4);
+        double cur[kCpl];
         if (edge)
-            sweep_row<TB, true>(rowp, mailbox, i, lane, p0 + 8 * lane, g, w, cur);
+            sweep_row<true>(ring + slot * (kRow * 8), mailbox, i & 1, lane, X0 + kCpl * lane, g, w, cur);
         else
-            sweep_row<TB, false>(rowp, mailbox, i, lane, p0 + 8 * lane, g, w, cur);
-        __syncwarp();  // mailbox hand-over between consecutive rows; every lane has consumed the stage row
+            sweep_row<false>(ring + slot * (kRow * 8), mailbox, i & 1, lane, X0 + kCpl * lane, g, w, cur);
+        __syncwarp();  // every lane has consumed the stage
+        if (lane == 0 && i + kTbStages < niter) issue(i + kTbStages, slot);
 
-        // level TB, row j = i - 1: cells s0 + 256 j + 8 lane .. +7
         if (i >= 1) {
-            const long long prow = p0 - 4 * TB;  // first cell of the output row
-            if (prow + kTbRow <= end) {
-                // whole row: stage it (conflict-free STS) and let the TMA write the 2 KB line segment
-                double *stage = outbuf + (i & 1) * kTbRow;
-                if (lane == 0) tma_store_wait_read<1>();  // the store issued from this staging row two rows ago has drained
+            const long long Xr = X0 - 4 * TB;  // first cell of the output row (level TB)
+            const long long rc = (Xr - g.out_off) >> 4;  // row of 16 in the store map (exact when Xr >= out_off)
+            if (g.use_tma && Xr >= g.xlo && Xr + kRow <= g.xhi && Xr >= g.out_off && rc + 32 <= g.out_rows) {
+                // whole row: stage it (conflict-free STS) and let the TMA write the 4 KB line segment
+                unsigned char *stage = outbuf + (i % kTbOutBufs) * (kRow * 8);
+                if (lane == 0) tma_store_wait_read<kTbOutBufs - 1>();  // the last store issued from this staging row has drained
                 __syncwarp();
-                store_rotated(stage + 8 * lane, lane, cur);
+                unsigned char *rowp = stage + lane * 128;
+                const int sw = lane & 7;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    *reinterpret_cast<double2 *>(rowp + ((k ^ sw) << 4)) = make_double2(cur[2 * k], cur[2 * k + 1]);
                 fence_proxy_async();  // generic-proxy writes -> visible to the async proxy
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_1d(g.out + 4 + prow, stage, kTbRow * 8);
+                    tma_store_2d(&omap, stage, 0, (int)rc);
                     tma_store_commit();
                 }
             } else {
-                const long long p = prow + 8 * lane;
-                double *o = g.out + 4 + p;
+                const long long x = Xr + kCpl * lane;
 #pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (p + q < end) o[q] = cur[q];
+                for (int q = 0; q < kCpl; q++)
+                    if (x + q >= g.xlo && x + q < g.xhi) g.out[x + q] = cur[q];
             }
         }
-        if (rr == kTbStageRows - 1 || i == niter - 1) {
-            if (lane == 0 && st + kStages < nst) issue(st + kStages, slot);
-        }
     }
-    if (lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last TMA stores
-}
-
-template <int TB>
-cudaError_t launch_tb(const Geom1DTB &g, const Weights1D &w, cudaStream_t s) {
-    const long long ctas = (g.ntasks + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_stencil1d_tb<TB><<<(unsigned)ctas, 32 * kWarpsPerCta, kSmem1Tb, s>>>(g, w);
-    return cudaGetLastError();
-}
-
-template <int TB>
-cudaError_t opt_in_tb() {
-    return cudaFuncSetAttribute(k_stencil1d_tb<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1Tb);
+    if (lane == 0) tma_store_wait_all();  // shared memory must outlive the last TMA stores
 }
 
 }  // namespace
 
 cudaError_t kernels_init_1d_tb() {
-    cudaError_t e;
-    if ((e = opt_in_tb<1>()) != cudaSuccess) return e;
-    if ((e = opt_in_tb<2>()) != cudaSuccess) return e;
-    if ((e = opt_in_tb<3>()) != cudaSuccess) return e;
-    return opt_in_tb<4>();
+    return cudaFuncSetAttribute(k_stencil1d_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1Tb);
 }
 
-cudaError_t launch_1d_tb(int tb, const Geom1DTB &g, const Weights1D &w, cudaStream_t s) {
+cudaError_t launch_1d_tb(const CUtensorMap &imap, const CUtensorMap &omap, const Geom1DTB &g, const Weights1D &w,
+                         cudaStream_t s) {
     if (g.ntasks <= 0) return cudaSuccess;
-    switch (tb) {
-        case 1: return launch_tb<1>(g, w, s);
-        case 2: return launch_tb<2>(g, w, s);
-        case 3: return launch_tb<3>(g, w, s);
-        case 4: return launch_tb<4>(g, w, s);
-        default: return cudaErrorInvalidValue;
-    }
+    if (g.tb < 1 || g.tb > kMaxTb1) return cudaErrorInvalidValue;
+    const long long ctas = (g.ntasks + kWarpsPerCta - 1) / kWarpsPerCta;
+    k_stencil1d_tb<<<(unsigned)ctas, 32 * kWarpsPerCta, kSmem1Tb, s>>>(imap, omap, g, w);
+    return cudaGetLastError();
 }
 
 }  // namespace lora

@@ -104,3 +104,8 @@ def last_loop_ms() -> float:
 
 def last_total_ms() -> float:
     return float(_lib.lib().lora_last_total_ms())
+
+
+def last_chunks() -> int:
+    """Chunks the last 1-D drop-in call was cut into to overlap its copies with its launches (1 = none)."""
+    return int(_lib.lib().lora_last_chunks())

@@ -32,7 +32,7 @@ import os
 
 import numpy as np
 
-from .plan import HALO
+from .plan import DEFAULT_TB_1D, HALO, MAX_TB_1D
 
 
 def temporal_schedule(times: int, max_tb: int):
@@ -99,8 +99,8 @@ class SlabRunner:
         self.cuda = self.device.type == "cuda"
         injected = step_fn is not None
         if temporal_block is None:
-            temporal_block = int(os.environ.get("LORA_TB", "4")) if (dim == 1 and (not injected or fused_fn)) else 1
-        self.max_tb = max(1, min(4, temporal_block)) if dim == 1 else 1
+            temporal_block = int(os.environ.get("LORA_TB", str(DEFAULT_TB_1D))) if (dim == 1 and (not injected or fused_fn)) else 1
+        self.max_tb = max(1, min(MAX_TB_1D, temporal_block)) if dim == 1 else 1
         if injected and fused_fn is None:
             self.max_tb = 1
         ghost = 4 * self.max_tb if (dim == 1 and self.max_tb > 1) else None

@@ -91,12 +91,13 @@ def _worker(rank, world, port, shape, dims, times, ret, fused=False):
 
 def test_temporal_schedule_lands_in_the_reference_buffer():
     from lorastencil_b200.slab import temporal_schedule
-    for max_tb in (1, 2, 3, 4):
+    for max_tb in (1, 2, 3, 4, 5, 8):
         for times in range(0, 60):
             tbs = temporal_schedule(times, max_tb)
             assert sum(tbs) == times and all(1 <= t <= max_tb for t in tbs)
             assert len(tbs) % 2 == times % 2  # result in buf[times % 2] (S3)
     assert temporal_schedule(1000, 4) == [4] * 250
+    assert temporal_schedule(1000, 8) == [8] * 124 + [4, 4]
 
 
 @pytest.mark.parametrize("shape,dims,world,times,fused", [
