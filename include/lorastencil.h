@@ -129,12 +129,16 @@ int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void
 /* Temporal blocking (new; the reference launches one kernel per time step).  lora_plan_run fuses up to
  * `tb` consecutive launches into one sweep that keeps the intermediate grids on chip; results are
  * bit-identical to unfused launches, halo semantics (S2) included.  Default: 15 (the maximum) for the 1-D
- * shapes (or the environment variable LORA_TB), 1 for 2-D / 3-D (not implemented there yet: the call clamps).  */
+ * shapes (or the environment variable LORA_TB).  2-D: 3 launches can be fused (tb >= 3 selects it, anything less
+ * means one launch per step, which is the default; environment variable LORA_TB2=3).  3-D: always 1.  */
 int lora_plan_set_temporal_block(lora_plan_t *plan, int tb);
 int lora_plan_temporal_block(const lora_plan_t *plan);
 
-/* One FUSED launch of `tb` (1..15) time steps over interior range [lo, hi) (1-D only): reads
- * src[lo - 4 tb, hi + 4 tb) clipped to the array, writes dst[lo, hi).  `launches_before` = time steps
+/* One FUSED launch of `tb` time steps over interior range [lo, hi) of the outermost axis.
+ * 2-D (tb = 1 or 3): rows [lo, hi); the ring of src must be the one its time parity calls for (caller's halo at even
+ * `launches_before`, zeros at odd -- what the ping-pong gives when every sweep advances an odd number of steps),
+ * halo_src is required, virt_lo / virt_hi say whether the rows above 0 / below m are the global halo ring.
+ * 1-D (tb = 1..15): reads src[lo - 4 tb, hi + 4 tb) clipped to the array, writes dst[lo, hi).  `launches_before` = time steps
  * already applied to src (its parity selects the halo each level sees).  virt_lo / virt_hi: that end of
  * the array is an end of the global line, whose halo cells are virtual -- caller's halo (read from the
  * padded buffer `halo_src`) at even times, zero at odd times; with 0 the side is an inter-slab boundary

@@ -115,6 +115,21 @@ struct Geom2D {
     int vec4;  // 256-bit stores allowed (n % 4 == 0 and 32-byte aligned base)
 };
 
+// temporally blocked 2-D sweep (stencil2d_tb.cu): TB (odd) launches fused; strips write 128 - 8 (TB - 1) columns
+struct Geom2DTB {
+    double *out;
+    const double *halo_src;  // padded buffer whose halo ring holds the caller's halo (buffer 0 of the ping-pong)
+    long long pitch;         // padded columns
+    int m, n;
+    int row_lo, row_hi;      // interior rows written by this launch
+    int rows_per_chunk;
+    int nstrips;
+    int ntasks;
+    int par0;                // parity of the launch count before level 0 (== parity of the source buffer)
+    int virt_top, virt_bot;  // rows beyond that end are the global halo ring (virtual halo), not neighbour-slab data
+    int vec4;
+};
+
 struct Geom3D {
     double *out;
     long long row_pitch;    // padded columns
@@ -131,11 +146,15 @@ cudaError_t launch_1d_tb(const CUtensorMap &imap, const CUtensorMap &omap, const
                          cudaStream_t s);
 cudaError_t launch_2d(int form, const CUtensorMap &tmap, const Geom2D &g, const Weights2D &w,
                       const WeightsDirect49 &wd, cudaStream_t s);
+cudaError_t launch_2d_tb(int form, int tb, const CUtensorMap &tmap, const Geom2DTB &g, const Weights2D &w,
+                         const WeightsDirect49 &wd, cudaStream_t s);
+int strip_out_cols_2d_tb(int tb);
 cudaError_t launch_3d(int form, const CUtensorMap &tmap, const Geom3D &g, const Weights3D &w, cudaStream_t s);
 cudaError_t kernels_init();     // opt in to large dynamic shared memory once per process/device
 cudaError_t kernels_init_1d();
 cudaError_t kernels_init_1d_tb();
 cudaError_t kernels_init_2d();
+cudaError_t kernels_init_2d_tb();
 cudaError_t kernels_init_3d();
 
 }  // namespace lora

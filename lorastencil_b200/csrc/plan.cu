@@ -93,6 +93,11 @@ struct lora_plan {
     int max_tb = 1;        // deepest temporal block lora_plan_run may fuse (1 = one launch per time step)
 };
 
+constexpr int kTb2 = 3;  // the 2-D temporal block (odd, so that time parity == buffer parity at every sweep)
+static bool tb2_form(int form) { return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID; }
+static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
+                         int tb, int launches_before, int virt_lo, int virt_hi, void *stream);
+
 static std::once_flag g_init_once;
 static cudaError_t g_init_err = cudaSuccess;
 
@@ -161,6 +166,11 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && sms > 0) p->sm_count = sms;
     const int warps_per_sm = (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
+    if (dim == 2 && tb2_form(p->form)) {
+        // 2-D fusion (stencil2d_tb.cu) is opt-in: with 3 levels x 28 accumulators per lane the kernel is bound by
+        // the register file / issue slots and measures 283 GStencil/s against 335 unfused (profiles/)
+        if (const char *e = getenv("LORA_TB2")) p->max_tb = (atoi(e) >= kTb2) ? kTb2 : 1;
+    }
     if (dim == 1) {
         p->max_tb = kDefaultTb1;
         if (const char *e = getenv("LORA_TB")) {
@@ -319,8 +329,47 @@ extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, lo
 
 extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
     if (!p || tb < 1) return fail(LORA_ERR_ARG, "bad argument");
-    const int cap = (p->dim == 1) ? kMaxTb1 : 1;
-    p->max_tb = tb < cap ? tb : cap;
+    if (p->dim == 1)
+        p->max_tb = tb < kMaxTb1 ? tb : kMaxTb1;
+    else if (p->dim == 2)
+        p->max_tb = (tb >= kTb2 && tb2_form(p->form)) ? kTb2 : 1;  // 2-D fuses exactly 3 launches or none
+    else
+        p->max_tb = 1;
+    return LORA_OK;
+}
+
+// 2-D fused launch of kTb2 time steps over interior rows [lo, hi): see stencil2d_tb.cu
+static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
+                         int tb, int launches_before, int virt_lo, int virt_hi, void *stream) {
+    if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
+    if (tb == 1) return lora_plan_step(p, src, dst, lo, hi, stream);
+    if (tb != kTb2 || !tb2_form(p->form))
+        return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid)", kTb2);
+    if (!halo_src) return fail(LORA_ERR_ARG, "fused 2-D launches need halo_src (the buffer holding the caller's halo)");
+    if (lo == hi) return LORA_OK;
+    const CUtensorMap *tm;
+    int rc = get_tmap(p, src, &tm);
+    if (rc) return rc;
+    Geom2DTB g{};
+    g.out = dst;
+    g.halo_src = halo_src;
+    g.pitch = p->padded[1];
+    g.m = (int)p->dims[0];
+    g.n = (int)p->dims[1];
+    g.row_lo = (int)lo;
+    g.row_hi = (int)hi;
+    const int wout = strip_out_cols_2d_tb(tb);
+    g.nstrips = (g.n + wout - 1) / wout;
+    g.rows_per_chunk = (int)pick_len(hi - lo, g.nstrips, (long long)p->sm_count * 2 * kWarpsPerCta, 768, 96);
+    const int chunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
+    g.ntasks = chunks * g.nstrips;
+    g.par0 = launches_before & 1;
+    g.virt_top = virt_lo ? 1 : 0;
+    g.virt_bot = virt_hi ? 1 : 0;
+    g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+    cudaError_t e = launch_2d_tb(p->form, tb, *tm, g, p->w2, p->wd, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    p->launches++;
     return LORA_OK;
 }
 
@@ -330,7 +379,8 @@ extern "C" int lora_plan_step_fused(lora_plan_t *p, const double *src, double *d
                                     long long lo, long long hi, int tb, int launches_before, int virt_lo, int virt_hi,
                                     void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
-    if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D shapes");
+    if (p->dim == 2) return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream);
+    if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D and 2-D shapes");
     if (tb < 1 || tb > kMaxTb1) return fail(LORA_ERR_ARG, "temporal block must be 1..%d", kMaxTb1);
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if ((virt_lo || virt_hi) && !halo_src) return fail(LORA_ERR_ARG, "virtual halo needs halo_src");
@@ -415,6 +465,18 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
     if (!p || !buf0 || !buf1) return fail(LORA_ERR_ARG, "null argument");
     if (p->dim == 1 && p->max_tb > 1 && times > 1) return run_fused_1d(p, buf0, buf1, times, 1, 1, stream);
     double *buf[2] = {buf0, buf1};
+    if (p->dim == 2 && p->max_tb == kTb2 && times >= kTb2) {
+        // sweeps of 3 launches, then the remainder one by one: every sweep advances an odd number of time steps,
+        // so sweep k reads buf[k%2] at a time of parity k%2 and the result lands in buf[times%2] (S3)
+        int k = 0;
+        for (int left = times; left > 0; k++) {
+            const int tb = left >= kTb2 ? kTb2 : 1;
+            int rc = step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tb, times - left, 1, 1, stream);
+            if (rc) return rc;
+            left -= tb;
+        }
+        return LORA_OK;
+    }
     for (int i = 0; i < times; i++) {
         int rc = lora_plan_step(p, buf[i % 2], buf[(i + 1) % 2], 0, p->dims[0], stream);
         if (rc) return rc;

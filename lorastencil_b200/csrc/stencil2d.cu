@@ -21,74 +21,12 @@
 // the FMA form; see DESIGN.md and profiles/ for the measured pipe rates.
 #include "common.cuh"
 #include "kernels.h"
+#include "stencil2d_push.cuh"
 #include "../../include/lorastencil.h"
 
 namespace lora {
 
 namespace {
-
-constexpr int NACC = 7;
-
-// x[4 + q + dc] is the input at (own column q) + dc; accumulator (3 - dr + PH) % 7 belongs to the
-// output row that sees this input row at row offset dr.
-template <int FORM, int PH>
-__device__ __forceinline__ void push_row(const double (&x)[12], double (&A)[NACC][4], const Weights2D &w,
-                                         const WeightsDirect49 &wd) {
-#define ACC(dr) A[((3 - (dr)) + PH) % NACC]
-    if constexpr (FORM == LORA_FORM_PYRAMID) {
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            const int rad = 3 - t;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                double h = w.horiz[t][3 - rad] * x[4 + q - rad];
-#pragma unroll
-                for (int dc = -rad + 1; dc <= rad; dc++) h = fma(w.horiz[t][3 + dc], x[4 + q + dc], h);
-#pragma unroll
-                for (int dr = -rad; dr <= rad; dr++) ACC(dr)[q] = fma(w.vert[t][3 + dr], h, ACC(dr)[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) ACC(0)[q] = fma(w.centre, x[4 + q], ACC(0)[q]);
-    } else if constexpr (FORM == LORA_FORM_CROSS) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-#pragma unroll
-            for (int dr = -3; dr <= 3; dr++) ACC(dr)[q] = fma(w.vert[0][3 + dr], x[4 + q], ACC(dr)[q]);
-            double h = w.horiz[1][0] * x[4 + q - 3];
-#pragma unroll
-            for (int dc = -2; dc <= 3; dc++)
-                if (dc != 0) h = fma(w.horiz[1][3 + dc], x[4 + q + dc], h);
-            ACC(0)[q] += h;
-        }
-    } else if constexpr (FORM == LORA_FORM_DIAMOND) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            double h = w.horiz[0][1] * x[4 + q - 2];
-#pragma unroll
-            for (int dc = -1; dc <= 2; dc++) h = fma(w.horiz[0][3 + dc], x[4 + q + dc], h);
-#pragma unroll
-            for (int dr = -2; dr <= 2; dr++) ACC(dr)[q] = fma(w.vert[0][3 + dr], h, ACC(dr)[q]);
-            ACC(0)[q] = fma(w.residual[0], x[4 + q - 3], ACC(0)[q]);
-            ACC(0)[q] = fma(w.residual[1], x[4 + q + 3], ACC(0)[q]);
-            ACC(-3)[q] = fma(w.residual[2], x[4 + q], ACC(-3)[q]);
-            ACC(3)[q] = fma(w.residual[3], x[4 + q], ACC(3)[q]);
-            ACC(-2)[q] = fma(w.residual[4], x[4 + q - 2], ACC(-2)[q]);
-            ACC(-2)[q] = fma(w.residual[5], x[4 + q + 2], ACC(-2)[q]);
-            ACC(2)[q] = fma(w.residual[6], x[4 + q - 2], ACC(2)[q]);
-            ACC(2)[q] = fma(w.residual[7], x[4 + q + 2], ACC(2)[q]);
-        }
-    } else {  // DIRECT49
-#pragma unroll
-        for (int dr = -3; dr <= 3; dr++)
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-#pragma unroll
-                for (int dc = -3; dc <= 3; dc++)
-                    ACC(dr)[q] = fma(wd.w[(dr + 3) * 7 + dc + 3], x[4 + q + dc], ACC(dr)[q]);
-    }
-#undef ACC
-}
 
 struct Sweep2D {
     const CUtensorMap *tmap;
@@ -133,8 +71,7 @@ __device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4
         }
         s.orow += s.pitch;
     }
-#pragma unroll
-    for (int q = 0; q < 4; q++) done[q] = 0.0;  // becomes logical accumulator 6 of the next row
+    // `done` is reborn as logical accumulator 6 by the next row's dr = -3 term (an assignment): no zeroing
 
     if (rr == kRowsPerStage - 1 || i == s.nin - 1) {
         __syncwarp();  // every lane has consumed this stage

@@ -1,0 +1,264 @@
+// stencil2d_tb.cu -- 2-D stencils with TEMPORAL BLOCKING: TB (odd) launches of the reference's 2-D kernels
+// (src/2d/gpu.cu:31-273) fused into one sweep; the intermediate grids never leave the register file.
+// New functionality (the reference launches one kernel per time step).
+//
+// Same worker model as stencil2d.cu -- a warp owns a strip of 128 columns, lane l four of them, and sweeps a
+// chunk of rows top to bottom through its private TMA ring -- extended into a register pipeline of TB levels:
+//
+//   input row i  --push-->  A_1 (7 row accumulators)  --retire row-->  v_1 (4 values per lane)
+//   v_1 + 3 columns from either neighbour lane (6 FP64 warp shuffles)  --push-->  A_2  --retire-->  v_2 ...
+//   ... v_TB leaves with one 256-bit store.
+//
+// Every level lags the one before by 3 rows (the radius), so one loop iteration advances all TB levels by one
+// row and the accumulator rings of all levels rotate in lock step (row loop unrolled 7x, no register moves).
+// Lanes 0 and 31 have no neighbour on one side, so the valid strip shrinks by one lane (4 columns >= radius 3)
+// per level and side: a warp reads 136 columns, computes 128 at every level and writes 128 - 8 (TB - 1)
+// (overlapped tiling across strips: 14 % redundant FP64 work at TB = 3, no inter-warp synchronisation at all).
+// Vertically a chunk re-computes 3 (TB - s) rows of level s above and below its output rows.
+//
+// Reference semantics under fusion (S2): the halo ring of the grid launch t reads is the
+// caller's halo when t is even and zero when t is odd, and no launch ever writes it.  Intermediate levels are
+// therefore PATCHED before they feed the next level: a retired cell outside the interior takes
+// (its time is even) ? caller's halo (buffer 0 of the ping-pong) : 0.  Only odd TB are offered, so that the time
+// parity equals the buffer parity at level 0 and the source buffer's own halo ring is already the right one.
+#include "common.cuh"
+#include "kernels.h"
+#include "stencil2d_push.cuh"
+#include "../../include/lorastencil.h"
+
+namespace lora {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct SweepTB {
+    const CUtensorMap *tmap;
+    double *ring;
+    uint64_t *bars;
+    double *orow;           // output row pointer (this lane's first column), advances by pitch once rows retire
+    const double *hsrc;     // caller's halo: padded buffer 0, pointing at (row 0, this lane's first column)
+    long long pitch;
+    int nin, nst, boxcol, row0_padded, lane;
+    int rho0;               // interior row of input row 0 of the chunk (= r0 - 3 TB)
+    int c0;                 // interior column of this lane's first cell
+    int m, n;
+    int out_lo, out_hi;     // interior rows this chunk writes: [out_lo, out_hi)
+    bool store_lane;        // this lane's columns are valid at level TB
+    bool col_edge;          // the strip has cells outside [0, n): intermediate levels need column patching
+    bool virt_top, virt_bot;  // rows above 0 / below m are the global halo ring (virtual), not a neighbour slab's rows
+    int par0;               // time parity before level 0
+    bool vec4;
+};
+
+// virtual halo for a retired row of level `level` (time par0 + level): cells outside the interior are not computed
+// values.  Rare (rows of the halo ring, strips at the left / right edge), so kept out of line; values travel in
+// registers both ways (no local-memory round trip on the hot path).
+__device__ __noinline__ double4 patch_row_slow(double v0, double v1, double v2, double v3, int rho, bool row_out,
+                                               bool caller, int c0, int m, int n, long long pitch, const double *hsrc) {
+    double v[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int c = c0 + q;
+        if (row_out || c < 0 || c >= n) {
+            double h = 0.0;
+            if (caller && rho >= -4 && rho < m + 4 && c >= -4 && c < n + 4) h = hsrc[(long long)rho * pitch + q];
+            v[q] = h;
+        }
+    }
+    return make_double4(v[0], v[1], v[2], v[3]);
+}
+
+__device__ __forceinline__ void patch_row(double (&v)[4], int rho, int level, const SweepTB &s) {
+    const bool row_out = (s.virt_top && rho < 0) || (s.virt_bot && rho >= s.m);
+    if (row_out || s.col_edge) {  // warp-uniform
+        const bool caller = ((s.par0 + level) & 1) == 0;  // at even times the ring holds the caller's halo
+        const double4 p = patch_row_slow(v[0], v[1], v[2], v[3], rho, row_out, caller, s.c0, s.m, s.n, s.pitch, s.hsrc);
+        v[0] = p.x;
+        v[1] = p.y;
+        v[2] = p.z;
+        v[3] = p.w;
+    }
+}
+
+template <int FORM, int TB, int PH>
+__device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NACC][4], const Weights2D &w,
+                                          const WeightsDirect49 &wd) {
+    const int st = i / kRowsPerStage, rr = i % kRowsPerStage, slot = st % kStages;
+    if (rr == 0) mbar_wait(&s.bars[slot], (st / kStages) & 1);
+    const double2 *rowp = reinterpret_cast<const double2 *>(s.ring + slot * kStageElems + rr * kBoxCols + 4 * s.lane);
+    double x[12];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const double2 v = rowp[k];
+        x[2 * k] = v.x;
+        x[2 * k + 1] = v.y;
+    }
+    if (rr == kRowsPerStage - 1 || i == s.nin - 1) {
+        __syncwarp();  // every lane has read this stage
+        if (s.lane == 0 && st + kStages < s.nst) {
+            mbar_arrive_expect_tx(&s.bars[slot], kStageElems * 8);
+            tma_load_2d(s.ring + slot * kStageElems, s.tmap, s.boxcol, s.row0_padded + (st + kStages) * kRowsPerStage,
+                        &s.bars[slot]);
+        }
+    }
+    push_row<FORM, PH>(x, A[0], w, wd);
+
+    double v[4];
+#pragma unroll
+    for (int lv = 1; lv <= TB; lv++) {
+        // retire logical accumulator 0 of level lv: its row is  rho0 + i - 3 lv
+        double(&done)[4] = A[lv - 1][PH % NACC];
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = done[q];  // reborn by the next row's dr = -3 term (an assignment)
+        if (lv == TB) break;
+        patch_row(v, s.rho0 + i - 3 * lv, lv, s);
+        // window of level lv: own 4 columns + 3 from either neighbour lane
+        x[4] = v[0];
+        x[5] = v[1];
+        x[6] = v[2];
+        x[7] = v[3];
+        x[1] = __shfl_up_sync(kFull, v[1], 1);
+        x[2] = __shfl_up_sync(kFull, v[2], 1);
+        x[3] = __shfl_up_sync(kFull, v[3], 1);
+        x[8] = __shfl_down_sync(kFull, v[0], 1);
+        x[9] = __shfl_down_sync(kFull, v[1], 1);
+        x[10] = __shfl_down_sync(kFull, v[2], 1);
+        x[0] = 0.0;
+        x[11] = 0.0;
+        push_row<FORM, PH>(x, A[lv], w, wd);
+    }
+
+    // v = level TB, row rho0 + i - 3 TB
+    const int rout = s.rho0 + i - 3 * TB;
+    if (rout >= s.out_lo && rout < s.out_hi) {
+        if (s.store_lane) {
+            const int left = s.n - s.c0;
+            if (left >= 4) {
+                if (s.vec4) {
+                    st_global_v4(s.orow, v[0], v[1], v[2], v[3]);
+                } else {
+                    st_global_v2(s.orow, v[0], v[1]);
+                    st_global_v2(s.orow + 2, v[2], v[3]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q < left) s.orow[q] = v[q];
+            }
+        }
+        s.orow += s.pitch;
+    }
+}
+
+template <int FORM, int TB>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 2)
+k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2DTB g,
+               const __grid_constant__ Weights2D w, const __grid_constant__ WeightsDirect49 wd) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task = blockIdx.x * kWarpsPerCta + warp;
+    if (task >= g.ntasks) return;  // warps never synchronise with each other
+
+    constexpr int kStripOut = kWarpCols - 8 * (TB - 1);  // columns a strip writes
+    const int strip = task % g.nstrips, chunk = task / g.nstrips;
+    const int r0 = g.row_lo + chunk * g.rows_per_chunk;  // first interior row this chunk writes
+    const int R = min(g.rows_per_chunk, g.row_hi - r0);
+    const int cs = strip * kStripOut;                    // first interior column the strip writes
+    const int cw = cs - 4 * (TB - 1);                    // first interior column the warp computes
+
+    SweepTB s;
+    s.tmap = &tmap;
+    s.ring = reinterpret_cast<double *>(smem_raw) + warp * (kStages * kStageElems);
+    s.bars = reinterpret_cast<uint64_t *>(smem_raw + kWarpsPerCta * kStages * kStageElems * 8) + warp * kStages;
+    s.nin = R + 6 * TB;  // input rows r0 - 3 TB .. r0 + R + 3 TB - 1
+    s.nst = (s.nin + kRowsPerStage - 1) / kRowsPerStage;
+    s.boxcol = cw;                       // padded column of the box origin = interior column cw - 4, + 4
+    s.row0_padded = r0 - 3 * TB + 4;     // padded row of input row 0 (negative rows are zero-filled by the TMA)
+    s.lane = lane;
+    s.rho0 = r0 - 3 * TB;
+    s.c0 = cw + 4 * lane;
+    s.m = g.m;
+    s.n = g.n;
+    s.out_lo = r0;
+    s.out_hi = r0 + R;
+    s.store_lane = lane >= TB - 1 && lane <= 32 - TB && s.c0 < g.n && s.c0 < cs + kStripOut;
+    s.col_edge = cw < 0 || cw + kWarpCols > g.n;
+    s.virt_top = g.virt_top != 0;
+    s.virt_bot = g.virt_bot != 0;
+    s.par0 = g.par0 & 1;
+    s.vec4 = g.vec4 != 0;
+    s.pitch = g.pitch;
+    s.orow = g.out + (long long)(r0 + 4) * g.pitch + 4 + s.c0;
+    s.hsrc = g.halo_src + 4 * g.pitch + 4 + s.c0;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kStages; k++) mbar_init(&s.bars[k], 1);
+        fence_barrier_init();
+#pragma unroll
+        for (int k = 0; k < kStages; k++)
+            if (k < s.nst) {
+                mbar_arrive_expect_tx(&s.bars[k], kStageElems * 8);
+                tma_load_2d(s.ring + k * kStageElems, &tmap, s.boxcol, s.row0_padded + k * kRowsPerStage, &s.bars[k]);
+            }
+    }
+    __syncwarp();
+
+    double A[TB][NACC][4];
+#pragma unroll
+    for (int lv = 0; lv < TB; lv++)
+#pragma unroll
+        for (int j = 0; j < NACC; j++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) A[lv][j][q] = 0.0;
+
+    for (int base = 0; base < s.nin; base += NACC) {
+        if (base + 0 < s.nin) row_phase<FORM, TB, 0>(base + 0, s, A, w, wd);
+        if (base + 1 < s.nin) row_phase<FORM, TB, 1>(base + 1, s, A, w, wd);
+        if (base + 2 < s.nin) row_phase<FORM, TB, 2>(base + 2, s, A, w, wd);
+        if (base + 3 < s.nin) row_phase<FORM, TB, 3>(base + 3, s, A, w, wd);
+        if (base + 4 < s.nin) row_phase<FORM, TB, 4>(base + 4, s, A, w, wd);
+        if (base + 5 < s.nin) row_phase<FORM, TB, 5>(base + 5, s, A, w, wd);
+        if (base + 6 < s.nin) row_phase<FORM, TB, 6>(base + 6, s, A, w, wd);
+    }
+}
+
+template <int FORM, int TB>
+cudaError_t launch_form(const CUtensorMap &tmap, const Geom2DTB &g, const Weights2D &w, const WeightsDirect49 &wd,
+                        cudaStream_t st) {
+    if (g.ntasks <= 0) return cudaSuccess;
+    const int ctas = (g.ntasks + kWarpsPerCta - 1) / kWarpsPerCta;
+    k_stencil2d_tb<FORM, TB><<<ctas, 32 * kWarpsPerCta, kSmem12, st>>>(tmap, g, w, wd);
+    return cudaGetLastError();
+}
+
+template <int FORM, int TB>
+cudaError_t opt_in() {
+    return cudaFuncSetAttribute(k_stencil2d_tb<FORM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem12);
+}
+
+}  // namespace
+
+cudaError_t kernels_init_2d_tb() {
+    cudaError_t e;
+    if ((e = opt_in<LORA_FORM_PYRAMID, 3>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_CROSS, 3>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_DIAMOND, 3>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+int strip_out_cols_2d_tb(int tb) { return kWarpCols - 8 * (tb - 1); }
+
+cudaError_t launch_2d_tb(int form, int tb, const CUtensorMap &tmap, const Geom2DTB &g, const Weights2D &w,
+                         const WeightsDirect49 &wd, cudaStream_t s) {
+    if (tb != 3) return cudaErrorInvalidValue;
+    switch (form) {
+        case LORA_FORM_PYRAMID: return launch_form<LORA_FORM_PYRAMID, 3>(tmap, g, w, wd, s);
+        case LORA_FORM_CROSS: return launch_form<LORA_FORM_CROSS, 3>(tmap, g, w, wd, s);
+        case LORA_FORM_DIAMOND: return launch_form<LORA_FORM_DIAMOND, 3>(tmap, g, w, wd, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace lora

@@ -17,19 +17,31 @@ SIZES = {"1d1r": (1 << 28,), "1d2r": (1 << 28,), "star2d1r": (10240, 10240), "bo
 ap = argparse.ArgumentParser()
 ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--shapes", default=",".join(SIZES))
+ap.add_argument("--tb", type=int, default=0, help="temporal block to request (0 = the plan's default)")
+ap.add_argument("--reps", type=int, default=1)
 args = ap.parse_args()
 for shape in args.shapes.split(","):
     dims = SIZES[shape]
     plan = ls.Plan(shape, dims)
+    if args.tb:
+        plan.temporal_block = args.tb
     g = torch.Generator(device="cuda").manual_seed(1)
     b0 = torch.randint(0, 100, plan.padded_shape, generator=g, device="cuda").double()
     b1 = plan.new_buffer()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    plan.run(b0, b1, args.launches)
-    e1.record()
-    torch.cuda.synchronize()
-    print(f"{shape} {dims}: {e0.elapsed_time(e1) / args.launches * 1e3:.1f} us/launch  [{plan.describe}]")
+    best = None
+    for _ in range(args.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run(b0, b1, args.launches)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    cells = 1
+    for d in dims:
+        cells *= d
+    print(f"{shape} {dims}: {best / args.launches * 1e3:.1f} us/time step, {cells * args.launches / best / 1e6:.1f} GStencil/s"
+          f"  [tb {plan.temporal_block}; {plan.describe}]")
     del plan, b0, b1
     torch.cuda.empty_cache()

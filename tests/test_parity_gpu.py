@@ -171,7 +171,8 @@ def test_plan_api_partial_ranges_and_device_buffers():
             assert np.array_equal(got[:-1], full[:-1])
         else:
             assert np.array_equal(got, full)
-        # 1-D fuses the 3 launches of `run` into one temporally blocked sweep; 2-D / 3-D launch once per step
+        # 1-D fuses the 3 launches of `run` into one temporally blocked sweep; 2-D (fusion is opt-in) and 3-D launch
+        # once per step
         assert plan.launches == len(cuts) - 1 + (1 if oracle.dim_of(shape) == 1 else 3)
 
 
@@ -299,3 +300,38 @@ def test_chunked_copy_overlapped_operator_equals_plain(shape, n, times, chunks, 
         assert chunked[-1] == -7.0  # the reference copies back n + 7 doubles (src/1d/gpu_1r.cu:134)
         ref = oracle.run(shape, data, oracle.effective_params(shape, p), times)
         assert max_rel_err(chunked[:-1], ref[:-1]) <= RTOL
+
+
+@pytest.mark.parametrize("shape", ["star2d3r", "star2d1r", "box2d1r"])
+@pytest.mark.parametrize("dims", [(40, 130), (64, 64), (300, 258), (257, 1000), (1000, 130), (9, 8), (2, 2)])
+def test_temporal_blocking_2d_equals_unfused_launches(shape, dims):
+    """2-D sweeps of 3 fused launches (intermediate grids in registers, virtual alternating halo ring on all four
+    sides, overlapped strips) give the same bits as one launch per step, and match the oracle, for every launch
+    count residue and ragged sizes."""
+    import torch
+    a = oracle.fill_rand(shape, dims)
+    rng = np.random.default_rng(dims[0] * 7 + dims[1])
+    af = rng.uniform(-1, 1, a.shape)
+    eff = oracle.effective_params(shape)
+    plan = ls.Plan(shape, dims)
+    assert plan.temporal_block == 1  # 2-D fusion is opt-in (not yet faster than one launch per step)
+    exact_upto = {"box2d1r": 5, "star2d1r": 6, "star2d3r": 9}[shape]
+    for data in (a, af):
+        for times in (3, 4, 5, 6, 7, 9, 10):
+            results = []
+            for tb in (1, 3):
+                plan.temporal_block = tb
+                assert plan.temporal_block == tb
+                b0, b1 = torch.from_numpy(data).cuda(), plan.new_buffer()
+                n0 = plan.launches
+                res = plan.run(b0, b1, times)
+                torch.cuda.synchronize()
+                assert res is (b0 if times % 2 == 0 else b1)
+                assert plan.launches - n0 == (times if tb == 1 else times // 3 + times % 3)
+                results.append(res.cpu().numpy())
+            assert np.array_equal(results[0], results[1]), (shape, dims, times)  # same operation order => same bits
+            ref = oracle.run(shape, data, eff, times)
+            if data is a and times <= exact_upto:
+                assert np.array_equal(results[1], ref), (shape, dims, times)
+            else:
+                assert max_rel_err(results[1], ref) <= RTOL, (shape, dims, times)
