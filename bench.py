@@ -235,6 +235,11 @@ def main():
     ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape table")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    # other BASELINE.json configs (parity-test cases by default, measurable on request): e.g. config e
+    #   --shape box2d1r --dims 40960,40960 --times 100 --scaling strong     (global grid cut into N slabs)
+    ap.add_argument("--shape", default=None, help="measure this shape instead of the headline 1d2r job")
+    ap.add_argument("--dims", default=None, help="comma-separated interior sizes (per GPU if weak, global if strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -263,13 +268,24 @@ def main():
     ops.set_verbose(False)
     hbm_gbs, peak_src = peaks()
     shape, dims, _ = HEADLINE
+    custom = args.shape is not None
+    if custom:
+        shape = args.shape
+        dims = tuple(int(x) for x in args.dims.split(","))
+        args.no_shapes = args.no_cpu = True
+        args.no_e2e = True
     times = args.times
     n = dims[0]
-    cells_per_gpu = float(n)
+    if args.scaling == "weak":
+        global_dims = (n * world,) + tuple(dims[1:])
+    else:
+        global_dims = tuple(dims)
+    cells_per_gpu = float(np.prod(global_dims)) / world
 
     # ---- device-resident arm: slab runner (world == 1: a plain plan) ----
-    runner = SlabRunner(shape, (n * world,), device=dev)
-    runner.buf[0].copy_(device_fill(torch, runner.geo.local_padded, 10000, dev, 1234 + rank))
+    runner = SlabRunner(shape, global_dims, device=dev)
+    runner.buf[0].copy_(device_fill(torch, runner.geo.local_padded, 10000 if len(dims) == 1 else 100, dev, 1234 + rank))
+    runner.sync_ranks()
     plan = runner.plan
 
     def barrier():
@@ -331,6 +347,7 @@ def main():
                 runner.buf[0].copy_(hin, non_blocking=True)
                 runner.buf[1].zero_()
                 runner.launch = runner.time = 0
+                runner.sync_ranks()  # nobody stores into a neighbour's ghost zone before that neighbour has refilled it
                 res = runner.run(times)
                 hout.copy_(res, non_blocking=True)
                 torch.cuda.synchronize()
@@ -357,24 +374,33 @@ def main():
             dist.destroy_process_group()
         return
 
+    halo_how = {"p2p": "edge bands stored straight into the neighbours' ghost rows over NVLink peer memory (CUDA IPC), "
+                       "64-bit flags in stream order; interior launches never wait",
+                "nccl": "NCCL send/recv of the edge bands on a side stream"}[runner.halo_mode]
+    dimname = {1: "1d", 2: "2d", 3: "3d"}[len(dims)]
+    buf_gb = float(np.prod(runner.geo.local_padded)) * 8 / 1e9
     line = {
         "metric": "GStencil/s", "value": value, "unit": "GStencil/s (cells x launches / s / 1e9)",
         "value_artifact_units": value * ARTIFACT_K[shape],
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"lorastencil_1d {shape} {n} {times} per GPU (BASELINE.json configs[1])",
-                   "shape": shape, "points_per_gpu": n, "launches_per_step": times,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"lorastencil_{dimname} {shape} {' '.join(map(str, dims))} {times} "
+                               + ("per GPU" if args.scaling == "weak" else "global grid")
+                               + (" (BASELINE.json configs[1])" if not custom else ""),
+                   "shape": shape, "points_per_gpu": int(cells_per_gpu), "launches_per_step": times,
+                   "global_dims": list(global_dims),
                    "decomposition": "single device" if world == 1 else
-                   f"{world} slabs, {4 * runner.max_tb}-element ghost-zone exchange per temporal block of {runner.max_tb} launches "
-                   "(NCCL send/recv on a side stream, edge bands first)",
-                   "l2": "inputs (2.1 GB per buffer) larger than L2; no flush needed",
-                   "values": "reference weights: FP64 overflows to inf after ~217 launches exactly as in the reference run; timing only",
+                   f"{world} slabs along the outermost axis, {runner.geo.wl if runner.geo.prev is not None else runner.geo.wr}"
+                   f"-deep ghost zones exchanged once per sweep of {runner.max_tb} launch(es): " + halo_how,
+                   "l2": f"inputs ({buf_gb:.1f} GB per buffer) larger than L2; no flush needed",
+                   "values": "reference weights: FP64 overflows to inf after ~130-340 launches exactly as in the reference run; timing only",
                    "kernel_form": plan.describe, "temporal_block": runner.max_tb},
         "gpu_launches": gpu_launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": None,
-                     "kernel": f"k_stencil1d_tb (tb = {runner.max_tb})" if runner.max_tb > 1 else "k_stencil1d",
+                     "kernel": (f"k_stencil1d_tb (tb = {runner.max_tb})" if runner.max_tb > 1 else "k_stencil1d")
+                     if len(dims) == 1 else f"k_stencil{len(dims)}d",
                      "us_per_launch": us_per_launch,
                      "algorithmic_bytes_per_launch": cells_per_gpu * 16 * steps_per_launch,
                      "time_steps_per_launch": steps_per_launch, "peak_source": peak_src,

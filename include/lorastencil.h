@@ -146,6 +146,26 @@ int lora_plan_temporal_block(const lora_plan_t *plan);
 int lora_plan_step_fused(lora_plan_t *plan, const double *src, double *dst, const double *halo_src, long long lo,
                          long long hi, int tb, int launches_before, int virt_lo, int virt_hi, void *stream);
 
+/* ---- multi-GPU slabs without a communication library (new; the reference is single-GPU) ----
+ * One process per GPU on one box.  Each rank allocates its ping-pong buffers with lora_peer_alloc and hands the
+ * 64-byte handle to its neighbours, which map the buffer with lora_peer_open (CUDA IPC over NVLink).  A rank then
+ * launches its EDGE BANDS with lora_plan_step_mirror / lora_plan_step_fused_mirror: every cell the launch stores
+ * at dst[x] is also stored at mirror_base[x], mirror_base being the address in the neighbour's buffer that
+ * corresponds to dst[0] (neighbour buffer + a row / plane / cell shift), i.e. the band lands directly in the
+ * neighbour's halo.  Ordering between ranks: 64-bit flags in peer memory, written (lora_stream_write_flag) and
+ * awaited (lora_stream_wait_flag_geq: blocks the stream until *flag >= value) in stream order. */
+int lora_peer_alloc(void **ptr, unsigned long long bytes, void *handle64_out);
+int lora_peer_free(void *ptr);
+int lora_peer_open(const void *handle64, void **ptr);
+int lora_peer_close(void *ptr);
+int lora_stream_write_flag(void *stream, void *flag, unsigned long long value);
+int lora_stream_wait_flag_geq(void *stream, void *flag, unsigned long long value);
+int lora_plan_step_mirror(lora_plan_t *plan, const double *src, double *dst, long long lo, long long hi,
+                          const double *mirror_base, void *stream);
+int lora_plan_step_fused_mirror(lora_plan_t *plan, const double *src, double *dst, const double *halo_src, long long lo,
+                                long long hi, int tb, int launches_before, int virt_lo, int virt_hi,
+                                const double *mirror_base, void *stream);
+
 /* how many kernel launches the plan has issued so far (bench.py's gpu_launches) */
 long long lora_plan_launch_count(const lora_plan_t *plan);
 

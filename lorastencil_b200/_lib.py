@@ -20,7 +20,9 @@ C_ABI_SYMBOLS = (
     "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
     "lora_last_total_ms", "lora_last_chunks", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
     "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_set_temporal_block",
-    "lora_plan_temporal_block", "lora_plan_step_fused", "lora_plan_launch_count", "lora_plan_describe",
+    "lora_plan_temporal_block", "lora_plan_step_fused", "lora_plan_step_mirror", "lora_plan_step_fused_mirror",
+    "lora_peer_alloc", "lora_peer_free", "lora_peer_open", "lora_peer_close", "lora_stream_write_flag",
+    "lora_stream_wait_flag_geq", "lora_plan_launch_count", "lora_plan_describe",
     "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
 )
 # the reference's own C++ symbols (include/lorastencil_dropin.hpp)
@@ -97,6 +99,23 @@ def lib() -> ctypes.CDLL:
     L.lora_plan_step_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int,
                                        c_int, c_int, c_void_p]
     L.lora_plan_step_fused.restype = c_int
+    L.lora_plan_step_mirror.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p]
+    L.lora_plan_step_mirror.restype = c_int
+    L.lora_plan_step_fused_mirror.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int,
+                                              c_int, c_int, c_void_p, c_void_p]
+    L.lora_plan_step_fused_mirror.restype = c_int
+    L.lora_peer_alloc.argtypes = [POINTER(c_void_p), ctypes.c_ulonglong, c_void_p]
+    L.lora_peer_alloc.restype = c_int
+    L.lora_peer_free.argtypes = [c_void_p]
+    L.lora_peer_free.restype = c_int
+    L.lora_peer_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.lora_peer_open.restype = c_int
+    L.lora_peer_close.argtypes = [c_void_p]
+    L.lora_peer_close.restype = c_int
+    L.lora_stream_write_flag.argtypes = [c_void_p, c_void_p, ctypes.c_ulonglong]
+    L.lora_stream_write_flag.restype = c_int
+    L.lora_stream_wait_flag_geq.argtypes = [c_void_p, c_void_p, ctypes.c_ulonglong]
+    L.lora_stream_wait_flag_geq.restype = c_int
     L.lora_plan_launch_count.argtypes = [c_void_p]
     L.lora_plan_launch_count.restype = c_longlong
     L.lora_plan_describe.argtypes = [c_void_p]

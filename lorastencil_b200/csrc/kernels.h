@@ -83,6 +83,7 @@ struct Geom1D {
     int rows_per_task;  // 128-element rows one warp sweeps
     long long ntasks;
     int vec4;           // 256-bit stores allowed (lo % 4 == 0 and 32-byte aligned base)
+    long long mirror;   // != 0: every cell stored at out[x] is also stored at out[x + mirror] (a neighbour's halo, over NVLink)
 };
 
 // temporally blocked 1-D sweep (stencil1d_tb.cu): TB launches fused.  X = PADDED coordinates (interior cell i = X 4 + i)
@@ -102,6 +103,7 @@ struct Geom1DTB {
     long long xcov;          // level-0 cells X >= xcov are not covered by the load map
     long long out_off;       // the store map starts at cell out_off (= -4 TB mod 16) ...
     long long out_rows;      // ... and covers out_rows rows of 16 cells
+    long long mirror;        // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
 struct Geom2D {
@@ -113,6 +115,7 @@ struct Geom2D {
     int nstrips;
     int ntasks;
     int vec4;  // 256-bit stores allowed (n % 4 == 0 and 32-byte aligned base)
+    long long mirror;  // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
 // temporally blocked 2-D sweep (stencil2d_tb.cu): TB (odd) launches fused; strips write 128 - 8 (TB - 1) columns
@@ -139,6 +142,7 @@ struct Geom3D {
     int planes_per_chunk;
     int tiles_m, tiles_n;
     int vec4;
+    long long mirror;  // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
 cudaError_t launch_1d(const Geom1D &g, const Weights1D &w, cudaStream_t s);

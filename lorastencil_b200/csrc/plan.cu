@@ -264,8 +264,14 @@ static long long pick_len(long long total, long long lanes, long long slots, lon
     return max_len;
 }
 
-extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
-                              void *stream) {
+// mirror_base: nullptr, or the address in a NEIGHBOUR's buffer (peer memory, lora_peer_open) that corresponds to
+// dst[0]: every cell this launch stores at dst[x] is stored at mirror_base[x] too
+static long long mirror_delta(const double *dst, const double *mirror_base) {
+    return mirror_base ? (long long)(mirror_base - dst) : 0;
+}
+
+static int plan_step_impl(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
+                          const double *mirror_base, void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if (lo == hi) return LORA_OK;
@@ -285,6 +291,7 @@ extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, lo
         g.rows_per_task = (int)pick_len(rows, 1, p->slots, 256, 16);
         g.ntasks = (rows + g.rows_per_task - 1) / g.rows_per_task;
         g.vec4 = (lo % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+        g.mirror = mirror_delta(dst, mirror_base);
         e = launch_1d(g, p->w1, st);
     } else if (p->dim == 2) {
         const CUtensorMap *tm;
@@ -302,6 +309,7 @@ extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, lo
         const int chunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
         g.ntasks = chunks * g.nstrips;
         g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+        g.mirror = mirror_delta(dst, mirror_base);
         e = launch_2d(p->form, *tm, g, p->w2, p->wd, st);
     } else {
         const CUtensorMap *tm;
@@ -320,11 +328,22 @@ extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, lo
         g.tiles_n = (g.n + k3TileCols - 1) / k3TileCols;
         g.planes_per_chunk = (int)pick_len(hi - lo, (long long)g.tiles_m * g.tiles_n, p->slots, 64, 8);
         g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+        g.mirror = mirror_delta(dst, mirror_base);
         e = launch_3d(p->form, *tm, g, p->w3, st);
     }
     if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     p->launches++;
     return LORA_OK;
+}
+
+extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
+                              void *stream) {
+    return plan_step_impl(p, src, dst, lo, hi, nullptr, stream);
+}
+
+extern "C" int lora_plan_step_mirror(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
+                                     const double *mirror_base, void *stream) {
+    return plan_step_impl(p, src, dst, lo, hi, mirror_base, stream);
 }
 
 extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
@@ -375,10 +394,27 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
 
 extern "C" int lora_plan_temporal_block(const lora_plan_t *p) { return p ? p->max_tb : 0; }
 
+static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const double *halo_src, long long lo,
+                           long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base,
+                           void *stream);
+
 extern "C" int lora_plan_step_fused(lora_plan_t *p, const double *src, double *dst, const double *halo_src,
                                     long long lo, long long hi, int tb, int launches_before, int virt_lo, int virt_hi,
                                     void *stream) {
+    return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, nullptr, stream);
+}
+
+extern "C" int lora_plan_step_fused_mirror(lora_plan_t *p, const double *src, double *dst, const double *halo_src,
+                                           long long lo, long long hi, int tb, int launches_before, int virt_lo,
+                                           int virt_hi, const double *mirror_base, void *stream) {
+    return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, mirror_base, stream);
+}
+
+static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const double *halo_src, long long lo,
+                           long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base,
+                           void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
+    if (p->dim == 2 && mirror_base) return fail(LORA_ERR_UNSUPPORTED, "fused 2-D launches have no mirror store");
     if (p->dim == 2) return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream);
     if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D and 2-D shapes");
     if (tb < 1 || tb > kMaxTb1) return fail(LORA_ERR_ARG, "temporal block must be 1..%d", kMaxTb1);
@@ -409,6 +445,7 @@ extern "C" int lora_plan_step_fused(lora_plan_t *p, const double *src, double *d
     g.use_tma = (in_rows >= 1 && out_rows >= 1) ? 1 : 0;
     g.xcov = g.use_tma ? in_rows * 16 : 0;
     g.out_rows = out_rows;
+    g.mirror = mirror_delta(dst, mirror_base);
     CUtensorMap imap, omap;
     std::memset(&imap, 0, sizeof imap);
     std::memset(&omap, 0, sizeof omap);

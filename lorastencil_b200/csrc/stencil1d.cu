@@ -90,6 +90,11 @@ k_stencil1d(const __grid_constant__ Geom1D g, const __grid_constant__ Weights1D 
             for (int q = 0; q < 4; q++)
                 if (s + q < g.hi) o[q] = y[q];
         }
+        if (g.mirror != 0) {  // the same cells into the neighbour slab's halo (peer memory)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (s + q < g.hi) o[g.mirror + q] = y[q];
+        }
         if (rr == kStageRows1 - 1 || r == nrows - 1) {
             __syncwarp();
             if (lane == 0 && st + kStages < nst) issue(st + kStages, slot);

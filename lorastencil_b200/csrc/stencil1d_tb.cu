@@ -169,7 +169,7 @@ k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__
         if (i >= 1) {
             const long long Xr = X0 - 4 * TB;  // first cell of the output row (level TB)
             const long long rc = (Xr - g.out_off) >> 4;  // row of 16 in the store map (exact when Xr >= out_off)
-            if (g.use_tma && Xr >= g.xlo && Xr + kRow <= g.xhi && Xr >= g.out_off && rc + 32 <= g.out_rows) {
+            if (g.use_tma && g.mirror == 0 && Xr >= g.xlo && Xr + kRow <= g.xhi && Xr >= g.out_off && rc + 32 <= g.out_rows) {
                 // whole row: stage it (conflict-free STS) and let the TMA write the 4 KB line segment
                 unsigned char *stage = outbuf + (i % kTbOutBufs) * (kRow * 8);
                 if (lane == 0) tma_store_wait_read<kTbOutBufs - 1>();  // the last store issued from this staging row has drained
@@ -189,7 +189,10 @@ k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__
                 const long long x = Xr + kCpl * lane;
 #pragma unroll
                 for (int q = 0; q < kCpl; q++)
-                    if (x + q >= g.xlo && x + q < g.xhi) g.out[x + q] = cur[q];
+                    if (x + q >= g.xlo && x + q < g.xhi) {
+                        g.out[x + q] = cur[q];
+                        if (g.mirror != 0) g.out[x + q + g.mirror] = cur[q];  // neighbour slab's ghost zone (peer memory)
+                    }
             }
         }
     }

@@ -33,7 +33,7 @@ struct Sweep2D {
     double *ring;
     uint64_t *bars;
     double *orow;  // next output row, this lane's first column
-    long long pitch;
+    long long pitch, mirror;
     int nin, nst, boxcol, row0_padded, lane, ncols_left;  // ncols_left = n - c0 (how many of the 4 columns exist)
     bool vec4;
 };
@@ -68,6 +68,11 @@ __device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4
 #pragma unroll
             for (int q = 0; q < 4; q++)
                 if (q < s.ncols_left) s.orow[q] = done[q];
+        }
+        if (s.mirror != 0) {  // the same row into the neighbour slab's halo rows (peer memory)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (q < s.ncols_left) s.orow[s.mirror + q] = done[q];
         }
         s.orow += s.pitch;
     }
@@ -109,6 +114,7 @@ k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     s.ncols_left = g.n - c0;
     s.vec4 = g.vec4 != 0;
     s.pitch = g.pitch;
+    s.mirror = g.mirror;
     s.orow = g.out + (long long)(r0 + 4) * g.pitch + 4 + c0;
 
     if (lane == 0) {

@@ -96,7 +96,7 @@ struct Sweep3D {
     uint64_t *full, *empty;
     int box_c, box_r, box_h;  // TMA box origin (padded coordinates) of input plane 0 of the chunk
     double *optr;        // output plane pointer for this lane's micro-tile origin (advances by plane_pitch)
-    long long row_pitch, plane_pitch;
+    long long row_pitch, plane_pitch, mirror;
     int nin, warp, lane;
     int rows_left, cols_left;  // how many of the 4 micro-tile rows / columns exist
     bool vec4;
@@ -157,6 +157,11 @@ __device__ __forceinline__ void plane_phase(int i, Sweep3D &s, double (&A)[3][4]
                     for (int q = 0; q < 4; q++)
                         if (q < s.cols_left) o[q] = done[r][q];
                 }
+                if (s.mirror != 0) {  // the same row into the neighbour slab's halo plane (peer memory)
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (q < s.cols_left) o[s.mirror + q] = done[r][q];
+                }
             }
         }
         s.optr += s.plane_pitch;
@@ -216,6 +221,7 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     s.vec4 = g.vec4 != 0;
     s.row_pitch = g.row_pitch;
     s.plane_pitch = g.plane_pitch;
+    s.mirror = g.mirror;
     s.optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(r0 + 2) * g.row_pitch + 4 + c0;
 
     double A[3][4][4];

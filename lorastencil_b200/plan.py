@@ -92,14 +92,16 @@ class Plan:
     def temporal_block(self, tb: int):
         _lib.check(_lib.lib().lora_plan_set_temporal_block(self._h, int(tb)), "lora_plan_set_temporal_block")
 
-    def step_fused(self, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream=None):
-        """One fused launch of `tb` time steps (1-D): see lora_plan_step_fused in include/lorastencil.h."""
+    def step_fused(self, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream=None, mirror=None):
+        """One fused launch of `tb` time steps: see lora_plan_step_fused in include/lorastencil.h.  ``mirror``: device
+        address (int) in a neighbour's buffer corresponding to dst[0] -- the launch stores there too."""
         import torch
         s = torch.cuda.current_stream(src.device) if stream is None else stream
-        _lib.check(_lib.lib().lora_plan_step_fused(
+        _lib.check(_lib.lib().lora_plan_step_fused_mirror(
             self._h, c_void_p(src.data_ptr()), c_void_p(dst.data_ptr()),
             c_void_p(halo_src.data_ptr()) if halo_src is not None else None, int(lo), int(hi), int(tb),
-            int(launches_before), int(bool(virt_lo)), int(bool(virt_hi)), c_void_p(s.cuda_stream)), "lora_plan_step_fused")
+            int(launches_before), int(bool(virt_lo)), int(bool(virt_hi)), c_void_p(mirror) if mirror else None,
+            c_void_p(s.cuda_stream)), "lora_plan_step_fused")
 
     @property
     def cells(self) -> int:
@@ -114,15 +116,17 @@ class Plan:
                 tuple(t.shape) != self.padded_shape:
             raise TypeError(f"expected a contiguous float64 CUDA tensor of shape {self.padded_shape}")
 
-    def step(self, src, dst, lo: int = 0, hi: int | None = None, stream=None):
-        """One launch: dst[interior, outermost index in [lo, hi)] = stencil(src).  Asynchronous."""
+    def step(self, src, dst, lo: int = 0, hi: int | None = None, stream=None, mirror=None):
+        """One launch: dst[interior, outermost index in [lo, hi)] = stencil(src).  Asynchronous.  ``mirror``: device
+        address (int) in a neighbour's buffer corresponding to dst[0] -- the launch stores there too."""
         import torch
         self._check_buf(src)
         self._check_buf(dst)
         hi = self.dims[0] if hi is None else hi
         s = torch.cuda.current_stream(src.device) if stream is None else stream
-        _lib.check(_lib.lib().lora_plan_step(self._h, c_void_p(src.data_ptr()), c_void_p(dst.data_ptr()), int(lo), int(hi),
-                                             c_void_p(s.cuda_stream)), "lora_plan_step")
+        _lib.check(_lib.lib().lora_plan_step_mirror(self._h, c_void_p(src.data_ptr()), c_void_p(dst.data_ptr()), int(lo),
+                                                    int(hi), c_void_p(mirror) if mirror else None,
+                                                    c_void_p(s.cuda_stream)), "lora_plan_step")
 
     def run(self, buf0, buf1, times: int, stream=None):
         """``times`` launches, launch i reads buf[i%2]; returns the tensor holding the result."""

@@ -32,6 +32,7 @@ import os
 
 import numpy as np
 
+from . import _lib
 from .plan import DEFAULT_TB_1D, HALO, MAX_TB_1D
 
 
@@ -84,6 +85,93 @@ class SlabGeometry:
         return slice(self.lo + self.halo - self.wl, self.hi + self.halo + self.wr)
 
 
+class _DevMem:
+    """Zero-copy torch view of device memory the C library owns (lora_peer_alloc)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerHalo:
+    """Halo exchange without a communication library: the ping-pong buffers and two 64-bit flags of every rank
+    live in CUDA-IPC memory that both neighbours map (NVLink peer access).  A rank's edge-band launch stores its
+    rows straight into the neighbour's ghost rows (`mirror`), then bumps the neighbour's flag in stream order; the
+    neighbour's next edge-band launch waits for the flag in its own stream.  Interior launches never wait."""
+
+    def __init__(self, runner):
+        import ctypes
+        import torch
+        self.L = _lib.lib()
+        self.torch = torch
+        g, dist = runner.geo, runner.dist
+        self.elems = int(np.prod(g.local_padded))
+        self.ptrs, handles = [], []
+        for _ in range(3):  # buffer 0, buffer 1, flags
+            nbytes = self.elems * 8 if len(self.ptrs) < 2 else 64
+            ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            _lib.check(self.L.lora_peer_alloc(ctypes.byref(ptr), nbytes, h), "lora_peer_alloc")
+            self.ptrs.append(ptr.value)
+            handles.append(h.raw)
+        self.buf = [torch.as_tensor(_DevMem(self.ptrs[i], g.local_padded, "<f8"), device=runner.device) for i in range(2)]
+        self.flags_ptr = self.ptrs[2]  # [0]: written by prev, [1]: written by next
+        everyone = [None] * runner.world
+        dist.all_gather_object(everyone, handles, group=runner.group)
+        self.opened = []
+        self.peer = {}
+        for name, r in (("prev", g.prev), ("next", g.next)):
+            if r is None:
+                continue
+            ptrs = []
+            for h in everyone[r]:
+                q = ctypes.c_void_p()
+                _lib.check(self.L.lora_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(q)), "lora_peer_open")
+                ptrs.append(q.value)
+                self.opened.append(q.value)
+            self.peer[name] = ptrs
+        # element shift from my outer index to the neighbour's: my first slab rows -> its trailing ghost rows, my
+        # last slab rows -> its leading ghost rows
+        rest = int(np.prod(g.local_padded[1:])) if g.dim > 1 else 1
+        self.shift = {}
+        if g.prev is not None:
+            gp = SlabGeometry(g.dims, g.world, g.prev, align=runner.align, ghost=runner.ghost)
+            self.shift["prev"] = ((gp.wl + gp.slab) - g.wl) * rest
+        if g.next is not None:
+            gn = SlabGeometry(g.dims, g.world, g.next, align=runner.align, ghost=runner.ghost)
+            self.shift["next"] = (gn.wl - g.wl - g.slab) * rest
+        self.seq = 0  # sweeps issued so far: flags only ever grow
+
+    def mirror(self, side: str, which: int):
+        """Address in the neighbour's buffer `which` that corresponds to element 0 of mine."""
+        if side not in self.peer:
+            return None
+        return self.peer[side][which] + 8 * self.shift[side]
+
+    def wait_neighbours(self, stream):
+        """Block `stream` until both neighbours have finished the edge bands of the previous sweep: their rows are in
+        my ghost zones, and they no longer read the ghost zones I am about to overwrite."""
+        from ctypes import c_void_p
+        for k, side in enumerate(("prev", "next")):
+            if side in self.peer and self.seq > 0:
+                _lib.check(self.L.lora_stream_wait_flag_geq(c_void_p(stream.cuda_stream), c_void_p(self.flags_ptr + 8 * k),
+                                                            self.seq), "lora_stream_wait_flag_geq")
+
+    def signal_neighbours(self, stream):
+        from ctypes import c_void_p
+        self.seq += 1
+        if "prev" in self.peer:  # I am prev's `next`
+            _lib.check(self.L.lora_stream_write_flag(c_void_p(stream.cuda_stream), c_void_p(self.peer["prev"][2] + 8),
+                                                     self.seq), "lora_stream_write_flag")
+        if "next" in self.peer:  # I am next's `prev`
+            _lib.check(self.L.lora_stream_write_flag(c_void_p(stream.cuda_stream), c_void_p(self.peer["next"][2]),
+                                                     self.seq), "lora_stream_write_flag")
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        for q in self.opened:
+            self.L.lora_peer_close(q)
+        self.opened = []
+
+
 class SlabRunner:
     def __init__(self, shape: str, global_dims, params=None, mode: int = 0, group=None, device=None, step_fn=None,
                  fused_fn=None, temporal_block: int | None = None):
@@ -104,7 +192,8 @@ class SlabRunner:
         if injected and fused_fn is None:
             self.max_tb = 1
         ghost = 4 * self.max_tb if (dim == 1 and self.max_tb > 1) else None
-        self.geo = SlabGeometry(global_dims, self.world, self.rank, align=16 if dim == 1 else 1, ghost=ghost)
+        self.ghost, self.align = ghost, (16 if dim == 1 else 1)
+        self.geo = SlabGeometry(global_dims, self.world, self.rank, align=self.align, ghost=ghost)
         if not injected:
             from .plan import Plan
             self.plan = Plan(shape, self.geo.local_dims, params=params, mode=mode)
@@ -112,13 +201,38 @@ class SlabRunner:
         else:
             self.plan = None
         self.step_fn, self.fused_fn = step_fn, fused_fn
-        self.buf = [torch.zeros(self.geo.local_padded, dtype=torch.float64, device=self.device) for _ in range(2)]
+        # halo exchange: "p2p" = edge bands stored straight into the neighbours' ghost rows over NVLink peer memory
+        # (PeerHalo); "nccl" = ncclSend/ncclRecv of the bands (torch.distributed); CPU tests always use the latter
+        self.halo_mode = "nccl"
+        self.peer = None
+        g = self.geo
+        if self.cuda and self.world > 1 and not injected and os.environ.get("LORA_HALO", "p2p") == "p2p":
+            thin = [SlabGeometry(global_dims, self.world, r, align=self.align, ghost=ghost) for r in range(self.world)]
+            if all(t.slab >= t.wl + t.wr for t in thin):  # bands of neighbouring sides must not overlap
+                self.halo_mode = "p2p"
+        if self.halo_mode == "p2p":
+            self.peer = PeerHalo(self)
+            self.buf = self.peer.buf
+            dist.barrier(group=group)  # every rank has mapped its neighbours before anyone stores into them
+        else:
+            self.buf = [torch.zeros(g.local_padded, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.launch = 0   # kernel sweeps issued: the result sits in buf[launch % 2]
         self.time = 0     # time steps applied
         if self.cuda:
             self.comm_stream = torch.cuda.Stream(device=self.device)
             self.ev_main = torch.cuda.Event()
             self.ev_comm = torch.cuda.Event()
+
+    def close(self):
+        """Unmap the neighbours' buffers and free the peer memory (p2p mode); the runner is unusable afterwards."""
+        if self.peer is not None:
+            self.sync_ranks()
+            self.peer.close()
+            self.sync_ranks()
+            self.buf = None
+            for ptr in self.peer.ptrs:
+                self.peer.L.lora_peer_free(ptr)
+            self.peer = None
 
     # ---- data movement helpers (tests / parity; not on the timed path) ----
     def load_global(self, a_global: np.ndarray):
@@ -127,6 +241,15 @@ class SlabRunner:
         self.buf[0].copy_(t)
         self.buf[1].zero_()
         self.launch = self.time = 0
+        self.sync_ranks()
+
+    def sync_ranks(self):
+        """Host-side rendezvous after the buffers were (re)filled from outside: no neighbour may store into my ghost
+        rows before I have finished writing them myself (p2p mode)."""
+        if self.cuda:
+            self.torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
 
     def result(self):
         return self.buf[self.launch % 2]
@@ -176,12 +299,16 @@ class SlabRunner:
         lo, hi = g.off, g.off + g.slab  # the slab in plan-interior coordinates
 
         if self.max_tb > 1:
-            def compute(a, b, stream=None):
+            def compute(a, b, stream=None, mirror=None):
                 kw = {} if stream is None else {"stream": stream}
+                if mirror:
+                    kw["mirror"] = mirror
                 self.fused_fn(src, dst, self.buf[0], a, b, tb, self.time, g.prev is None, g.next is None, **kw)
         else:
-            def compute(a, b, stream=None):
+            def compute(a, b, stream=None, mirror=None):
                 kw = {} if stream is None else {"stream": stream}
+                if mirror:
+                    kw["mirror"] = mirror
                 self.step_fn(src, dst, a, b, **kw)
 
         if self.world == 1 or not self.cuda:
@@ -196,11 +323,20 @@ class SlabRunner:
             top = min(lo + g.wl, hi) if g.prev is not None else lo
             bot = max(hi - g.wr, top) if g.next is not None else hi
             with torch.cuda.stream(self.comm_stream):
-                if top > lo:
-                    compute(lo, top, self.comm_stream)
-                if bot < hi:
-                    compute(bot, hi, self.comm_stream)
-                self._exchange(dst)
+                if self.peer is not None:
+                    which = (self.launch + 1) % 2
+                    self.peer.wait_neighbours(self.comm_stream)
+                    if top > lo:
+                        compute(lo, top, self.comm_stream, self.peer.mirror("prev", which))
+                    if bot < hi:
+                        compute(bot, hi, self.comm_stream, self.peer.mirror("next", which))
+                    self.peer.signal_neighbours(self.comm_stream)
+                else:
+                    if top > lo:
+                        compute(lo, top, self.comm_stream)
+                    if bot < hi:
+                        compute(bot, hi, self.comm_stream)
+                    self._exchange(dst)
                 self.ev_comm.record(self.comm_stream)
             if bot > top:
                 compute(top, bot, main)
