@@ -45,6 +45,16 @@ SHAPE_TABLE = [("1d1r", (1 << 28,), 50), ("1d2r", (1 << 28,), 50), ("star2d1r", 
                ("box3d1r", (512, 512, 512), 100), ("star3d1r", (512, 512, 512), 100)]
 
 
+def measured_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel_key)
+    except (OSError, ValueError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -340,7 +350,10 @@ def main():
                 ops.gpu_1d2r(hin, hout, params, times, n)
             torch.cuda.synchronize()
             el = time.perf_counter() - t0
-            e2e_detail = {"launch_loop_ms_last_call": ops.last_loop_ms(), "whole_call_ms_last_call": ops.last_total_ms()}
+            e2e_detail = {"launch_loop_ms_last_call": ops.last_loop_ms(), "whole_call_ms_last_call": ops.last_total_ms(),
+                          "chunks": ops.last_chunks(),
+                          "overlap": "the operator cuts the line into ghost-margined chunks (4 x times cells) and overlaps "
+                                     "chunk H2D / launches / D2H on separate streams; results bit-identical to the plain path"}
         else:
             e2e_detail = {}
             def e2e_step():
@@ -398,7 +411,8 @@ def main():
         "gpu_launches": gpu_launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": None,
+                     "traffic": (measured_traffic(f"{shape}:{'x'.join(map(str, dims))}:tb{runner.max_tb}") or {}).get("bytes"),
+                     "traffic_source": (measured_traffic(f"{shape}:{'x'.join(map(str, dims))}:tb{runner.max_tb}") or {}).get("source"),
                      "kernel": (f"k_stencil1d_tb (tb = {runner.max_tb})" if runner.max_tb > 1 else "k_stencil1d")
                      if len(dims) == 1 else f"k_stencil{len(dims)}d",
                      "us_per_launch": us_per_launch,

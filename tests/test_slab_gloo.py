@@ -115,3 +115,31 @@ def test_slab_run_equals_single_domain(shape, dims, world, times, fused):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert ret.get(timeout=10) is True
+
+
+def test_peer_mirror_shifts_map_edge_bands_onto_neighbour_ghost_rows():
+    """The element shift the p2p halo exchange adds to a store address (slab.PeerHalo.shift) must send a rank's
+    first / last ghost-width slab rows exactly onto the neighbour's trailing / leading ghost rows: checked against
+    the global-row bookkeeping, for 1-D ghost zones and 2-D / 3-D storage halos, ragged splits included."""
+    from lorastencil_b200.slab import SlabGeometry
+    for dims, world, align, ghost in (((1 << 20,), 4, 16, 60), ((100003,), 3, 16, 16), ((300, 258), 4, 1, None),
+                                      ((40960, 64), 8, 1, None), ((33, 40, 136), 3, 1, None)):
+        gs = [SlabGeometry(dims, world, r, align=align, ghost=ghost) for r in range(world)]
+        rest = int(np.prod(gs[0].local_padded[1:])) if len(dims) > 1 else 1
+        for r, g in enumerate(gs):
+            first_global = g.global_rows().start  # global padded outer index of my local outer index 0
+            if g.prev is not None:
+                gp = gs[g.prev]
+                shift = ((gp.wl + gp.slab) - g.wl) * rest          # PeerHalo.shift["prev"]
+                assert shift % rest == 0
+                for u in range(g.wl, g.wl + gp.wr):                # my top band, local outer index u
+                    v = u + shift // rest                          # where it lands in prev's buffer
+                    assert gp.wl + gp.slab <= v < gp.local_padded[0]
+                    assert gp.global_rows().start + v == first_global + u  # same global row
+            if g.next is not None:
+                gn = gs[g.next]
+                shift = (gn.wl - g.wl - g.slab) * rest             # PeerHalo.shift["next"]
+                for u in range(g.wl + g.slab - gn.wl, g.wl + g.slab):  # my bottom band
+                    v = u + shift // rest
+                    assert 0 <= v < gn.wl
+                    assert gn.global_rows().start + v == first_global + u
