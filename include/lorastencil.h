@@ -130,7 +130,8 @@ int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void
  * `tb` consecutive launches into one sweep that keeps the intermediate grids on chip; results are
  * bit-identical to unfused launches, halo semantics (S2) included.  Default: 15 (the maximum) for the 1-D
  * shapes (or the environment variable LORA_TB).  2-D: 3 launches can be fused (tb >= 3 selects it, anything less
- * means one launch per step, which is the default; environment variable LORA_TB2=3).  3-D: always 1.  */
+ * means one launch per step); default 3 for the cross and diamond forms, 1 for the FP64-bound pyramid / direct
+ * forms (environment variable LORA_TB2=3|1).  3-D: always 1.  */
 int lora_plan_set_temporal_block(lora_plan_t *plan, int tb);
 int lora_plan_temporal_block(const lora_plan_t *plan);
 

@@ -97,6 +97,8 @@ __device__ __forceinline__ void tma_load_3d(void *dst_smem, const CUtensorMap *m
         : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -126,8 +126,8 @@ struct Geom2DTB {
     int m, n;
     int row_lo, row_hi;      // interior rows written by this launch
     int rows_per_chunk;
-    int nstrips;
-    int ntasks;
+    int nstrips, nchunks;
+    int ntasks;              // nstrips * nchunks, + 2 * nchunks when nstrips >= 3 (edge strips run as half-length tasks)
     int par0;                // parity of the launch count before level 0 (== parity of the source buffer)
     int virt_top, virt_bot;  // rows beyond that end are the global halo ring (virtual halo), not neighbour-slab data
     int vec4;

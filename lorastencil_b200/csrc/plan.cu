@@ -167,8 +167,9 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     const int warps_per_sm = (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
     if (dim == 2 && tb2_form(p->form)) {
-        // 2-D fusion (stencil2d_tb.cu) is opt-in: with 3 levels x 28 accumulators per lane the kernel is bound by
-        // the register file / issue slots and measures 283 GStencil/s against 335 unfused (profiles/)
+        // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 450 vs 335 GStencil/s unfused, diamond 385 vs
+        // 327); the pyramid form is FP64-bound already and loses (223 vs 339), so it stays at one launch per step
+        p->max_tb = (p->form == LORA_FORM_CROSS || p->form == LORA_FORM_DIAMOND) ? kTb2 : 1;
         if (const char *e = getenv("LORA_TB2")) p->max_tb = (atoi(e) >= kTb2) ? kTb2 : 1;
     }
     if (dim == 1) {
@@ -380,8 +381,8 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
     const int wout = strip_out_cols_2d_tb(tb);
     g.nstrips = (g.n + wout - 1) / wout;
     g.rows_per_chunk = (int)pick_len(hi - lo, g.nstrips, (long long)p->sm_count * 2 * kWarpsPerCta, 768, 96);
-    const int chunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
-    g.ntasks = chunks * g.nstrips;
+    g.nchunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
+    g.ntasks = g.nchunks * g.nstrips + (g.nstrips >= 3 ? 2 * g.nchunks : 0);
     g.par0 = launches_before & 1;
     g.virt_top = virt_lo ? 1 : 0;
     g.virt_bot = virt_hi ? 1 : 0;

@@ -51,39 +51,72 @@ struct SweepTB {
     bool vec4;
 };
 
-// virtual halo for a retired row of level `level` (time par0 + level): cells outside the interior are not computed
-// values.  Rare (rows of the halo ring, strips at the left / right edge), so kept out of line; values travel in
-// registers both ways (no local-memory round trip on the hot path).
-__device__ __noinline__ double4 patch_row_slow(double v0, double v1, double v2, double v3, int rho, bool row_out,
-                                               bool caller, int c0, int m, int n, long long pitch, const double *hsrc) {
-    double v[4] = {v0, v1, v2, v3};
+// Virtual halo for a retired row of level `level` (time par0 + level): cells outside the interior are not computed
+// values but (time even) ? caller's halo : 0.  Only tasks that can meet the ring run this (EDGE variant of the loop).
+//   * a whole row outside [0, m) (at most 3 per level at the top / bottom of the grid): loaded on the spot;
+//   * cells of an inside row whose column is outside [0, n) (first / last strip, every row): their caller's-halo
+//     values were PREFETCHED one iteration ago into hcol[] (levels alternate parity, so at most one level per
+//     sweep needs them), which keeps the L2 round trip off the row's dependency chain.
+// Out of line on purpose (14 inlined copies -- 2 levels x 7 phases -- made the patched loop 2.2x the size of the lean
+// one), and fed scalars rather than the SweepTB reference so that the sweep state stays in registers.
+struct PatchCtx {
+    const double *hsrc;
+    long long pitch;
+    int c0, m, n, par0;
+    bool virt_top, virt_bot, col_edge;
+};
+
+__device__ __noinline__ void patch_row_impl(double *v, double *hcol, int rho, int level, const PatchCtx s) {
+    const bool caller = ((s.par0 + level) & 1) == 0;  // warp-uniform: at even times the ring holds the caller's halo
+    const bool row_out = (s.virt_top && rho < 0) || (s.virt_bot && rho >= s.m);  // warp-uniform
+    if (row_out) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int c = c0 + q;
-        if (row_out || c < 0 || c >= n) {
+        for (int q = 0; q < 4; q++) {
+            const int c = s.c0 + q;
             double h = 0.0;
-            if (caller && rho >= -4 && rho < m + 4 && c >= -4 && c < n + 4) h = hsrc[(long long)rho * pitch + q];
+            if (caller && rho >= -4 && rho < s.m + 4 && c >= -4 && c < s.n + 4) h = s.hsrc[(long long)rho * s.pitch + q];
             v[q] = h;
         }
+    } else if (s.col_edge) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = s.c0 + q;
+            if (c < 0 || c >= s.n) v[q] = caller ? hcol[q] : 0.0;
+        }
     }
-    return make_double4(v[0], v[1], v[2], v[3]);
+    if (s.col_edge && caller) {  // fetch the next row's halo cells of this level
+        const int rn = rho + 1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = s.c0 + q;
+            const bool halo_col = (c >= -4 && c < 0) || (c >= s.n && c < s.n + 4);
+            hcol[q] = (halo_col && rn >= -4 && rn < s.m + 4) ? s.hsrc[(long long)rn * s.pitch + q] : 0.0;
+        }
+        // ... and pull the line of the row 12 further down into L2: every row's halo cells sit in a different DRAM
+        // page (the pitch is ~80 KB), one iteration is shorter than a DRAM round trip
+        const int rp = rho + 12;
+        const bool any_halo = (s.c0 < 0 && s.c0 + 3 >= -4) || (s.c0 + 3 >= s.n && s.c0 < s.n + 4);
+        if (any_halo && rp < s.m + 4) prefetch_l2(s.hsrc + (long long)rp * s.pitch);
+    }
 }
 
-__device__ __forceinline__ void patch_row(double (&v)[4], int rho, int level, const SweepTB &s) {
-    const bool row_out = (s.virt_top && rho < 0) || (s.virt_bot && rho >= s.m);
-    if (row_out || s.col_edge) {  // warp-uniform
-        const bool caller = ((s.par0 + level) & 1) == 0;  // at even times the ring holds the caller's halo
-        const double4 p = patch_row_slow(v[0], v[1], v[2], v[3], rho, row_out, caller, s.c0, s.m, s.n, s.pitch, s.hsrc);
-        v[0] = p.x;
-        v[1] = p.y;
-        v[2] = p.z;
-        v[3] = p.w;
-    }
+__device__ __forceinline__ void patch_row(double (&v)[4], double (&hcol)[4], int rho, int level, const SweepTB &s) {
+    PatchCtx c;
+    c.hsrc = s.hsrc;
+    c.pitch = s.pitch;
+    c.c0 = s.c0;
+    c.m = s.m;
+    c.n = s.n;
+    c.par0 = s.par0;
+    c.virt_top = s.virt_top;
+    c.virt_bot = s.virt_bot;
+    c.col_edge = s.col_edge;
+    patch_row_impl(v, hcol, rho, level, c);
 }
 
-template <int FORM, int TB, int PH>
-__device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NACC][4], const Weights2D &w,
-                                          const WeightsDirect49 &wd) {
+template <int FORM, int TB, bool EDGE, int PH>
+__device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NACC][4], double (&hcol)[4],
+                                          const Weights2D &w, const WeightsDirect49 &wd) {
     const int st = i / kRowsPerStage, rr = i % kRowsPerStage, slot = st % kStages;
     if (rr == 0) mbar_wait(&s.bars[slot], (st / kStages) & 1);
     const double2 *rowp = reinterpret_cast<const double2 *>(s.ring + slot * kStageElems + rr * kBoxCols + 4 * s.lane);
@@ -112,7 +145,7 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
 #pragma unroll
         for (int q = 0; q < 4; q++) v[q] = done[q];  // reborn by the next row's dr = -3 term (an assignment)
         if (lv == TB) break;
-        patch_row(v, s.rho0 + i - 3 * lv, lv, s);
+        if (EDGE) patch_row(v, hcol, s.rho0 + i - 3 * lv, lv, s);
         // window of level lv: own 4 columns + 3 from either neighbour lane
         x[4] = v[0];
         x[5] = v[1];
@@ -151,6 +184,44 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
     }
 }
 
+// The row loop.  Groups of 7 rows (one turn of the accumulator rings) whose retired rows can meet the halo ring run
+// the phases WITH the patch code, all others the lean phases: a task at the top or bottom of the grid pays for
+// the patch code during its first / last few groups only; tasks of the first / last strip pay for it throughout.
+template <int FORM, int TB>
+__device__ __forceinline__ void sweep_rows(SweepTB &s, const Weights2D &w, const WeightsDirect49 &wd) {
+    double A[TB][NACC][4];
+#pragma unroll
+    for (int lv = 0; lv < TB; lv++)
+#pragma unroll
+        for (int j = 0; j < NACC; j++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) A[lv][j][q] = 0.0;
+    double hcol[4] = {0.0, 0.0, 0.0, 0.0};  // prefetched caller's-halo cells of the next row (see patch_row)
+
+    for (int base = 0; base < s.nin; base += NACC) {
+        // rows retired by levels 1 .. TB-1 during this group: [rho0 + base - 3 (TB - 1), rho0 + base + 3]
+        const bool edge = s.col_edge || (s.virt_top && s.rho0 + base - 3 * (TB - 1) < 0) ||
+                          (s.virt_bot && s.rho0 + base + 3 >= s.m);
+        if (edge) {
+            if (base + 0 < s.nin) row_phase<FORM, TB, true, 0>(base + 0, s, A, hcol, w, wd);
+            if (base + 1 < s.nin) row_phase<FORM, TB, true, 1>(base + 1, s, A, hcol, w, wd);
+            if (base + 2 < s.nin) row_phase<FORM, TB, true, 2>(base + 2, s, A, hcol, w, wd);
+            if (base + 3 < s.nin) row_phase<FORM, TB, true, 3>(base + 3, s, A, hcol, w, wd);
+            if (base + 4 < s.nin) row_phase<FORM, TB, true, 4>(base + 4, s, A, hcol, w, wd);
+            if (base + 5 < s.nin) row_phase<FORM, TB, true, 5>(base + 5, s, A, hcol, w, wd);
+            if (base + 6 < s.nin) row_phase<FORM, TB, true, 6>(base + 6, s, A, hcol, w, wd);
+        } else {
+            if (base + 0 < s.nin) row_phase<FORM, TB, false, 0>(base + 0, s, A, hcol, w, wd);
+            if (base + 1 < s.nin) row_phase<FORM, TB, false, 1>(base + 1, s, A, hcol, w, wd);
+            if (base + 2 < s.nin) row_phase<FORM, TB, false, 2>(base + 2, s, A, hcol, w, wd);
+            if (base + 3 < s.nin) row_phase<FORM, TB, false, 3>(base + 3, s, A, hcol, w, wd);
+            if (base + 4 < s.nin) row_phase<FORM, TB, false, 4>(base + 4, s, A, hcol, w, wd);
+            if (base + 5 < s.nin) row_phase<FORM, TB, false, 5>(base + 5, s, A, hcol, w, wd);
+            if (base + 6 < s.nin) row_phase<FORM, TB, false, 6>(base + 6, s, A, hcol, w, wd);
+        }
+    }
+}
+
 template <int FORM, int TB>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, 2)
 k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2DTB g,
@@ -161,9 +232,32 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (task >= g.ntasks) return;  // warps never synchronise with each other
 
     constexpr int kStripOut = kWarpCols - 8 * (TB - 1);  // columns a strip writes
-    const int strip = task % g.nstrips, chunk = task / g.nstrips;
-    const int r0 = g.row_lo + chunk * g.rows_per_chunk;  // first interior row this chunk writes
-    const int R = min(g.rows_per_chunk, g.row_hi - r0);
+    // Edge tasks (first / last strip of every chunk, first / last chunk) run the slower patched loop.  They are
+    // scheduled first, and the edge strips -- which patch every row -- are cut into half-length tasks, so that they
+    // never form the tail of the launch.  Task order: [0, 4 nchunks) edge-strip halves, then the inner strips chunk
+    // by chunk with the first and last chunk in front.
+    int strip, r0, R;
+    if (g.nstrips >= 3) {
+        const int nedge = 4 * g.nchunks;
+        if (task < nedge) {
+            strip = (task & 1) ? g.nstrips - 1 : 0;
+            const int e = task >> 1, chunk = e >> 1, half = (g.rows_per_chunk + 1) / 2;
+            r0 = g.row_lo + chunk * g.rows_per_chunk + (e & 1) * half;
+            R = min((e & 1) ? g.rows_per_chunk - half : half, g.row_hi - r0);
+        } else {
+            const int t = task - nedge, inner = g.nstrips - 2;
+            strip = 1 + t % inner;
+            int chunk = t / inner;
+            chunk = chunk == 0 ? 0 : (chunk == 1 ? g.nchunks - 1 : chunk - 1);
+            r0 = g.row_lo + chunk * g.rows_per_chunk;
+            R = min(g.rows_per_chunk, g.row_hi - r0);
+        }
+    } else {
+        strip = task % g.nstrips;
+        r0 = g.row_lo + (task / g.nstrips) * g.rows_per_chunk;
+        R = min(g.rows_per_chunk, g.row_hi - r0);
+    }
+    if (R <= 0) return;
     const int cs = strip * kStripOut;                    // first interior column the strip writes
     const int cw = cs - 4 * (TB - 1);                    // first interior column the warp computes
 
@@ -205,23 +299,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     __syncwarp();
 
-    double A[TB][NACC][4];
-#pragma unroll
-    for (int lv = 0; lv < TB; lv++)
-#pragma unroll
-        for (int j = 0; j < NACC; j++)
-#pragma unroll
-            for (int q = 0; q < 4; q++) A[lv][j][q] = 0.0;
-
-    for (int base = 0; base < s.nin; base += NACC) {
-        if (base + 0 < s.nin) row_phase<FORM, TB, 0>(base + 0, s, A, w, wd);
-        if (base + 1 < s.nin) row_phase<FORM, TB, 1>(base + 1, s, A, w, wd);
-        if (base + 2 < s.nin) row_phase<FORM, TB, 2>(base + 2, s, A, w, wd);
-        if (base + 3 < s.nin) row_phase<FORM, TB, 3>(base + 3, s, A, w, wd);
-        if (base + 4 < s.nin) row_phase<FORM, TB, 4>(base + 4, s, A, w, wd);
-        if (base + 5 < s.nin) row_phase<FORM, TB, 5>(base + 5, s, A, w, wd);
-        if (base + 6 < s.nin) row_phase<FORM, TB, 6>(base + 6, s, A, w, wd);
-    }
+    sweep_rows<FORM, TB>(s, w, wd);
 }
 
 template <int FORM, int TB>

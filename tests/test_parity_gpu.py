@@ -171,9 +171,10 @@ def test_plan_api_partial_ranges_and_device_buffers():
             assert np.array_equal(got[:-1], full[:-1])
         else:
             assert np.array_equal(got, full)
-        # 1-D fuses the 3 launches of `run` into one temporally blocked sweep; 2-D (fusion is opt-in) and 3-D launch
-        # once per step
-        assert plan.launches == len(cuts) - 1 + (1 if oracle.dim_of(shape) == 1 else 3)
+        # 1-D and the 2-D star forms fuse the 3 launches of `run` into one temporally blocked sweep; the FP64-bound
+        # 2-D box form and 3-D launch once per step
+        fused = oracle.dim_of(shape) == 1 or shape in ("star2d1r", "star2d3r")
+        assert plan.launches == len(cuts) - 1 + (1 if fused else 3)
 
 
 def test_linearity_and_shift_invariance_at_scale():
@@ -314,7 +315,7 @@ def test_temporal_blocking_2d_equals_unfused_launches(shape, dims):
     af = rng.uniform(-1, 1, a.shape)
     eff = oracle.effective_params(shape)
     plan = ls.Plan(shape, dims)
-    assert plan.temporal_block == 1  # 2-D fusion is opt-in (not yet faster than one launch per step)
+    assert plan.temporal_block == (1 if shape == "box2d1r" else 3)  # the FP64-bound pyramid form is not fused by default
     exact_upto = {"box2d1r": 5, "star2d1r": 6, "star2d3r": 9}[shape]
     for data in (a, af):
         for times in (3, 4, 5, 6, 7, 9, 10):
