@@ -95,7 +95,8 @@ double lora_last_total_ms(void);
 /* The 1-D drop-in operators overlap their copies with their launches: a cell after `times` launches depends on
  * 4 * times cells either side only, so a long line is cut into chunks with ghost margins of that width; every
  * chunk runs all its launches on its own while the next chunk's H2D copy and the previous chunk's D2H copy are
- * in flight (bit-identical results; lora_last_loop_ms is then the sum of the chunks' launch loops).  Returns how
+ * in flight (bit-identical results; lora_last_loop_ms and the banner's Time are then the time during which at least
+ * one chunk's launch loop was running).  Returns how
  * many chunks the last lora_gpu_* call used (1 = plain H2D -> launches -> D2H).  Environment: LORA_CHUNKS=0
  * disables the overlap, LORA_CHUNKS=k forces k chunks. */
 int lora_last_chunks(void);

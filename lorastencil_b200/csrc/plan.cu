@@ -5,6 +5,7 @@
 //   src/1d/gpu_1r.cu:90-137, src/1d/gpu_2r.cu:91-137, src/2d/gpu.cu:276-557,
 //   src/3d/gpu_box.cu:143-226, src/3d/gpu_star.cu:136-195
 // (weight factorisation -> upload -> cudaMalloc x2 -> launch loop -> timing printout -> D2H).
+#include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -703,16 +704,14 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
     CU_DIE(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     CU_DIE(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
     for (auto &st : s_comp) CU_DIE(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> in_done(K), comp_done(K), out_done(K);
+    std::vector<cudaEvent_t> in_done(K), comp_done(K), out_done(K), t0(K);
     std::vector<lora_plan *> plans(K, nullptr);
     for (long long c = 0; c < K; c++) {
         CU_DIE(cudaEventCreateWithFlags(&in_done[c], cudaEventDisableTiming));
-        CU_DIE(cudaEventCreateWithFlags(&comp_done[c], cudaEventDisableTiming));
+        CU_DIE(cudaEventCreate(&comp_done[c]));  // timed: end of the chunk's launch loop
         CU_DIE(cudaEventCreateWithFlags(&out_done[c], cudaEventDisableTiming));
+        CU_DIE(cudaEventCreate(&t0[c]));         // timed: start of the chunk's launch loop
     }
-    cudaEvent_t t_first, t_last;
-    CU_DIE(cudaEventCreate(&t_first));
-    CU_DIE(cudaEventCreate(&t_last));
     for (long long c = 0; c < K; c++) {
         const long long lo = c * C, hi = (lo + C < n) ? lo + C : n;
         const long long gl = G < lo ? G : lo, gr = G < n - hi ? G : n - hi;
@@ -730,7 +729,7 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
         const long long d[1] = {nloc};
         if (lora_plan_create(&plans[c], shape, mode, params, d) != LORA_OK) die_plan("plan");
         CU_DIE(cudaStreamWaitEvent(sc, in_done[c], 0));
-        if (c == 0) CU_DIE(cudaEventRecord(t_first, sc));
+        CU_DIE(cudaEventRecord(t0[c], sc));
         if (run_fused_1d(plans[c], b0, b1, times, virt_lo, virt_hi, sc) != LORA_OK) die_plan("launch");
         CU_DIE(cudaEventRecord(comp_done[c], sc));
 
@@ -745,28 +744,39 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
         }
         if (c == K - 1) cnt += 3;
         CU_DIE(cudaStreamWaitEvent(s_out, comp_done[c], 0));
-        if (c == K - 1) {
-            if (K >= 2) CU_DIE(cudaStreamWaitEvent(s_out, comp_done[K - 2], 0));
-            CU_DIE(cudaEventRecord(t_last, s_out));  // every chunk's launches have finished
-        }
         CU_DIE(cudaMemcpyAsync(out + dst_off, res + src_off, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
         CU_DIE(cudaEventRecord(out_done[c], s_out));
     }
     CU_DIE(cudaStreamSynchronize(s_out));
     for (auto &st : s_comp) CU_DIE(cudaStreamSynchronize(st));
     CU_DIE(cudaStreamSynchronize(s_in));
-    // the reference's timed region is its launch loop (src/1d/gpu_1r.cu:118-126): here first launch -> last launch
-    // done, which also contains whatever time the launches spent waiting for a chunk's H2D copy
-    float ms = 0;
-    CU_DIE(cudaEventElapsedTime(&ms, t_first, t_last));
+    // The reference's timed region is its launch loop (src/1d/gpu_1r.cu:118-126).  Here the chunks' launch loops
+    // overlap each other and the copies, so the equivalent is the time during which AT LEAST ONE chunk's launch
+    // loop was running: the union of the intervals [t0[c], comp_done[c]] (waiting for a chunk's H2D is not in it).
+    std::vector<std::pair<float, float>> iv(K);
+    for (long long c = 0; c < K; c++) {
+        CU_DIE(cudaEventElapsedTime(&iv[c].first, t0[0], t0[c]));
+        CU_DIE(cudaEventElapsedTime(&iv[c].second, t0[0], comp_done[c]));
+    }
+    std::sort(iv.begin(), iv.end());
+    float ms = 0, cur_lo = iv[0].first, cur_hi = iv[0].second;
+    for (long long c = 1; c < K; c++) {
+        if (iv[c].first > cur_hi) {
+            ms += cur_hi - cur_lo;
+            cur_lo = iv[c].first;
+            cur_hi = iv[c].second;
+        } else if (iv[c].second > cur_hi) {
+            cur_hi = iv[c].second;
+        }
+    }
+    ms += cur_hi - cur_lo;
     for (long long c = 0; c < K; c++) {
         lora_plan_destroy(plans[c]);
         cudaEventDestroy(in_done[c]);
         cudaEventDestroy(comp_done[c]);
         cudaEventDestroy(out_done[c]);
+        cudaEventDestroy(t0[c]);
     }
-    cudaEventDestroy(t_first);
-    cudaEventDestroy(t_last);
     cudaStreamDestroy(s_in);
     cudaStreamDestroy(s_out);
     for (auto &st : s_comp) cudaStreamDestroy(st);

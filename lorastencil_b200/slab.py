@@ -106,18 +106,23 @@ class PeerHalo:
         g, dist = runner.geo, runner.dist
         self.elems = int(np.prod(g.local_padded))
         self.ptrs, handles = [], []
-        for _ in range(3):  # buffer 0, buffer 1, flags
-            nbytes = self.elems * 8 if len(self.ptrs) < 2 else 64
-            ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-            _lib.check(self.L.lora_peer_alloc(ctypes.byref(ptr), nbytes, h), "lora_peer_alloc")
-            self.ptrs.append(ptr.value)
-            handles.append(h.raw)
-        self.buf = [torch.as_tensor(_DevMem(self.ptrs[i], g.local_padded, "<f8"), device=runner.device) for i in range(2)]
-        self.flags_ptr = self.ptrs[2]  # [0]: written by prev, [1]: written by next
-        everyone = [None] * runner.world
-        dist.all_gather_object(everyone, handles, group=runner.group)
         self.opened = []
         self.peer = {}
+        try:
+            for _ in range(3):  # buffer 0, buffer 1, flags
+                nbytes = self.elems * 8 if len(self.ptrs) < 2 else 64
+                ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+                _lib.check(self.L.lora_peer_alloc(ctypes.byref(ptr), nbytes, h), "lora_peer_alloc")
+                self.ptrs.append(ptr.value)
+                handles.append(h.raw)
+        except Exception:  # noqa: BLE001 -- the gather below is collective: every rank has to reach it
+            handles = None
+        everyone = [None] * runner.world
+        dist.all_gather_object(everyone, handles, group=runner.group)
+        if any(h is None for h in everyone):
+            raise _lib.LoraError("lora_peer_alloc failed on some rank")
+        self.buf = [torch.as_tensor(_DevMem(self.ptrs[i], g.local_padded, "<f8"), device=runner.device) for i in range(2)]
+        self.flags_ptr = self.ptrs[2]  # [0]: written by prev, [1]: written by next
         for name, r in (("prev", g.prev), ("next", g.next)):
             if r is None:
                 continue
@@ -171,6 +176,13 @@ class PeerHalo:
             self.L.lora_peer_close(q)
         self.opened = []
 
+    def abandon(self):
+        """Give everything back after a failed collective set-up."""
+        self.close()
+        for ptr in self.ptrs:
+            self.L.lora_peer_free(ptr)
+        self.ptrs = []
+
 
 class SlabRunner:
     def __init__(self, shape: str, global_dims, params=None, mode: int = 0, group=None, device=None, step_fn=None,
@@ -211,10 +223,25 @@ class SlabRunner:
             if all(t.slab >= t.wl + t.wr for t in thin):  # bands of neighbouring sides must not overlap
                 self.halo_mode = "p2p"
         if self.halo_mode == "p2p":
-            self.peer = PeerHalo(self)
-            self.buf = self.peer.buf
-            dist.barrier(group=group)  # every rank has mapped its neighbours before anyone stores into them
-        else:
+            # all ranks switch together: if CUDA IPC / peer mapping fails anywhere (container without IPC, GPUs
+            # without peer access), everybody falls back to NCCL send/recv
+            err = None
+            try:
+                self.peer = PeerHalo(self)
+            except Exception as e:  # noqa: BLE001 -- whatever went wrong, the collective decision is what matters
+                err = e
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 1:
+                self.buf = self.peer.buf
+            else:
+                if self.peer is not None:
+                    self.peer.abandon()
+                    self.peer = None
+                self.halo_mode = "nccl"
+                if self.rank == 0:
+                    print(f"lorastencil_b200.slab: peer-memory halo exchange unavailable ({err}); using NCCL", flush=True)
+        if self.halo_mode != "p2p":
             self.buf = [torch.zeros(g.local_padded, dtype=torch.float64, device=self.device) for _ in range(2)]
         self.launch = 0   # kernel sweeps issued: the result sits in buf[launch % 2]
         self.time = 0     # time steps applied
