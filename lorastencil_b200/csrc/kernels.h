@@ -118,6 +118,12 @@ struct Geom2D {
     long long mirror;  // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
+// fused 2-D kernel: tasks of the first / last strip stage their rows' caller's-halo columns in shared memory
+constexpr int kTb2Max = 3;
+constexpr int kEdgeRows2Tb = 160;                          // longest edge-strip task (output rows)
+constexpr int kHalRows2Tb = kEdgeRows2Tb + 6 * kTb2Max;    // its input rows
+constexpr int kSmem2Tb = kSmem12 + kWarpsPerCta * kHalRows2Tb * 8 * 8;
+
 // temporally blocked 2-D sweep (stencil2d_tb.cu): TB (odd) launches fused; strips write 128 - 8 (TB - 1) columns
 struct Geom2DTB {
     double *out;
@@ -127,7 +133,8 @@ struct Geom2DTB {
     int row_lo, row_hi;      // interior rows written by this launch
     int rows_per_chunk;
     int nstrips, nchunks;
-    int ntasks;              // nstrips * nchunks, + 2 * nchunks when nstrips >= 3 (edge strips run as half-length tasks)
+    int edge_rows, nedge;    // nstrips >= 3: the two edge strips run as 2 * nedge tasks of edge_rows (<= kEdgeRows2Tb) rows
+    int ntasks;              // nstrips >= 3: 2 * nedge + (nstrips - 2) * nchunks; else nstrips * nchunks
     int par0;                // parity of the launch count before level 0 (== parity of the source buffer)
     int virt_top, virt_bot;  // rows beyond that end are the global halo ring (virtual halo), not neighbour-slab data
     int vec4;

@@ -168,7 +168,7 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     const int warps_per_sm = (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
     if (dim == 2 && tb2_form(p->form)) {
-        // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 450 vs 335 GStencil/s unfused, diamond 385 vs
+        // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 560 vs 335 GStencil/s unfused, diamond 387 vs
         // 327); the pyramid form is FP64-bound already and loses (223 vs 339), so it stays at one launch per step
         p->max_tb = (p->form == LORA_FORM_CROSS || p->form == LORA_FORM_DIAMOND) ? kTb2 : 1;
         if (const char *e = getenv("LORA_TB2")) p->max_tb = (atoi(e) >= kTb2) ? kTb2 : 1;
@@ -381,9 +381,44 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
     g.row_hi = (int)hi;
     const int wout = strip_out_cols_2d_tb(tb);
     g.nstrips = (g.n + wout - 1) / wout;
-    g.rows_per_chunk = (int)pick_len(hi - lo, g.nstrips, (long long)p->sm_count * 2 * kWarpsPerCta, 768, 96);
-    g.nchunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
-    g.ntasks = g.nchunks * g.nstrips + (g.nstrips >= 3 ? 2 * g.nchunks : 0);
+    const long long slots = (long long)p->sm_count * 2 * kWarpsPerCta;
+    const long long rows = hi - lo;
+    if (g.nstrips >= 3) {
+        // Inner strips are cut into nchunks tasks each; the two edge strips patch every row (about twice the time
+        // per row), so they are cut into tasks of half that length (<= kEdgeRows2Tb rows: their halo columns are
+        // staged in shared memory).  Take the fewest waves k and, within it, the most chunks such that all tasks fit
+        // k x the resident warps: equal-length tasks in whole waves, no straggler round.
+        long long edge_cap = kEdgeRows2Tb;
+        if (const char *e = getenv("LORA_TB2_EDGE_ROWS")) {  // tuning knob
+            const long long v = atoll(e);
+            if (v >= 8 && v <= kEdgeRows2Tb) edge_cap = v;
+        }
+        long long best_chunks = 0;
+        for (long long k = 1; k <= 64 && !best_chunks; k++) {
+            for (long long nc = (rows + 95) / 96; nc >= 1; nc--) {  // most chunks first
+                const long long R = (rows + nc - 1) / nc;
+                if (R > 768) break;
+                const long long el = R / 2 < edge_cap ? (R + 1) / 2 : edge_cap;
+                const long long tasks = (g.nstrips - 2) * ((rows + R - 1) / R) + 2 * ((rows + el - 1) / el);
+                if (tasks <= k * slots) {
+                    best_chunks = nc;
+                    break;
+                }
+            }
+        }
+        if (!best_chunks) best_chunks = (rows + 767) / 768;
+        g.rows_per_chunk = (int)((rows + best_chunks - 1) / best_chunks);
+        g.nchunks = (int)((rows + g.rows_per_chunk - 1) / g.rows_per_chunk);
+        g.edge_rows = (int)(g.rows_per_chunk / 2 < edge_cap ? (g.rows_per_chunk + 1) / 2 : edge_cap);
+        g.nedge = (int)((rows + g.edge_rows - 1) / g.edge_rows);
+        g.ntasks = 2 * g.nedge + (g.nstrips - 2) * g.nchunks;
+    } else {
+        g.rows_per_chunk = (int)pick_len(rows, g.nstrips, slots, kEdgeRows2Tb, 32);
+        g.nchunks = (int)((rows + g.rows_per_chunk - 1) / g.rows_per_chunk);
+        g.edge_rows = g.rows_per_chunk;
+        g.nedge = 0;
+        g.ntasks = g.nstrips * g.nchunks;
+    }
     g.par0 = launches_before & 1;
     g.virt_top = virt_lo ? 1 : 0;
     g.virt_bot = virt_hi ? 1 : 0;

@@ -38,6 +38,7 @@ struct SweepTB {
     uint64_t *bars;
     double *orow;           // output row pointer (this lane's first column), advances by pitch once rows retire
     const double *hsrc;     // caller's halo: padded buffer 0, pointing at (row 0, this lane's first column)
+    const double *hal;      // shared memory: caller's halo columns of the task's rows, [nin][4 left + 4 right]
     long long pitch;
     int nin, nst, boxcol, row0_padded, lane;
     int rho0;               // interior row of input row 0 of the chunk (= r0 - 3 TB)
@@ -57,16 +58,13 @@ struct SweepTB {
 //   * cells of an inside row whose column is outside [0, n) (first / last strip, every row): their caller's-halo
 //     values were PREFETCHED one iteration ago into hcol[] (levels alternate parity, so at most one level per
 //     sweep needs them), which keeps the L2 round trip off the row's dependency chain.
-// Out of line on purpose (14 inlined copies -- 2 levels x 7 phases -- made the patched loop 2.2x the size of the lean
-// one), and fed scalars rather than the SweepTB reference so that the sweep state stays in registers.
-struct PatchCtx {
-    const double *hsrc;
-    long long pitch;
-    int c0, m, n, par0;
-    bool virt_top, virt_bot, col_edge;
-};
-
-__device__ __noinline__ void patch_row_impl(double *v, double *hcol, int rho, int level, const PatchCtx s) {
+// Virtual halo for a retired row of level `level` (time par0 + level): cells outside the interior are not computed
+// values but (time even) ? caller's halo : 0.  Only groups of rows that can meet the ring run this (EDGE phases).
+//   * a whole row outside [0, m) (at most 3 per level at the top / bottom of the grid): loaded on the spot;
+//   * cells of an inside row whose column is outside [0, n) (first / last strip, every row): the caller's-halo
+//     columns of all the task's rows were staged in shared memory when the task started (s.hal: 4 left + 4 right
+//     doubles per row), so the patch is a predicated LDS, not an L2 / DRAM round trip per row.
+__device__ __forceinline__ void patch_row(double (&v)[4], int i_row, int rho, int level, const SweepTB &s) {
     const bool caller = ((s.par0 + level) & 1) == 0;  // warp-uniform: at even times the ring holds the caller's halo
     const bool row_out = (s.virt_top && rho < 0) || (s.virt_bot && rho >= s.m);  // warp-uniform
     if (row_out) {
@@ -78,45 +76,21 @@ __device__ __noinline__ void patch_row_impl(double *v, double *hcol, int rho, in
             v[q] = h;
         }
     } else if (s.col_edge) {
+        const double *hr = s.hal + 8 * min(max(i_row, 0), s.nin - 1);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int c = s.c0 + q;
-            if (c < 0 || c >= s.n) v[q] = caller ? hcol[q] : 0.0;
+            if (c < 0)
+                v[q] = (caller && c >= -4) ? hr[c + 4] : 0.0;
+            else if (c >= s.n)
+                v[q] = (caller && c < s.n + 4) ? hr[4 + c - s.n] : 0.0;
         }
     }
-    if (s.col_edge && caller) {  // fetch the next row's halo cells of this level
-        const int rn = rho + 1;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int c = s.c0 + q;
-            const bool halo_col = (c >= -4 && c < 0) || (c >= s.n && c < s.n + 4);
-            hcol[q] = (halo_col && rn >= -4 && rn < s.m + 4) ? s.hsrc[(long long)rn * s.pitch + q] : 0.0;
-        }
-        // ... and pull the line of the row 12 further down into L2: every row's halo cells sit in a different DRAM
-        // page (the pitch is ~80 KB), one iteration is shorter than a DRAM round trip
-        const int rp = rho + 12;
-        const bool any_halo = (s.c0 < 0 && s.c0 + 3 >= -4) || (s.c0 + 3 >= s.n && s.c0 < s.n + 4);
-        if (any_halo && rp < s.m + 4) prefetch_l2(s.hsrc + (long long)rp * s.pitch);
-    }
-}
-
-__device__ __forceinline__ void patch_row(double (&v)[4], double (&hcol)[4], int rho, int level, const SweepTB &s) {
-    PatchCtx c;
-    c.hsrc = s.hsrc;
-    c.pitch = s.pitch;
-    c.c0 = s.c0;
-    c.m = s.m;
-    c.n = s.n;
-    c.par0 = s.par0;
-    c.virt_top = s.virt_top;
-    c.virt_bot = s.virt_bot;
-    c.col_edge = s.col_edge;
-    patch_row_impl(v, hcol, rho, level, c);
 }
 
 template <int FORM, int TB, bool EDGE, int PH>
-__device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NACC][4], double (&hcol)[4],
-                                          const Weights2D &w, const WeightsDirect49 &wd) {
+__device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NACC][4], const Weights2D &w,
+                                          const WeightsDirect49 &wd) {
     const int st = i / kRowsPerStage, rr = i % kRowsPerStage, slot = st % kStages;
     if (rr == 0) mbar_wait(&s.bars[slot], (st / kStages) & 1);
     const double2 *rowp = reinterpret_cast<const double2 *>(s.ring + slot * kStageElems + rr * kBoxCols + 4 * s.lane);
@@ -145,7 +119,7 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
 #pragma unroll
         for (int q = 0; q < 4; q++) v[q] = done[q];  // reborn by the next row's dr = -3 term (an assignment)
         if (lv == TB) break;
-        if (EDGE) patch_row(v, hcol, s.rho0 + i - 3 * lv, lv, s);
+        if (EDGE) patch_row(v, i - 3 * lv, s.rho0 + i - 3 * lv, lv, s);
         // window of level lv: own 4 columns + 3 from either neighbour lane
         x[4] = v[0];
         x[5] = v[1];
@@ -196,28 +170,27 @@ __device__ __forceinline__ void sweep_rows(SweepTB &s, const Weights2D &w, const
         for (int j = 0; j < NACC; j++)
 #pragma unroll
             for (int q = 0; q < 4; q++) A[lv][j][q] = 0.0;
-    double hcol[4] = {0.0, 0.0, 0.0, 0.0};  // prefetched caller's-halo cells of the next row (see patch_row)
 
     for (int base = 0; base < s.nin; base += NACC) {
         // rows retired by levels 1 .. TB-1 during this group: [rho0 + base - 3 (TB - 1), rho0 + base + 3]
         const bool edge = s.col_edge || (s.virt_top && s.rho0 + base - 3 * (TB - 1) < 0) ||
                           (s.virt_bot && s.rho0 + base + 3 >= s.m);
         if (edge) {
-            if (base + 0 < s.nin) row_phase<FORM, TB, true, 0>(base + 0, s, A, hcol, w, wd);
-            if (base + 1 < s.nin) row_phase<FORM, TB, true, 1>(base + 1, s, A, hcol, w, wd);
-            if (base + 2 < s.nin) row_phase<FORM, TB, true, 2>(base + 2, s, A, hcol, w, wd);
-            if (base + 3 < s.nin) row_phase<FORM, TB, true, 3>(base + 3, s, A, hcol, w, wd);
-            if (base + 4 < s.nin) row_phase<FORM, TB, true, 4>(base + 4, s, A, hcol, w, wd);
-            if (base + 5 < s.nin) row_phase<FORM, TB, true, 5>(base + 5, s, A, hcol, w, wd);
-            if (base + 6 < s.nin) row_phase<FORM, TB, true, 6>(base + 6, s, A, hcol, w, wd);
+            if (base + 0 < s.nin) row_phase<FORM, TB, true, 0>(base + 0, s, A, w, wd);
+            if (base + 1 < s.nin) row_phase<FORM, TB, true, 1>(base + 1, s, A, w, wd);
+            if (base + 2 < s.nin) row_phase<FORM, TB, true, 2>(base + 2, s, A, w, wd);
+            if (base + 3 < s.nin) row_phase<FORM, TB, true, 3>(base + 3, s, A, w, wd);
+            if (base + 4 < s.nin) row_phase<FORM, TB, true, 4>(base + 4, s, A, w, wd);
+            if (base + 5 < s.nin) row_phase<FORM, TB, true, 5>(base + 5, s, A, w, wd);
+            if (base + 6 < s.nin) row_phase<FORM, TB, true, 6>(base + 6, s, A, w, wd);
         } else {
-            if (base + 0 < s.nin) row_phase<FORM, TB, false, 0>(base + 0, s, A, hcol, w, wd);
-            if (base + 1 < s.nin) row_phase<FORM, TB, false, 1>(base + 1, s, A, hcol, w, wd);
-            if (base + 2 < s.nin) row_phase<FORM, TB, false, 2>(base + 2, s, A, hcol, w, wd);
-            if (base + 3 < s.nin) row_phase<FORM, TB, false, 3>(base + 3, s, A, hcol, w, wd);
-            if (base + 4 < s.nin) row_phase<FORM, TB, false, 4>(base + 4, s, A, hcol, w, wd);
-            if (base + 5 < s.nin) row_phase<FORM, TB, false, 5>(base + 5, s, A, hcol, w, wd);
-            if (base + 6 < s.nin) row_phase<FORM, TB, false, 6>(base + 6, s, A, hcol, w, wd);
+            if (base + 0 < s.nin) row_phase<FORM, TB, false, 0>(base + 0, s, A, w, wd);
+            if (base + 1 < s.nin) row_phase<FORM, TB, false, 1>(base + 1, s, A, w, wd);
+            if (base + 2 < s.nin) row_phase<FORM, TB, false, 2>(base + 2, s, A, w, wd);
+            if (base + 3 < s.nin) row_phase<FORM, TB, false, 3>(base + 3, s, A, w, wd);
+            if (base + 4 < s.nin) row_phase<FORM, TB, false, 4>(base + 4, s, A, w, wd);
+            if (base + 5 < s.nin) row_phase<FORM, TB, false, 5>(base + 5, s, A, w, wd);
+            if (base + 6 < s.nin) row_phase<FORM, TB, false, 6>(base + 6, s, A, w, wd);
         }
     }
 }
@@ -232,18 +205,16 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (task >= g.ntasks) return;  // warps never synchronise with each other
 
     constexpr int kStripOut = kWarpCols - 8 * (TB - 1);  // columns a strip writes
-    // Edge tasks (first / last strip of every chunk, first / last chunk) run the slower patched loop.  They are
-    // scheduled first, and the edge strips -- which patch every row -- are cut into half-length tasks, so that they
-    // never form the tail of the launch.  Task order: [0, 4 nchunks) edge-strip halves, then the inner strips chunk
-    // by chunk with the first and last chunk in front.
+    // Edge strips (first / last: every row is patched) are cut into short tasks of g.edge_rows rows, whose halo
+    // columns fit the shared-memory staging area, and scheduled first; then the inner strips chunk by chunk with
+    // the first and last chunk (whose first / last rows are patched) in front.
     int strip, r0, R;
     if (g.nstrips >= 3) {
-        const int nedge = 4 * g.nchunks;
+        const int nedge = 2 * g.nedge;
         if (task < nedge) {
             strip = (task & 1) ? g.nstrips - 1 : 0;
-            const int e = task >> 1, chunk = e >> 1, half = (g.rows_per_chunk + 1) / 2;
-            r0 = g.row_lo + chunk * g.rows_per_chunk + (e & 1) * half;
-            R = min((e & 1) ? g.rows_per_chunk - half : half, g.row_hi - r0);
+            r0 = g.row_lo + (task >> 1) * g.edge_rows;
+            R = min(g.edge_rows, g.row_hi - r0);
         } else {
             const int t = task - nedge, inner = g.nstrips - 2;
             strip = 1 + t % inner;
@@ -252,7 +223,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             r0 = g.row_lo + chunk * g.rows_per_chunk;
             R = min(g.rows_per_chunk, g.row_hi - r0);
         }
-    } else {
+    } else {  // narrow grid: every strip is an edge strip (the host keeps rows_per_chunk <= kEdgeRows2Tb)
         strip = task % g.nstrips;
         r0 = g.row_lo + (task / g.nstrips) * g.rows_per_chunk;
         R = min(g.rows_per_chunk, g.row_hi - r0);
@@ -285,6 +256,21 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.pitch = g.pitch;
     s.orow = g.out + (long long)(r0 + 4) * g.pitch + 4 + s.c0;
     s.hsrc = g.halo_src + 4 * g.pitch + 4 + s.c0;
+    double *hal = reinterpret_cast<double *>(smem_raw + kSmem12) + warp * (kHalRows2Tb * 8);
+    s.hal = hal;
+    if (s.col_edge) {
+        // stage the caller's halo columns (4 left of column 0, 4 right of column n-1) of the task's rows
+        for (int idx = lane; idx < s.nin; idx += 32) {
+            const int rho = s.rho0 + idx;
+            const bool row_ok = rho >= -4 && rho < g.m + 4;
+            const double *rowp = g.halo_src + (long long)(rho + 4) * g.pitch;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                hal[8 * idx + q] = row_ok ? rowp[q] : 0.0;
+                hal[8 * idx + 4 + q] = row_ok ? rowp[g.n + 4 + q] : 0.0;
+            }
+        }
+    }
 
     if (lane == 0) {
 #pragma unroll
@@ -307,13 +293,13 @@ cudaError_t launch_form(const CUtensorMap &tmap, const Geom2DTB &g, const Weight
                         cudaStream_t st) {
     if (g.ntasks <= 0) return cudaSuccess;
     const int ctas = (g.ntasks + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_stencil2d_tb<FORM, TB><<<ctas, 32 * kWarpsPerCta, kSmem12, st>>>(tmap, g, w, wd);
+    k_stencil2d_tb<FORM, TB><<<ctas, 32 * kWarpsPerCta, kSmem2Tb, st>>>(tmap, g, w, wd);
     return cudaGetLastError();
 }
 
 template <int FORM, int TB>
 cudaError_t opt_in() {
-    return cudaFuncSetAttribute(k_stencil2d_tb<FORM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem12);
+    return cudaFuncSetAttribute(k_stencil2d_tb<FORM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2Tb);
 }
 
 }  // namespace
