@@ -138,6 +138,7 @@ struct Geom2DTB {
     int par0;                // parity of the launch count before level 0 (== parity of the source buffer)
     int virt_top, virt_bot;  // rows beyond that end are the global halo ring (virtual halo), not neighbour-slab data
     int vec4;
+    long long mirror;        // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
 struct Geom3D {

@@ -97,7 +97,7 @@ struct lora_plan {
 constexpr int kTb2 = 3;  // the 2-D temporal block (odd, so that time parity == buffer parity at every sweep)
 static bool tb2_form(int form) { return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID; }
 static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
-                         int tb, int launches_before, int virt_lo, int virt_hi, void *stream);
+                         int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base, void *stream);
 
 static std::once_flag g_init_once;
 static cudaError_t g_init_err = cudaSuccess;
@@ -361,9 +361,9 @@ extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
 
 // 2-D fused launch of kTb2 time steps over interior rows [lo, hi): see stencil2d_tb.cu
 static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
-                         int tb, int launches_before, int virt_lo, int virt_hi, void *stream) {
+                         int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base, void *stream) {
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
-    if (tb == 1) return lora_plan_step(p, src, dst, lo, hi, stream);
+    if (tb == 1) return plan_step_impl(p, src, dst, lo, hi, mirror_base, stream);
     if (tb != kTb2 || !tb2_form(p->form))
         return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid)", kTb2);
     if (!halo_src) return fail(LORA_ERR_ARG, "fused 2-D launches need halo_src (the buffer holding the caller's halo)");
@@ -423,6 +423,7 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
     g.virt_top = virt_lo ? 1 : 0;
     g.virt_bot = virt_hi ? 1 : 0;
     g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+    g.mirror = mirror_delta(dst, mirror_base);
     cudaError_t e = launch_2d_tb(p->form, tb, *tm, g, p->w2, p->wd, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     p->launches++;
@@ -451,8 +452,8 @@ static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const
                            long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base,
                            void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
-    if (p->dim == 2 && mirror_base) return fail(LORA_ERR_UNSUPPORTED, "fused 2-D launches have no mirror store");
-    if (p->dim == 2) return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream);
+    if (p->dim == 2)
+        return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, mirror_base, stream);
     if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D and 2-D shapes");
     if (tb < 1 || tb > kMaxTb1) return fail(LORA_ERR_ARG, "temporal block must be 1..%d", kMaxTb1);
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
@@ -471,7 +472,12 @@ static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const
     // output row r (level tb) covers padded cells [512 r - 4 tb, 512 r - 4 tb + 512)
     g.rho0 = (g.xlo + 4 * tb) / kTbRowCells;
     g.nrows = (g.xhi - 1 + 4 * tb) / kTbRowCells - g.rho0 + 1;
-    g.rows_per_task = (int)pick_len(g.nrows, 1, (long long)p->sm_count * kTbCtasPerSm * kWarpsPerCta, 128, 8);
+    long long max_rows = 128;  // rows per task: whole waves of the longest tasks below this (1 warm-up row each)
+    if (const char *e = getenv("LORA_TB1_MAX_ROWS")) {  // tuning knob
+        const long long v = atoll(e);
+        if (v >= 8 && v <= 4096) max_rows = v;
+    }
+    g.rows_per_task = (int)pick_len(g.nrows, 1, (long long)p->sm_count * kTbCtasPerSm * kWarpsPerCta, max_rows, 8);
     g.ntasks = (g.nrows + g.rows_per_task - 1) / g.rows_per_task;
     g.tb = tb;
     g.par0 = launches_before & 1;
@@ -545,7 +551,7 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
         int k = 0;
         for (int left = times; left > 0; k++) {
             const int tb = left >= kTb2 ? kTb2 : 1;
-            int rc = step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tb, times - left, 1, 1, stream);
+            int rc = step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tb, times - left, 1, 1, nullptr, stream);
             if (rc) return rc;
             left -= tb;
         }

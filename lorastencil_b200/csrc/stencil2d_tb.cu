@@ -39,7 +39,7 @@ struct SweepTB {
     double *orow;           // output row pointer (this lane's first column), advances by pitch once rows retire
     const double *hsrc;     // caller's halo: padded buffer 0, pointing at (row 0, this lane's first column)
     const double *hal;      // shared memory: caller's halo columns of the task's rows, [nin][4 left + 4 right]
-    long long pitch;
+    long long pitch, mirror;
     int nin, nst, boxcol, row0_padded, lane;
     int rho0;               // interior row of input row 0 of the chunk (= r0 - 3 TB)
     int c0;                 // interior column of this lane's first cell
@@ -153,6 +153,11 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
                 for (int q = 0; q < 4; q++)
                     if (q < left) s.orow[q] = v[q];
             }
+            if (s.mirror != 0) {  // the same row into the neighbour slab's ghost rows (peer memory)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q < left) s.orow[s.mirror + q] = v[q];
+            }
         }
         s.orow += s.pitch;
     }
@@ -254,6 +259,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.par0 = g.par0 & 1;
     s.vec4 = g.vec4 != 0;
     s.pitch = g.pitch;
+    s.mirror = g.mirror;
     s.orow = g.out + (long long)(r0 + 4) * g.pitch + 4 + s.c0;
     s.hsrc = g.halo_src + 4 * g.pitch + 4 + s.c0;
     double *hal = reinterpret_cast<double *>(smem_raw + kSmem12) + warp * (kHalRows2Tb * 8);

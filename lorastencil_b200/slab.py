@@ -54,6 +54,15 @@ def temporal_schedule(times: int, max_tb: int):
     return tbs
 
 
+def temporal_schedule_2d(times: int, max_tb: int):
+    """2-D fuses exactly 3 launches or none: sweeps of 3, then the remainder one by one.  Every sweep advances an odd
+    number of steps, so sweep k reads buf[k % 2] at a time of parity k % 2 (the source buffer's own halo ring is the
+    right one for level 0) and the result lands in buf[times % 2] (S3)."""
+    if max_tb < 3:
+        return [1] * times
+    return [3] * (times // 3) + [1] * (times % 3)
+
+
 class SlabGeometry:
     """Contiguous balanced split of the outermost interior axis (multiples of `align` except the tail).
     `ghost` = cells kept beyond the slab on a side that faces a neighbour (>= halo)."""
@@ -199,16 +208,35 @@ class SlabRunner:
         self.cuda = self.device.type == "cuda"
         injected = step_fn is not None
         if temporal_block is None:
-            temporal_block = int(os.environ.get("LORA_TB", str(DEFAULT_TB_1D))) if (dim == 1 and (not injected or fused_fn)) else 1
-        self.max_tb = max(1, min(MAX_TB_1D, temporal_block)) if dim == 1 else 1
+            if dim == 1 and (not injected or fused_fn):
+                temporal_block = int(os.environ.get("LORA_TB", str(DEFAULT_TB_1D)))
+            elif dim == 2 and not injected:
+                from .plan import Plan
+                temporal_block = Plan(shape, (16, 16), params=params, mode=mode).temporal_block  # 3 for star forms
+            else:
+                temporal_block = 1
+        if dim == 1:
+            self.max_tb = max(1, min(MAX_TB_1D, temporal_block))
+        elif dim == 2:
+            self.max_tb = 3 if temporal_block >= 3 else 1  # 2-D fuses exactly 3 launches or none
+        else:
+            self.max_tb = 1
         if injected and fused_fn is None:
             self.max_tb = 1
-        ghost = 4 * self.max_tb if (dim == 1 and self.max_tb > 1) else None
+        # ghost zone towards a neighbour: radius x deepest temporal block (1-D: 4 x tb cells, 2-D: 3 x 3 rows), never
+        # less than the reference's storage halo
+        ghost = None
+        if dim == 1 and self.max_tb > 1:
+            ghost = 4 * self.max_tb
+        elif dim == 2 and self.max_tb > 1:
+            ghost = 3 * self.max_tb
         self.ghost, self.align = ghost, (16 if dim == 1 else 1)
         self.geo = SlabGeometry(global_dims, self.world, self.rank, align=self.align, ghost=ghost)
         if not injected:
             from .plan import Plan
             self.plan = Plan(shape, self.geo.local_dims, params=params, mode=mode)
+            if dim == 2:
+                self.plan.temporal_block = self.max_tb
             step_fn, fused_fn = self.plan.step, self.plan.step_fused
         else:
             self.plan = None
@@ -383,7 +411,8 @@ class SlabRunner:
             return res
         if self.max_tb > 1:
             assert self.launch % 2 == self.time % 2, "fused runs must start from a parity-consistent state"
-            for tb in temporal_schedule(times, self.max_tb):
+            sched = temporal_schedule(times, self.max_tb) if self.geo.dim == 1 else temporal_schedule_2d(times, self.max_tb)
+            for tb in sched:
                 self._sweep(tb)
         else:
             for _ in range(times):

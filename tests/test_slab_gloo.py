@@ -60,6 +60,33 @@ def _oracle_fused_fn(eff):
     return fused
 
 
+def _oracle_fused_fn_2d(eff):
+    """CPU stand-in for the 2-D lora_plan_step_fused: tb oracle steps; the halo ring is virtual (caller's at even
+    times, zero at odd) on the left / right always and on the top / bottom where the slab ends the global grid; rows
+    towards a neighbour are ordinary data (valid only inside the dependency cone, like in the kernel)."""
+    def fused(src, dst, halo_src, lo, hi, tb, t0, virt_lo, virt_hi, stream=None):
+        cur = src.numpy().copy()
+        H = halo_src.numpy()
+        for s in range(tb):
+            use_h = (t0 + s) % 2 == 0
+            if s > 0:  # level 0 reads the source buffer's own ring
+                cur[:, :4] = H[:, :4] if use_h else 0.0
+                cur[:, -4:] = H[:, -4:] if use_h else 0.0
+                if virt_lo:
+                    cur[:4] = H[:4] if use_h else 0.0
+                if virt_hi:
+                    cur[-4:] = H[-4:] if use_h else 0.0
+            # like the kernel, intermediate levels are computed on EVERY stored row (rows of the ghost zone that sit
+            # in the storage halo included), with zeros beyond the array
+            ext = np.zeros((cur.shape[0] + 8, cur.shape[1]))
+            ext[4:-4] = cur
+            nxt = cur.copy()
+            nxt[:, 4:-4] = oracle.step(2, ext, eff)[4:-4, 4:-4]
+            cur = nxt
+        dst.numpy()[4 + lo:4 + hi, 4:-4] = cur[4 + lo:4 + hi, 4:-4]
+    return fused
+
+
 def _worker(rank, world, port, shape, dims, times, ret, fused=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -75,9 +102,13 @@ def _worker(rank, world, port, shape, dims, times, ret, fused=False):
             dst.numpy()[sl] = full[sl]
 
         a = oracle.fill_rand(shape, dims)  # every rank generates the same global input
-        runner = SlabRunner(shape, dims, step_fn=step_fn, fused_fn=_oracle_fused_fn(eff) if fused else None,
-                            temporal_block=4 if fused else None)
-        assert runner.max_tb == (4 if fused else 1)
+        if d == 2 and fused:
+            runner = SlabRunner(shape, dims, step_fn=step_fn, fused_fn=_oracle_fused_fn_2d(eff), temporal_block=3)
+            assert runner.max_tb == 3 and (runner.geo.wl == 9 or runner.geo.prev is None)
+        else:
+            runner = SlabRunner(shape, dims, step_fn=step_fn, fused_fn=_oracle_fused_fn(eff) if fused else None,
+                                temporal_block=4 if fused else None)
+            assert runner.max_tb == (4 if fused else 1)
         runner.load_global(a)
         runner.run(times)
         got = runner.gather_global(a.shape)
@@ -103,7 +134,8 @@ def test_temporal_schedule_lands_in_the_reference_buffer():
 @pytest.mark.parametrize("shape,dims,world,times,fused", [
     ("1d2r", (4096,), 2, 3, False), ("box2d3r", (48, 64), 2, 4, False), ("star2d1r", (40, 36), 3, 3, False),
     ("box3d1r", (12, 8, 64), 2, 3, False), ("star3d1r", (9, 5, 30), 3, 2, False), ("box2d1r", (32, 64), 2, 1, False),
-    ("1d2r", (4096,), 2, 7, True), ("1d1r", (1000,), 3, 10, True)])
+    ("1d2r", (4096,), 2, 7, True), ("1d1r", (1000,), 3, 10, True), ("star2d3r", (60, 40), 2, 7, True),
+    ("star2d1r", (66, 36), 3, 5, True)])
 def test_slab_run_equals_single_domain(shape, dims, world, times, fused):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
