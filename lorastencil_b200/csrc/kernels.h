@@ -9,9 +9,17 @@ namespace lora {
 constexpr int kWarpCols = 128;     // one warp owns 32 lanes x 4 consecutive columns
 constexpr int kWarpsPerCta = 4;     // 1-D / 2-D: warps are independent workers, the CTA is only a container
 constexpr int kBoxCols = 136;      // 128 + 4 halo columns each side (stencil radius <= 4, 32-byte aligned)
-constexpr int kRowsPerStage = 4;   // rows of one TMA box
-constexpr int kStages = 3;         // per-warp ring depth
-constexpr int kStageElems = kRowsPerStage * kBoxCols;            // 544 doubles = 4352 B (34 x 128 B)
+// per-warp TMA ring of the 1-D / 2-D kernels: 2 stages x 8 rows measured best (profiles/r1_ring_variants.log:
+// against 3 x 4, unfused diamond 334 -> 367, unfused 1-D 369 -> 388, pyramid 335 -> 343 GStencil/s, fused cross equal)
+#ifndef LORA_ROWS_PER_STAGE
+#define LORA_ROWS_PER_STAGE 8
+#endif
+#ifndef LORA_STAGES
+#define LORA_STAGES 2
+#endif
+constexpr int kRowsPerStage = LORA_ROWS_PER_STAGE;   // rows of one TMA box
+constexpr int kStages = LORA_STAGES;                 // per-warp ring depth
+constexpr int kStageElems = kRowsPerStage * kBoxCols;            // 1088 doubles = 8704 B (68 x 128 B)
 constexpr int kSmem12 = kWarpsPerCta * kStages * kStageElems * 8 + kWarpsPerCta * kStages * 8;
 // ---- temporally blocked 1-D kernel (stencil1d_tb.cu) ----
 // Rows of 512 cells (lane = 16 cells = 128 B).  Per-warp shared memory: kTbStages x 4 KB TMA load ring +

@@ -4,7 +4,7 @@
 // src/1d/gpu_2r.cu:22-88), which fold 1024 outputs into an 8x128 matrix so the convolution becomes
 // X(8x16) . P(16x8) on the FP64 tensor cores (16 MACs per output, 9 useful).  Here the line is cut
 // into "rows" of 128 outputs; every warp is an independent worker that sweeps a run of consecutive
-// rows.  Its private TMA ring (cp.async.bulk, no tensor map needed in 1-D) stages 4 rows + 8 halo
+// rows.  Its private TMA ring (cp.async.bulk, no tensor map needed in 1-D) stages 8 rows + 8 halo
 // doubles per transaction; lane l reads its 12-double window with six 128-bit LDS, evaluates the
 // 9 taps for its 4 outputs with FP64 FMAs (weights from the constant bank / uniform registers) and
 // writes them with one 256-bit store.  9 MACs per output, no CTA-wide synchronisation.
@@ -16,7 +16,7 @@ namespace lora {
 namespace {
 
 constexpr int kRowElems = kWarpCols;                       // 128 outputs per row
-constexpr int kStageRows1 = kRowsPerStage;                 // 4 rows per bulk copy
+constexpr int kStageRows1 = kRowsPerStage;                 // rows per bulk copy
 constexpr int kStageLoad1 = kStageRows1 * kRowElems + 8;   // doubles fetched per stage (520)
 
 __global__ void __launch_bounds__(32 * kWarpsPerCta, 4)

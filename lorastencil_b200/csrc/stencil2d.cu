@@ -8,7 +8,7 @@
 //   * every warp is an independent worker: it owns a strip of 128 columns and sweeps a chunk of rows
 //     top to bottom.  Lane l owns 4 consecutive columns.
 //   * input rows reach shared memory through the warp's private TMA ring (cp.async.bulk.tensor.2d,
-//     boxes of 136 columns x 4 rows, 3 stages, one mbarrier per stage); no CTA-wide barrier exists.
+//     boxes of 136 columns x 8 rows, 2 stages, one mbarrier per stage); no CTA-wide barrier exists.
 //   * per input row a lane reads its 12-double window with six 128-bit LDS, forms the horizontal
 //     profile sums h_t (FP64 FMA, weights straight from the constant bank) and PUSHES u_t[dr] * h_t
 //     into seven per-column register accumulators (one per pending output row).  The oldest
