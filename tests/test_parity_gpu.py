@@ -336,3 +336,42 @@ def test_temporal_blocking_2d_equals_unfused_launches(shape, dims):
                 assert np.array_equal(results[1], ref), (shape, dims, times)
             else:
                 assert max_rel_err(results[1], ref) <= RTOL, (shape, dims, times)
+
+
+@pytest.mark.parametrize("shape,dims,times", [("1d1r", (5000,), 31), ("1d2r", (100003,), 16), ("star2d1r", (70, 250), 7),
+                                              ("box2d1r", (64, 130), 4), ("star2d3r", (300, 370), 10), ("box3d1r", (9, 34, 130), 4),
+                                              ("star3d1r", (12, 8, 64), 5), ("star2d3r", (9, 8), 4)])
+def test_no_write_outside_the_destination_interior(shape, dims, times):
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are hunted with canaries: both ping-pong
+    buffers are carved out of one allocation with guard zones around them, every guard double and every halo cell of
+    the buffers must come back untouched (S2: a launch writes the interior of its destination only), for the plain
+    and the fused (TMA-store, overlapped-strip, edge-task) paths."""
+    import torch
+    plan = ls.Plan(shape, dims)
+    n = int(np.prod(plan.padded_shape))
+    guard = 4096
+    pool = torch.full((3 * guard + 2 * n + 64,), -123.25, dtype=torch.float64, device="cuda")
+    off0 = guard
+    off1 = (2 * guard + n + 3) // 4 * 4  # keep 32-byte alignment
+    b0 = pool[off0:off0 + n].view(plan.padded_shape)
+    b1 = pool[off1:off1 + n].view(plan.padded_shape)
+    a = np.random.default_rng(11).uniform(-1, 1, plan.padded_shape)
+    b0.copy_(torch.from_numpy(a))
+    b1.zero_()
+    res = plan.run(b0, b1, times)
+    torch.cuda.synchronize()
+    ref = oracle.run(shape, a, oracle.effective_params(shape), times)
+    got = res.cpu().numpy()
+    if oracle.dim_of(shape) == 1:
+        got, ref = got[:-1], ref[:-1]
+    assert max_rel_err(got, ref) <= RTOL
+    host = pool.cpu().numpy()
+    assert np.all(host[:off0] == -123.25) and np.all(host[off0 + n:off1] == -123.25) and np.all(host[off1 + n:] == -123.25)
+    # the halo of buffer 0 still holds the caller's halo, the halo of buffer 1 is still zero
+    inner = interior(shape, dims)
+    h0, h1 = b0.cpu().numpy().copy(), b1.cpu().numpy().copy()
+    a_h = a.copy()
+    h0[inner] = 0.0
+    a_h[inner] = 0.0
+    h1[inner] = 0.0
+    assert np.array_equal(h0, a_h) and not h1.any()
