@@ -1,26 +1,31 @@
-"""Multi-GPU slab decomposition: one process per GPU, nearest-neighbour halo exchange per launch
-(2-D / 3-D) or per temporal block (1-D).
+"""Multi-GPU slab decomposition: one process per GPU, nearest-neighbour halo exchange once per sweep (= once per
+launch, or once per temporal block where launches are fused: 1-D, 2-D star forms).
 
 New functionality (the reference is single-GPU: no cudaSetDevice / NCCL / MPI anywhere in src/).  The
 grid is cut along its OUTERMOST axis into `world` contiguous slabs; every rank keeps the reference's
 two ping-pong buffers for its slab, padded with the reference's storage halo (4 elements / 4 rows /
 1 plane -- S1 of SURVEY.md section 8a), which is >= the stencil radius (4 / 3 / 1).
 
-Per launch i (src = buf[i%2], dst = buf[(i+1)%2]) a rank
-  1. computes its two edge bands (the first and last `halo` interior rows of dst) on the comm stream,
-  2. posts send/recv of those bands with its neighbours (torch.distributed P2P = ncclSend/ncclRecv over
-     NVLink) on the comm stream -- the bands land directly in the neighbours' halo rows of dst,
-  3. computes the rest of the interior on the main stream, overlapping the exchange,
+Per sweep i (src = buf[i%2], dst = buf[(i+1)%2]) a rank
+  1. computes its two edge bands (the first and last ghost-width interior rows of dst) on the comm stream,
+  2. gets those bands into the neighbours' ghost rows of dst:
+       "p2p"  (default on GPUs): the edge-band kernel itself stores every row a second time, into the neighbour's
+              buffer mapped over NVLink (CUDA IPC; `mirror` argument of lora_plan_step_mirror), then bumps a 64-bit
+              flag in the neighbour's memory in stream order; the neighbour's next edge-band launch waits for it
+              (PeerHalo, csrc/peer.cu).  No communication library on the data path;
+       "nccl" (LORA_HALO=nccl, and the CPU tests with gloo): send/recv of the bands (torch.distributed P2P),
+  3. computes the rest of the interior on the main stream -- it reads the rank's own rows only and never waits
+     for a neighbour,
   4. joins the two streams.
 Halo rows on the outer faces of the global grid are never written, so they keep the reference's
 semantics (S2): caller's halo in buf[0], zeros in buf[1].  Results are bit-identical to a single-GPU
 run because every cell sees the same operands in the same order.
 
-1-D with temporal blocking (tb launches fused per sweep, lorastencil_b200/csrc/stencil1d_tb.cu): sides
-that face a neighbour carry a GHOST zone of 4*tb_max cells instead of the 4-cell halo.  A fused launch
-reads up to 4*tb cells beyond the slab, so one exchange of 4*tb_max cells per temporal block replaces tb
-exchanges of 4 cells; sides that face the end of the global line keep the 4-cell halo, which the kernel
-treats as virtual (caller's halo at even times, zero at odd times).
+Temporal blocking: sides that face a neighbour carry a GHOST zone of radius x tb_max (1-D: 4 x 15 = 60 cells,
+lorastencil_b200/csrc/stencil1d_tb.cu; 2-D cross / diamond forms: 3 x 3 = 9 rows, stencil2d_tb.cu) instead of the
+storage halo.  A fused launch reads up to radius x tb cells beyond the slab, so one exchange per temporal block
+replaces tb exchanges; sides that face the end of the global grid keep the storage halo, which the kernels treat as
+virtual (caller's halo at even times, zero at odd times).
 
 The compute step is pluggable (`step_fn(src, dst, lo, hi)`, `fused_fn(...)`): the product uses `Plan.step`
 / `Plan.step_fused` (CUDA); the CPU tests (gloo, world_size 2-3) inject the oracle to exercise the

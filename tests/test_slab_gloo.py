@@ -25,7 +25,7 @@ def test_geometry_covers_the_axis_without_overlap():
         assert gs[0].prev is None and gs[-1].next is None and gs[0].next == 1
         for g in gs:
             assert g.local_padded[0] == g.hi - g.lo + 2 * g.halo
-    # ghost zones (1-D temporal blocking): 16 cells towards neighbours, the 4-cell halo towards the ends
+    # ghost zones (1-D temporal blocking, tb = 4 here): 16 cells towards neighbours, the 4-cell halo towards the ends
     gs = [SlabGeometry((4096,), 3, r, 16, ghost=16) for r in range(3)]
     assert [(g.wl, g.wr) for g in gs] == [(4, 16), (16, 16), (16, 4)]
     assert [g.off for g in gs] == [0, 12, 12]
