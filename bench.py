@@ -270,11 +270,12 @@ def measure_shape(torch, ls, shape, dims, launches, hbm_gbs, reps=3):
     gst = cells / per_launch_s / 1e9
     ach = cells * 16 / per_launch_s / 1e9
     desc = plan.describe
+    tb = plan.temporal_block
     del plan, b0, b1
     torch.cuda.empty_cache()
     return {"shape": shape, "dims": list(dims), "launches": launches, "gstencils": gst,
             "gstencils_artifact_units": gst * ARTIFACT_K[shape], "us_per_launch": per_launch_s * 1e6,
-            "hbm_gbs_algorithmic": ach, "roofline_frac": ach / hbm_gbs, "form": desc}
+            "hbm_gbs_algorithmic": ach, "roofline_frac": ach / hbm_gbs, "form": desc, "temporal_block": tb}
 
 
 def main():
@@ -465,6 +466,23 @@ def main():
                              "frac can exceed 1 -- `traffic` is the measured DRAM bytes per launch",
                      "frac_of_nominal_8TBs": achieved / 8000.0},
     }
+    # the honest ceilings of a temporally blocked sweep: the DRAM bytes it really moves, and the FP64 pipe
+    traffic = line["roofline"]["traffic"]
+    if traffic:
+        dram_gbs = traffic / (us_per_launch * 1e-6) / 1e9
+        line["roofline"]["dram_achieved_gbs"] = dram_gbs
+        line["roofline"]["dram_frac"] = dram_gbs / hbm_gbs
+    flop_per_cell = {1: 18.0}.get(len(dims))  # 9 taps = 9 FP64 FMA per cell per time step
+    try:
+        fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_pipes.json")))["dfma_tflops"])
+    except (OSError, ValueError, KeyError):
+        fp64_peak = None
+    if flop_per_cell and fp64_peak:
+        tf = value / world * flop_per_cell / 1e3
+        line["roofline"]["fp64"] = {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                                    "peak_source": "measured DFMA stream on this pool (profiles/r1_fp64_pipes.json)",
+                                    "note": "9 FMA per cell per time step is the floor for general 9-tap weights; with "
+                                            "15 launches fused per sweep this pipe, not HBM, bounds the kernel"}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
