@@ -393,8 +393,12 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
             const long long v = atoll(e);
             if (v >= 8 && v <= kEdgeRows2Tb) edge_cap = v;
         }
-        long long best_chunks = 0;
-        for (long long k = 1; k <= 64 && !best_chunks; k++) {
+        long long best_chunks = 0, k0 = 1;
+        if (const char *e = getenv("LORA_TB2_MIN_WAVES")) {  // tuning knob
+            const long long v = atoll(e);
+            if (v >= 1 && v <= 16) k0 = v;
+        }
+        for (long long k = k0; k <= 64 && !best_chunks; k++) {
             for (long long nc = (rows + 95) / 96; nc >= 1; nc--) {  // most chunks first
                 const long long R = (rows + nc - 1) / nc;
                 if (R > 768) break;
