@@ -189,7 +189,9 @@ enum {
     LORA_FORM_DIRECT49 = 4,   /* 2-D: all 49 taps */
     LORA_FORM_SEP3 = 5,       /* 3-D box: one rank-1 term a (x) b (x) c */
     LORA_FORM_STAR7 = 6,      /* 3-D star: 7 taps */
-    LORA_FORM_DIRECT27 = 7    /* 3-D: all 27 taps */
+    LORA_FORM_DIRECT27 = 7,   /* 3-D: all 27 taps */
+    LORA_FORM_PYRAMID_PRUNED = 8 /* PYRAMID whose middle term is zero at offsets +-1 and whose centre remainder is
+                                    zero (true for the reference's box table): those taps are not computed at all */
 };
 
 typedef struct {

@@ -95,7 +95,9 @@ struct lora_plan {
 };
 
 constexpr int kTb2 = 3;  // the 2-D temporal block (odd, so that time parity == buffer parity at every sweep)
-static bool tb2_form(int form) { return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID; }
+static bool tb2_form(int form) {
+    return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID || form == LORA_FORM_PYRAMID_PRUNED;
+}
 static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
                          int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base, void *stream);
 
@@ -165,7 +167,8 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     cudaGetDevice(&p->device);
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && sms > 0) p->sm_count = sms;
-    const int warps_per_sm = (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
+    const int warps_per_sm =
+        (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_PYRAMID_PRUNED || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
     if (dim == 2 && tb2_form(p->form)) {
         // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 560 vs 335 GStencil/s unfused, diamond 387 vs

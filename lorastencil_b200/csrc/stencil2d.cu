@@ -89,7 +89,8 @@ __device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4
 }
 
 template <int FORM>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, (FORM == LORA_FORM_PYRAMID || FORM == LORA_FORM_DIRECT49) ? 3 : 4)
+__global__ void __launch_bounds__(32 * kWarpsPerCta,
+                                  (FORM == LORA_FORM_PYRAMID || FORM == LORA_FORM_PYRAMID_PRUNED || FORM == LORA_FORM_DIRECT49) ? 3 : 4)
 k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2D g,
             const __grid_constant__ Weights2D w, const __grid_constant__ WeightsDirect49 wd) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -166,6 +167,7 @@ cudaError_t opt_in() {
 cudaError_t kernels_init_2d() {
     cudaError_t e;
     if ((e = opt_in<LORA_FORM_PYRAMID>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_PYRAMID_PRUNED>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_CROSS>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_DIAMOND>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_DIRECT49>()) != cudaSuccess) return e;
@@ -176,6 +178,7 @@ cudaError_t launch_2d(int form, const CUtensorMap &tmap, const Geom2D &g, const 
                       const WeightsDirect49 &wd, cudaStream_t s) {
     switch (form) {
         case LORA_FORM_PYRAMID: return launch_form<LORA_FORM_PYRAMID>(tmap, g, w, wd, s);
+        case LORA_FORM_PYRAMID_PRUNED: return launch_form<LORA_FORM_PYRAMID_PRUNED>(tmap, g, w, wd, s);
         case LORA_FORM_CROSS: return launch_form<LORA_FORM_CROSS>(tmap, g, w, wd, s);
         case LORA_FORM_DIAMOND: return launch_form<LORA_FORM_DIAMOND>(tmap, g, w, wd, s);
         case LORA_FORM_DIRECT49: return launch_form<LORA_FORM_DIRECT49>(tmap, g, w, wd, s);

@@ -21,7 +21,29 @@ template <int FORM, int PH>
 __device__ __forceinline__ void push_row(const double (&x)[12], double (&A)[NACC][4], const Weights2D &w,
                                          const WeightsDirect49 &wd) {
 #define ACC(dr) A[((3 - (dr)) + PH) % NACC]
-    if constexpr (FORM == LORA_FORM_PYRAMID) {
+    if constexpr (FORM == LORA_FORM_PYRAMID_PRUNED) {
+        // PYRAMID without the taps the host found to be structurally zero: middle term at offsets -2, 0, +2 only,
+        // no centre remainder (decompose.cpp: prune_pyramid)
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int rad = 3 - t;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double h = w.horiz[t][3 - rad] * x[4 + q - rad];
+#pragma unroll
+                for (int dc = -rad + 1; dc <= rad; dc++)
+                    if (!(t == 1 && (dc == -1 || dc == 1))) h = fma(w.horiz[t][3 + dc], x[4 + q + dc], h);
+#pragma unroll
+                for (int dr = -rad; dr <= rad; dr++) {
+                    if (t == 1 && (dr == -1 || dr == 1)) continue;
+                    if (dr == -3)
+                        ACC(dr)[q] = w.vert[t][3 + dr] * h;  // birth of the output row 3 below (t == 0 only)
+                    else
+                        ACC(dr)[q] = fma(w.vert[t][3 + dr], h, ACC(dr)[q]);
+                }
+            }
+        }
+    } else if constexpr (FORM == LORA_FORM_PYRAMID) {
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             const int rad = 3 - t;

@@ -313,6 +313,7 @@ cudaError_t opt_in() {
 cudaError_t kernels_init_2d_tb() {
     cudaError_t e;
     if ((e = opt_in<LORA_FORM_PYRAMID, 3>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_PYRAMID_PRUNED, 3>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_CROSS, 3>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_DIAMOND, 3>()) != cudaSuccess) return e;
     return cudaSuccess;
@@ -325,6 +326,7 @@ cudaError_t launch_2d_tb(int form, int tb, const CUtensorMap &tmap, const Geom2D
     if (tb != 3) return cudaErrorInvalidValue;
     switch (form) {
         case LORA_FORM_PYRAMID: return launch_form<LORA_FORM_PYRAMID, 3>(tmap, g, w, wd, s);
+        case LORA_FORM_PYRAMID_PRUNED: return launch_form<LORA_FORM_PYRAMID_PRUNED, 3>(tmap, g, w, wd, s);
         case LORA_FORM_CROSS: return launch_form<LORA_FORM_CROSS, 3>(tmap, g, w, wd, s);
         case LORA_FORM_DIAMOND: return launch_form<LORA_FORM_DIAMOND, 3>(tmap, g, w, wd, s);
         default: return cudaErrorInvalidValue;

@@ -11,7 +11,8 @@ from . import _lib
 HALO = {1: (4,), 2: (4, 4), 3: (1, 2, 4)}  # S1: src/1d/main.cu:96, src/2d/main.cu:217-218, src/3d/main.cu:21-23
 MAX_TB_1D = 15     # deepest temporal block of the 1-D kernel (kMaxTb1 in csrc/kernels.h)
 DEFAULT_TB_1D = 15  # kDefaultTb1
-FORM_NAMES = {0: "taps9", 1: "cross", 2: "pyramid", 3: "diamond", 4: "direct49", 5: "sep3", 6: "star7", 7: "direct27"}
+FORM_NAMES = {0: "taps9", 1: "cross", 2: "pyramid", 3: "diamond", 4: "direct49", 5: "sep3", 6: "star7", 7: "direct27",
+              8: "pyramid_pruned"}
 
 
 def _dp(a: np.ndarray):

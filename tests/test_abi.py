@@ -59,10 +59,12 @@ def test_reference_tables_and_effective_weights():
 def test_pyramid_matches_reference_peel():
     d = ls.decompose_2d("box2d3r", ls.reference_table("box2d3r"), mode=ls.WEIGHTS_REFERENCE)
     u, v, centre = oracle.reference_peel_box2d(oracle.reference_params("box2d3r"))
-    assert d["form"] == "pyramid" and d["nterms"] == 3 and d["macs_per_cell"] == 30
+    # the reference's table peels into [1,2,3,4,3,2,1], [0,1,0,-1,0,1,0], [0,0,-1,-3,-1,0,0]: the middle term's zero
+    # taps are pruned (26 FP64 operations per cell instead of 30)
+    assert d["form"] == "pyramid_pruned" and d["nterms"] == 3 and d["macs_per_cell"] == 26
     assert np.array_equal(d["vert"], u) and np.array_equal(d["horiz"], v)
     g = ls.decompose_2d("box2d3r", ls.reference_table("box2d3r"), mode=ls.WEIGHTS_GENERAL)
-    assert g["form"] == "pyramid" and g["centre"] == 0.0 and g["recon_err"] == 0.0
+    assert g["form"] == "pyramid_pruned" and g["centre"] == 0.0 and g["recon_err"] == 0.0
 
 
 def test_reference_mode_restates_the_reference_peel_on_any_table():
