@@ -142,7 +142,8 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         decompose_1d(shape, mode, params, d);
         std::memcpy(p->w1.w, d.w, sizeof d.w);
         p->form = LORA_FORM_TAPS9;
-        p->desc = "1d 9 direct taps";
+        p->desc = (d.w[0] == 0.0 && d.w[8] == 0.0) ? "1d 9 direct taps, outer two are zero: 7 computed in fused sweeps"
+                                                   : "1d 9 direct taps";
     } else if (dim == 2) {
         Decomp2D d;
         decompose_2d(shape, mode, params, d);

@@ -52,7 +52,9 @@ __device__ __forceinline__ void fix_halo(double (&v)[kCpl], long long X, int lev
 
 // One row through all TB levels.  X = padded coordinate of this lane's first level-0 cell; on return cur[]
 // holds level TB of the cells X - 4 TB .. X - 4 TB + 15.
-template <bool FIX>
+// NT = taps actually computed: 9, or 7 when the host found w[0] == w[8] == 0 (the reference's 1d1r table
+// {0,1,2,3,4,3,2,1,0}): structural zeros cost nothing -- 7 instead of 9 FP64 operations per cell per level.
+template <bool FIX, int NT>
 __device__ __forceinline__ void sweep_row(const unsigned char *stage, double *mailbox, int par, int lane, long long X,
                                           const Geom1DTB &g, const Weights1D &w, double (&cur)[kCpl]) {
     {
@@ -102,9 +104,10 @@ __device__ __forceinline__ void sweep_row(const unsigned char *stage, double *ma
         // level s, cell q sits at (level s-1 position of win[0]) + 4 + q: taps win[q .. q+8]
 #pragma unroll
         for (int q = 0; q < kCpl; q++) {
-            double a = w.w[0] * win[q];
+            constexpr int k0 = (9 - NT) / 2;
+            double a = w.w[k0] * win[q + k0];
 #pragma unroll
-            for (int k = 1; k < 9; k++) a = fma(w.w[k], win[q + k], a);
+            for (int k = k0 + 1; k < 9 - k0; k++) a = fma(w.w[k], win[q + k], a);
             cur[q] = a;
         }
         X -= 4;
@@ -112,6 +115,7 @@ __device__ __forceinline__ void sweep_row(const unsigned char *stage, double *ma
     }
 }
 
+template <int NT>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, kTbCtasPerSm)
 k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__ CUtensorMap omap,
                const __grid_constant__ Geom1DTB g, const __grid_constant__ Weights1D w) {
@@ -160,9 +164,9 @@ k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__
                           (g.virt_right && X0 + kRow > g.n + 4);
         double cur[kCpl];
         if (edge)
-            sweep_row<true>(ring + slot * (kRow * 8), mailbox, i & 1, lane, X0 + kCpl * lane, g, w, cur);
+            sweep_row<true, NT>(ring + slot * (kRow * 8), mailbox, i & 1, lane, X0 + kCpl * lane, g, w, cur);
         else
-            sweep_row<false>(ring + slot * (kRow * 8), mailbox, i & 1, lane, X0 + kCpl * lane, g, w, cur);
+            sweep_row<false, NT>(ring + slot * (kRow * 8), mailbox, i & 1, lane, X0 + kCpl * lane, g, w, cur);
         __syncwarp();  // every lane has consumed the stage
         if (lane == 0 && i + kTbStages < niter) issue(i + kTbStages, slot);
 
@@ -202,7 +206,9 @@ k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__
 }  // namespace
 
 cudaError_t kernels_init_1d_tb() {
-    return cudaFuncSetAttribute(k_stencil1d_tb, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1Tb);
+    cudaError_t e = cudaFuncSetAttribute(k_stencil1d_tb<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1Tb);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_stencil1d_tb<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem1Tb);
 }
 
 cudaError_t launch_1d_tb(const CUtensorMap &imap, const CUtensorMap &omap, const Geom1DTB &g, const Weights1D &w,
@@ -210,7 +216,10 @@ cudaError_t launch_1d_tb(const CUtensorMap &imap, const CUtensorMap &omap, const
     if (g.ntasks <= 0) return cudaSuccess;
     if (g.tb < 1 || g.tb > kMaxTb1) return cudaErrorInvalidValue;
     const long long ctas = (g.ntasks + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_stencil1d_tb<<<(unsigned)ctas, 32 * kWarpsPerCta, kSmem1Tb, s>>>(imap, omap, g, w);
+    if (w.w[0] == 0.0 && w.w[8] == 0.0)  // outer taps are structural zeros: the 7-tap variant
+        k_stencil1d_tb<7><<<(unsigned)ctas, 32 * kWarpsPerCta, kSmem1Tb, s>>>(imap, omap, g, w);
+    else
+        k_stencil1d_tb<9><<<(unsigned)ctas, 32 * kWarpsPerCta, kSmem1Tb, s>>>(imap, omap, g, w);
     return cudaGetLastError();
 }
 
