@@ -53,12 +53,6 @@ struct SweepTB {
 };
 
 // Virtual halo for a retired row of level `level` (time par0 + level): cells outside the interior are not computed
-// values but (time even) ? caller's halo : 0.  Only tasks that can meet the ring run this (EDGE variant of the loop).
-//   * a whole row outside [0, m) (at most 3 per level at the top / bottom of the grid): loaded on the spot;
-//   * cells of an inside row whose column is outside [0, n) (first / last strip, every row): their caller's-halo
-//     values were PREFETCHED one iteration ago into hcol[] (levels alternate parity, so at most one level per
-//     sweep needs them), which keeps the L2 round trip off the row's dependency chain.
-// Virtual halo for a retired row of level `level` (time par0 + level): cells outside the interior are not computed
 // values but (time even) ? caller's halo : 0.  Only groups of rows that can meet the ring run this (EDGE phases).
 //   * a whole row outside [0, m) (at most 3 per level at the top / bottom of the grid): loaded on the spot;
 //   * cells of an inside row whose column is outside [0, n) (first / last strip, every row): the caller's-halo
