@@ -168,8 +168,15 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     cudaGetDevice(&p->device);
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && sms > 0) p->sm_count = sms;
-    const int warps_per_sm =
+    // task-planning granularity of the 1-D / 2-D kernels, in warp tasks per SM and wave.  12 warps are resident (3 CTAs:
+    // the per-warp TMA ring, and the registers of the pyramid / direct forms); planning the cheap forms for 16 --
+    // i.e. more, shorter tasks than resident warps -- measured 8 % faster (dynamic CTA dispatch evens out the tail)
+    int warps_per_sm =
         (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_PYRAMID_PRUNED || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
+    if (const char *e = getenv("LORA_SLOTS_PER_SM")) {  // tuning knob
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) warps_per_sm = v;
+    }
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
     if (dim == 2 && tb2_form(p->form)) {
         // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 560 vs 335 GStencil/s unfused, diamond 387 vs
@@ -311,7 +318,19 @@ static int plan_step_impl(lora_plan_t *p, const double *src, double *dst, long l
         g.row_lo = (int)lo;
         g.row_hi = (int)hi;
         g.nstrips = (g.n + kWarpCols - 1) / kWarpCols;
-        g.rows_per_chunk = (int)pick_len(hi - lo, g.nstrips, p->slots, 256, 32);
+        // Chunk length: about 8 tasks per resident warp, between 64 and 256 rows (6 warm-up rows per chunk).  Many
+        // short tasks beat whole waves of long ones here: CTAs are dispatched in task order, so the warps that are
+        // resident at any moment work on a few neighbouring row bands (DRAM page and L2 locality) and the tail of
+        // the launch is short.  Measured, box2d 10240^2: 337 (256 rows) / 367 (96) / 376 (64) / 357 (32) GStencil/s;
+        // 40960^2: 397 at 96..256 rows (profiles/r1_chunk_rows_2d.log).
+        long long want = (hi - lo) * g.nstrips / (8 * (long long)p->slots);
+        want = want < 64 ? 64 : (want > 256 ? 256 : want);
+        if (const char *e = getenv("LORA_MAX_ROWS_2D")) {  // tuning knob
+            const long long v = atoll(e);
+            if (v >= 8 && v <= 4096) want = v;
+        }
+        const long long nch = (hi - lo + want - 1) / want;
+        g.rows_per_chunk = (int)((hi - lo + nch - 1) / nch);
         const int chunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
         g.ntasks = chunks * g.nstrips;
         g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
