@@ -423,3 +423,28 @@ class SlabRunner:
             for _ in range(times):
                 self._sweep(1)
         return self.result()
+
+
+# ---- host-resident 1-D lines on N GPUs without any exchange -------------------------------------------------
+def host_segment(n_global: int, world: int, rank: int, times: int):
+    """Split a global 1-D line of n_global cells for `world` independent drop-in operator calls.
+
+    A cell after `times` launches depends on 4 x times cells either side only, so a rank that is handed its slab
+    PLUS a margin of that width can run the whole job on its own, no halo exchange at all: its operator call treats
+    the ends of its segment as ends of a line, and that error travels 4 cells per launch -- it never leaves the
+    margin.  Returns (lo, hi, gl, gr): the slab [lo, hi) and the margins kept left / right of it (0 at the ends of
+    the global line, where the segment's end IS the line's end)."""
+    units = -(-n_global // 16)
+    bounds = [min(n_global, 16 * (units * r // world)) for r in range(world + 1)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    margin = 4 * times + 8
+    return lo, hi, min(margin, lo), min(margin, n_global - hi)
+
+
+def run_host_segment(shape: str, seg_in, seg_out, params, times: int):
+    """One rank's share of a host-resident 1-D job: `seg_in` = padded segment (4 halo + margin + slab + margin + 4
+    halo doubles, cut out of the global padded line), `seg_out` likewise; the reference-facing operator runs on it
+    (chunked, copies overlapped with launches).  The slab part of seg_out is exact; the margins are not."""
+    from . import ops
+    n_seg = int(seg_in.numel() if hasattr(seg_in, "numel") else seg_in.size) - 8
+    return ops.BY_SHAPE[shape](seg_in, seg_out, params, times, n_seg)

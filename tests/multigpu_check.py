@@ -50,6 +50,30 @@ def main():
             ok = np.array_equal(got, ref)
             print(f"[{world} GPUs, halo {used}] {shape} {dims} x{times}: {'identical' if ok else 'MISMATCH'}", flush=True)
             bad += 0 if ok else 1
+    # host-resident 1-D job without any exchange: every rank runs the drop-in operator on its slab + a margin of the
+    # dependency-cone width, the slabs put together must equal the single-GPU operator call on the whole line
+    from lorastencil_b200 import ops
+    from lorastencil_b200.slab import host_segment, run_host_segment
+    ops.set_verbose(False)
+    for shape, n, times in (("1d2r", 1 << 20, 37), ("1d1r", 300000, 8)):
+        rng = np.random.default_rng(7)
+        a = rng.integers(0, 10, size=(n + 8,)).astype(np.float64)
+        p = ls.reference_table(shape)
+        lo, hi, gl, gr = host_segment(n, world, rank, times)
+        seg = np.ascontiguousarray(a[lo - gl:hi + gr + 8])
+        out = np.zeros_like(seg)
+        run_host_segment(shape, seg, out, p, times)
+        mine = torch.from_numpy(out[4 + gl:4 + gl + hi - lo].copy())
+        pieces = [None] * world
+        dist.all_gather_object(pieces, (lo, hi, mine.numpy()))
+        if rank == 0:
+            whole = np.zeros_like(a)
+            ops.BY_SHAPE[shape](a, whole, p, times, n)
+            got = np.concatenate([x[2] for x in sorted(pieces, key=lambda t: t[0])])
+            ok = np.array_equal(got, whole[4:4 + n])
+            print(f"[{world} GPUs, no exchange] {shape} ({n},) x{times} host segments with margins: {'identical' if ok else 'MISMATCH'}",
+                  flush=True)
+            bad += 0 if ok else 1
     flag = torch.tensor([bad], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
