@@ -14,7 +14,7 @@ run() {  # name N bench-args...
     echo "$name n=$n rc=$? $(python -c "import json,sys; d=json.load(open('${out}_${name}_n$n.json')); print(round(d['value'],1), 'GStencil/s', round(d['ms_per_step'],2), 'ms/step', d['config']['decomposition'][:40])" 2>&1 | tail -1)"
 }
 ngpu=$(nvidia-smi -L | wc -l)
-for n in 8 4 2 1; do
+for n in ${NS:-8 4 2 1}; do
     [ $n -le $ngpu ] || continue
     run box2d1r_40960 $n --shape box2d1r --dims 40960,40960 --times 100 --scaling strong
     run box3d1r_1024 $n --shape box3d1r --dims 1024,1024,1024 --times 100 --scaling strong
