@@ -178,6 +178,14 @@ const char *lora_plan_describe(const lora_plan_t *plan);
 /* last error message of layer 2/3 on this thread ("" if none) */
 const char *lora_last_error(void);
 
+/* ---- host-side planning, exposed for tests (no GPU needed) ----
+ * lora_debug_temporal_schedule: the temporal blocks lora_plan_run uses for `times` launches of a 1-D plan whose deepest
+ * block is max_tb (their count has the parity of `times`: S3); returns the number of blocks.
+ * lora_debug_tasks_2dtb: the warp tasks (strip, first row, rows) of one fused 2-D launch over rows [lo, hi) of an
+ * m x n grid on a GPU with sm_count SMs, in launch order; returns the number of tasks. */
+int lora_debug_temporal_schedule(int times, int max_tb, int *blocks_out, int cap);
+int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int *strip_row_rows_out, int cap);
+
 /* ------------------------------------------------------------------------------------------
  * Layer 3: host low-rank decomposition (inspection / tests)
  * ------------------------------------------------------------------------------------------ */

@@ -149,6 +149,36 @@ struct Geom2DTB {
     long long mirror;        // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
+// Which strip and rows a warp task of the fused 2-D kernel handles -- shared by the kernel and by the host-side
+// coverage test (lora_debug_tasks_2dtb).  Edge strips (first / last: every row is patched) are cut into short tasks of
+// g.edge_rows rows, whose halo columns fit the shared-memory staging area, and come first; then the inner strips chunk
+// by chunk with the first and last chunk (whose first / last rows are patched) in front.  Returns false for an empty task.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline bool decode_task_2dtb(const Geom2DTB &g, int task, int &strip, int &r0, int &R) {
+    if (g.nstrips >= 3) {
+        const int nedge = 2 * g.nedge;
+        if (task < nedge) {
+            strip = (task & 1) ? g.nstrips - 1 : 0;
+            r0 = g.row_lo + (task >> 1) * g.edge_rows;
+            R = g.row_hi - r0 < g.edge_rows ? g.row_hi - r0 : g.edge_rows;
+        } else {
+            const int t = task - nedge, inner = g.nstrips - 2;
+            strip = 1 + t % inner;
+            int chunk = t / inner;
+            chunk = chunk == 0 ? 0 : (chunk == 1 ? g.nchunks - 1 : chunk - 1);
+            r0 = g.row_lo + chunk * g.rows_per_chunk;
+            R = g.row_hi - r0 < g.rows_per_chunk ? g.row_hi - r0 : g.rows_per_chunk;
+        }
+    } else {  // narrow grid: every strip is an edge strip (the host keeps rows_per_chunk <= kEdgeRows2Tb)
+        strip = task % g.nstrips;
+        r0 = g.row_lo + (task / g.nstrips) * g.rows_per_chunk;
+        R = g.row_hi - r0 < g.rows_per_chunk ? g.row_hi - r0 : g.rows_per_chunk;
+    }
+    return R > 0;
+}
+
 struct Geom3D {
     double *out;
     long long row_pitch;    // padded columns

@@ -394,30 +394,8 @@ extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
     return LORA_OK;
 }
 
-// 2-D fused launch of kTb2 time steps over interior rows [lo, hi): see stencil2d_tb.cu
-static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
-                         int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base, void *stream) {
-    if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
-    if (tb == 1) return plan_step_impl(p, src, dst, lo, hi, mirror_base, stream);
-    if (tb != kTb2 || !tb2_form(p->form))
-        return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid)", kTb2);
-    if (!halo_src) return fail(LORA_ERR_ARG, "fused 2-D launches need halo_src (the buffer holding the caller's halo)");
-    if (lo == hi) return LORA_OK;
-    const CUtensorMap *tm;
-    int rc = get_tmap(p, src, &tm);
-    if (rc) return rc;
-    Geom2DTB g{};
-    g.out = dst;
-    g.halo_src = halo_src;
-    g.pitch = p->padded[1];
-    g.m = (int)p->dims[0];
-    g.n = (int)p->dims[1];
-    g.row_lo = (int)lo;
-    g.row_hi = (int)hi;
-    const int wout = strip_out_cols_2d_tb(tb);
-    g.nstrips = (g.n + wout - 1) / wout;
-    const long long slots = (long long)p->sm_count * 2 * kWarpsPerCta;
-    const long long rows = hi - lo;
+// Task geometry of a fused 2-D launch over `rows` rows (g.nstrips set): see decode_task_2dtb in kernels.h
+static void plan_tasks_2dtb(Geom2DTB &g, long long rows, long long slots) {
     if (g.nstrips >= 3) {
         // Inner strips are cut into nchunks tasks each; the two edge strips patch every row (about twice the time
         // per row), so they are cut into tasks of half that length (<= kEdgeRows2Tb rows: their halo columns are
@@ -462,6 +440,31 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
         g.nedge = 0;
         g.ntasks = g.nstrips * g.nchunks;
     }
+}
+
+// 2-D fused launch of kTb2 time steps over interior rows [lo, hi): see stencil2d_tb.cu
+static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
+                         int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base, void *stream) {
+    if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
+    if (tb == 1) return plan_step_impl(p, src, dst, lo, hi, mirror_base, stream);
+    if (tb != kTb2 || !tb2_form(p->form))
+        return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid)", kTb2);
+    if (!halo_src) return fail(LORA_ERR_ARG, "fused 2-D launches need halo_src (the buffer holding the caller's halo)");
+    if (lo == hi) return LORA_OK;
+    const CUtensorMap *tm;
+    int rc = get_tmap(p, src, &tm);
+    if (rc) return rc;
+    Geom2DTB g{};
+    g.out = dst;
+    g.halo_src = halo_src;
+    g.pitch = p->padded[1];
+    g.m = (int)p->dims[0];
+    g.n = (int)p->dims[1];
+    g.row_lo = (int)lo;
+    g.row_hi = (int)hi;
+    const int wout = strip_out_cols_2d_tb(tb);
+    g.nstrips = (g.n + wout - 1) / wout;
+    plan_tasks_2dtb(g, hi - lo, (long long)p->sm_count * 2 * kWarpsPerCta);
     g.par0 = launches_before & 1;
     g.virt_top = virt_lo ? 1 : 0;
     g.virt_bot = virt_hi ? 1 : 0;
@@ -605,6 +608,35 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
         if (rc) return rc;
     }
     return LORA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side planning, exposed for the CPU tests (no GPU needed)
+// ---------------------------------------------------------------------------------------------
+extern "C" int lora_debug_temporal_schedule(int times, int max_tb, int *out, int cap) {
+    const std::vector<int> tbs = temporal_schedule(times, max_tb);
+    for (size_t i = 0; i < tbs.size() && (int)i < cap; i++) out[i] = tbs[i];
+    return (int)tbs.size();
+}
+
+extern "C" int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int *out3, int cap) {
+    if (m <= 0 || n <= 0 || lo < 0 || hi > m || lo >= hi || sm_count <= 0) return -1;
+    Geom2DTB g{};
+    g.m = m;
+    g.n = n;
+    g.row_lo = lo;
+    g.row_hi = hi;
+    const int wout = strip_out_cols_2d_tb(kTb2);
+    g.nstrips = (n + wout - 1) / wout;
+    plan_tasks_2dtb(g, hi - lo, (long long)sm_count * 2 * kWarpsPerCta);
+    for (int t = 0; t < g.ntasks && t < cap; t++) {
+        int strip = -1, r0 = 0, R = 0;
+        if (!decode_task_2dtb(g, t, strip, r0, R)) R = 0;
+        out3[3 * t] = strip;
+        out3[3 * t + 1] = r0;
+        out3[3 * t + 2] = R;
+    }
+    return g.ntasks;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -204,30 +204,8 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (task >= g.ntasks) return;  // warps never synchronise with each other
 
     constexpr int kStripOut = kWarpCols - 8 * (TB - 1);  // columns a strip writes
-    // Edge strips (first / last: every row is patched) are cut into short tasks of g.edge_rows rows, whose halo
-    // columns fit the shared-memory staging area, and scheduled first; then the inner strips chunk by chunk with
-    // the first and last chunk (whose first / last rows are patched) in front.
     int strip, r0, R;
-    if (g.nstrips >= 3) {
-        const int nedge = 2 * g.nedge;
-        if (task < nedge) {
-            strip = (task & 1) ? g.nstrips - 1 : 0;
-            r0 = g.row_lo + (task >> 1) * g.edge_rows;
-            R = min(g.edge_rows, g.row_hi - r0);
-        } else {
-            const int t = task - nedge, inner = g.nstrips - 2;
-            strip = 1 + t % inner;
-            int chunk = t / inner;
-            chunk = chunk == 0 ? 0 : (chunk == 1 ? g.nchunks - 1 : chunk - 1);
-            r0 = g.row_lo + chunk * g.rows_per_chunk;
-            R = min(g.rows_per_chunk, g.row_hi - r0);
-        }
-    } else {  // narrow grid: every strip is an edge strip (the host keeps rows_per_chunk <= kEdgeRows2Tb)
-        strip = task % g.nstrips;
-        r0 = g.row_lo + (task / g.nstrips) * g.rows_per_chunk;
-        R = min(g.rows_per_chunk, g.row_hi - r0);
-    }
-    if (R <= 0) return;
+    if (!decode_task_2dtb(g, task, strip, r0, R)) return;  // task order and lengths: kernels.h
     const int cs = strip * kStripOut;                    // first interior column the strip writes
     const int cw = cs - 4 * (TB - 1);                    // first interior column the warp computes
 

@@ -135,3 +135,55 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "liboracle" not in text and "oracle/" not in text, f
+
+
+def test_temporal_schedule_of_the_library_matches_the_python_mirror():
+    """lora_plan_run's block schedule (C++) == slab.temporal_schedule (Python, used by the multi-GPU runner): same
+    blocks, their sum is `times`, their count has the parity of `times` (the result lands in buf[times % 2], S3)."""
+    import ctypes
+    from lorastencil_b200.slab import temporal_schedule
+    L = ls.lib()
+    buf = (ctypes.c_int * 4096)()
+    for max_tb in (1, 2, 3, 4, 8, 15):
+        for times in list(range(0, 70)) + [100, 999, 1000, 1001]:
+            k = L.lora_debug_temporal_schedule(times, max_tb, buf, 4096)
+            got = [buf[i] for i in range(k)]
+            assert got == temporal_schedule(times, max_tb), (times, max_tb)
+            assert sum(got) == times and len(got) % 2 == times % 2 and all(1 <= t <= max_tb for t in got)
+
+
+def test_fused_2d_task_plan_covers_every_row_of_every_strip_exactly_once():
+    """Host-side planning of a fused 2-D launch (lora_debug_tasks_2dtb = the kernel's own task decode): the tasks tile
+    strips x rows exactly once, edge-strip tasks fit the shared-memory staging area (<= 160 rows) and come first, and
+    the launch fits whole waves of the resident warps when there is enough work."""
+    import ctypes
+    L = ls.lib()
+    cap = 200000
+    buf = (ctypes.c_int * (3 * cap))()
+    rng = np.random.default_rng(0)
+    cases = [(10240, 10240, 0, 10240), (40960, 40960, 0, 40960), (300, 258, 0, 300), (9, 8, 0, 9), (2, 2, 0, 2),
+             (100000, 200, 0, 100000), (50, 100000, 0, 50), (2048, 1024, 5, 1029), (1000, 130, 991, 1000)]
+    cases += [(int(m), int(n), 0, int(m)) for m, n in zip(rng.integers(1, 5000, 12), rng.integers(1, 5000, 12))]
+    for m, n, lo, hi in cases:
+        for sms in (148, 4):
+            k = L.lora_debug_tasks_2dtb(m, n, lo, hi, sms, buf, cap)
+            assert 0 < k <= cap, (m, n, lo, hi)
+            nstrips = -(-n // 112)
+            cover = np.zeros((nstrips, hi - lo), dtype=np.int32)
+            first_inner = None
+            for t in range(k):
+                strip, r0, R = buf[3 * t], buf[3 * t + 1], buf[3 * t + 2]
+                if R <= 0:
+                    continue
+                assert 0 <= strip < nstrips and lo <= r0 and r0 + R <= hi, (m, n, t, strip, r0, R)
+                cover[strip, r0 - lo:r0 - lo + R] += 1
+                edge_strip = strip in (0, nstrips - 1)
+                if edge_strip:
+                    assert R <= 160
+                    if nstrips >= 3:
+                        assert first_inner is None  # all edge-strip tasks precede the inner ones
+                elif first_inner is None:
+                    first_inner = t
+            assert (cover == 1).all(), (m, n, lo, hi, sms)
+            if sms == 148 and m == n == 10240:
+                assert k <= 2 * 148 * 8  # two whole waves of the 8 resident warps per SM
