@@ -806,9 +806,23 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
         forced = true;
     }
     if (times < 1 || K < 2 || K > n) return false;
-    const long long C = ((n + K - 1) / K + 511) / 512 * 512;  // chunk length, whole kernel rows
+    long long C = ((n + K - 1) / K + 511) / 512 * 512;  // chunk length, whole kernel rows
     if (!forced && G > C / 16) return false;
-    K = (n + C - 1) / C;
+    // chunk boundaries.  Only the first chunk's H2D copy and the last chunk's D2H copy are not hidden behind launches,
+    // so (unless a chunk count is forced) those two chunks are quarter-length.
+    std::vector<long long> cut{0};
+    if (!forced && K >= 4) {
+        C = ((long long)(n / (K - 1.5)) + 511) / 512 * 512;
+        const long long small = (C / 4 + 511) / 512 * 512;
+        cut.push_back(small < n ? small : n);
+        while (cut.back() < n) {
+            const long long left = n - cut.back();
+            cut.push_back(left <= C + small ? (left > small + 512 ? n - small : n) : cut.back() + C);
+        }
+    } else {
+        while (cut.back() < n) cut.push_back(cut.back() + C < n ? cut.back() + C : n);
+    }
+    K = (long long)cut.size() - 1;
     if (K < 2) return false;
 
     // Two chunks compute at a time (two launch streams): the tail of one chunk's sweep, where SMs run dry, is
@@ -829,7 +843,7 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
         CU_DIE(cudaEventCreate(&t0[c]));         // timed: start of the chunk's launch loop
     }
     for (long long c = 0; c < K; c++) {
-        const long long lo = c * C, hi = (lo + C < n) ? lo + C : n;
+        const long long lo = cut[c], hi = cut[c + 1];
         const long long gl = G < lo ? G : lo, gr = G < n - hi ? G : n - hi;
         const long long nloc = (hi + gr) - (lo - gl);        // interior length of the chunk's own padded array
         const int virt_lo = (lo - gl == 0), virt_hi = (hi + gr == n);

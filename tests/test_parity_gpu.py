@@ -375,3 +375,19 @@ def test_no_write_outside_the_destination_interior(shape, dims, times):
     a_h[inner] = 0.0
     h1[inner] = 0.0
     assert np.array_equal(h0, a_h) and not h1.any()
+
+
+def test_chunked_operator_automatic_boundaries_at_scale(monkeypatch):
+    """The chunk boundaries the operator picks on its own for a long line (quarter-length first / last chunk, not
+    multiples of the kernel row): same bits as the plain path on a 2^26-point line, halo cells included."""
+    shape, n, times = "1d2r", 1 << 26, 10
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 10, size=(n + 8,)).astype(np.float64)
+    p = oracle.reference_params(shape)
+    monkeypatch.setenv("LORA_CHUNKS", "0")
+    plain = run_dropin(shape, a, p, times, (n,))
+    assert ops.last_chunks() == 1
+    monkeypatch.delenv("LORA_CHUNKS")
+    auto = run_dropin(shape, a, p, times, (n,))
+    assert ops.last_chunks() >= 4
+    assert np.array_equal(auto, plain)
