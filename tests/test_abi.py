@@ -187,3 +187,93 @@ def test_fused_2d_task_plan_covers_every_row_of_every_strip_exactly_once():
             assert (cover == 1).all(), (m, n, lo, hi, sms)
             if sms == 148 and m == n == 10240:
                 assert k <= 2 * 148 * 8  # two whole waves of the 8 resident warps per SM
+
+
+def _reconstruct_2d(d):
+    """Independent numpy reconstruction of the 7x7 table from what lora_decompose_2d hands the kernels."""
+    T = np.zeros((7, 7))
+    f = d["form"]
+    if f == "cross":
+        T[:, 3] += d["vert"][0]                      # column arm, centre included
+        row = d["horiz"][1].copy()
+        row[3] = 0.0                                 # row arm, centre excluded
+        T[3, :] += row
+    elif f in ("pyramid", "pyramid_pruned"):
+        for t in range(3):
+            T += np.outer(d["vert"][t], d["horiz"][t])
+        T[3, 3] += d["centre"]
+    elif f == "diamond":
+        T += np.outer(d["vert"][0], d["horiz"][0])
+        for (r, c), w in zip([(3, 0), (3, 6), (0, 3), (6, 3), (1, 1), (1, 5), (5, 1), (5, 5)], d["residual"]):
+            T[r, c] += w
+    else:
+        return None
+    return T
+
+
+def test_general_decomposition_reconstructs_random_tables_of_every_structure():
+    """Property test (hypothesis) of the host low-rank decomposition in GENERAL mode: whatever exact form it picks
+    for a random cross / pyramidal / diamond-structured / unstructured 7x7 table, (i) the factors it would upload
+    rebuild the table, (ii) the effective direct-tap weights equal the table (what the oracle is fed), (iii) a
+    structured table is never demoted to the 49-tap form."""
+    from hypothesis import given, settings, strategies as st
+
+    vals = st.floats(min_value=-4, max_value=4, allow_nan=False, allow_infinity=False).map(lambda v: round(v, 3))
+    nz = vals.filter(lambda v: abs(v) > 0.1)
+
+    @st.composite
+    def tables(draw):
+        kind = draw(st.sampled_from(["cross", "pyramid", "diamond", "random"]))
+        T = np.zeros((7, 7))
+        if kind == "cross":
+            T[:, 3] = [draw(vals) for _ in range(7)]
+            T[3, :] = [draw(vals) for _ in range(7)]
+        elif kind == "pyramid":
+            for t in range(3):
+                u, v = np.zeros(7), np.zeros(7)
+                u[t:7 - t] = [draw(nz) for _ in range(7 - 2 * t)]
+                v[t:7 - t] = [draw(nz) for _ in range(7 - 2 * t)]
+                T += np.outer(u, v)
+            T[3, 3] += draw(vals)
+        elif kind == "diamond":
+            u, v = np.zeros(7), np.zeros(7)
+            u[1:6] = [draw(nz) for _ in range(5)]
+            v[1:6] = [draw(nz) for _ in range(5)]
+            T += np.outer(u, v)
+            for r, c in [(3, 0), (3, 6), (0, 3), (6, 3), (1, 1), (1, 5), (5, 1), (5, 5)]:
+                T[r, c] += draw(vals)
+        else:
+            T = np.array([[draw(vals) for _ in range(7)] for _ in range(7)])
+        return kind, T
+
+    @settings(max_examples=150, deadline=None)
+    @given(tables())
+    def check(kt):
+        kind, T = kt
+        d = ls.decompose_2d("box2d3r", T, mode=ls.WEIGHTS_GENERAL)
+        scale = max(1.0, np.abs(T).max())
+        assert np.abs(ls.effective_weights("box2d3r", ls.WEIGHTS_GENERAL, T).reshape(7, 7) - T).max() <= 1e-12 * scale
+        R = _reconstruct_2d(d)
+        if R is not None:
+            assert np.abs(R - T).max() <= 1e-9 * scale, (kind, d["form"])
+        if kind != "random":
+            assert d["form"] != "direct49", kind
+        assert d["macs_per_cell"] <= 49
+
+    check()
+
+
+def test_general_3d_effective_weights_equal_the_table_for_every_structure():
+    """3-D GENERAL mode: separable (a (x) b (x) c), 7-point star and unstructured 27-point tables all come back
+    as exactly the taps the plan will apply (the forms differ -- sep3 / star7 / direct27 -- the mathematics must not)."""
+    rng = np.random.default_rng(12)
+    for _ in range(40):
+        a, b, c = (np.round(rng.uniform(-3, 3, 3), 3) for _ in range(3))
+        sep = np.einsum("i,j,k->ijk", a, b, c)
+        star = np.zeros((3, 3, 3))
+        star[1, 1, 1], star[0, 1, 1], star[2, 1, 1] = np.round(rng.uniform(-3, 3, 3), 3)
+        star[1, 0, 1], star[1, 2, 1], star[1, 1, 0], star[1, 1, 2] = np.round(rng.uniform(-3, 3, 4), 3)
+        full = np.round(rng.uniform(-3, 3, (3, 3, 3)), 3)
+        for T in (sep, star, full):
+            eff = ls.effective_weights("box3d1r", ls.WEIGHTS_GENERAL, T.reshape(-1)).reshape(3, 3, 3)
+            assert np.abs(eff - T).max() <= 1e-12 * max(1.0, np.abs(T).max())
