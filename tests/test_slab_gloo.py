@@ -175,3 +175,33 @@ def test_peer_mirror_shifts_map_edge_bands_onto_neighbour_ghost_rows():
                     v = u + shift // rest
                     assert 0 <= v < gn.wl
                     assert gn.global_rows().start + v == first_global + u
+
+
+def test_2d_schedule_uses_odd_blocks_only():
+    """2-D sweeps advance 3 or 1 launches: every prefix has time parity == sweep parity (the source buffer's own halo
+    ring is then the right one for level 0), and the result lands in buf[times % 2] (S3)."""
+    from lorastencil_b200.slab import temporal_schedule_2d
+    for times in range(0, 50):
+        for max_tb in (1, 3):
+            tbs = temporal_schedule_2d(times, max_tb)
+            assert sum(tbs) == times and all(t in (1, 3) for t in tbs) and (max_tb == 3 or all(t == 1 for t in tbs))
+            done = 0
+            for k, t in enumerate(tbs):
+                assert done % 2 == k % 2
+                done += t
+            assert len(tbs) % 2 == times % 2
+
+
+def test_host_segments_cover_the_line_and_carry_the_dependency_cone():
+    """slab.host_segment: the slabs of all ranks tile [0, n) exactly; a margin is the dependency cone of `times`
+    launches (4 cells per launch, + the 4-cell halo and alignment slack) or reaches the end of the line."""
+    from lorastencil_b200.slab import host_segment
+    for n, world, times in ((1 << 28, 8, 1000), (1 << 20, 3, 37), (300000, 2, 8), (1000, 4, 500), (17, 2, 1)):
+        segs = [host_segment(n, world, r, times) for r in range(world)]
+        assert segs[0][0] == 0 and segs[-1][1] == n
+        for (lo, hi, gl, gr), nxt in zip(segs, segs[1:] + [None]):
+            assert lo <= hi
+            if nxt is not None:
+                assert hi == nxt[0]
+            assert gl == min(4 * times + 8, lo) and gr == min(4 * times + 8, n - hi)
+            assert lo - gl >= 0 and hi + gr <= n
