@@ -47,6 +47,7 @@ struct SweepTB {
     int out_lo, out_hi;     // interior rows this chunk writes: [out_lo, out_hi)
     bool store_lane;        // this lane's columns are valid at level TB
     bool col_edge;          // the strip has cells outside [0, n): intermediate levels need column patching
+    bool hal_ok;            // ... and the task is short enough for its halo columns to be staged in s.hal
     bool virt_top, virt_bot;  // rows above 0 / below m are the global halo ring (virtual), not a neighbour slab's rows
     int par0;               // time parity before level 0
     bool vec4;
@@ -69,7 +70,7 @@ __device__ __forceinline__ void patch_row(double (&v)[4], int i_row, int rho, in
             if (caller && rho >= -4 && rho < s.m + 4 && c >= -4 && c < s.n + 4) h = s.hsrc[(long long)rho * s.pitch + q];
             v[q] = h;
         }
-    } else if (s.col_edge) {
+    } else if (s.col_edge && s.hal_ok) {
         const double *hr = s.hal + 8 * min(max(i_row, 0), s.nin - 1);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -78,6 +79,16 @@ __device__ __forceinline__ void patch_row(double (&v)[4], int i_row, int rho, in
                 v[q] = (caller && c >= -4) ? hr[c + 4] : 0.0;
             else if (c >= s.n)
                 v[q] = (caller && c < s.n + 4) ? hr[4 + c - s.n] : 0.0;
+        }
+    } else if (s.col_edge) {
+        // an INNER strip whose 128-column window crosses column n (the last strip is narrower than 8 columns) runs
+        // as a long task, too long for the staging area: its few halo cells come straight from global memory
+        const bool row_ok = rho >= -4 && rho < s.m + 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c = s.c0 + q;
+            if (c < 0 || c >= s.n)
+                v[q] = (caller && row_ok && c >= -4 && c < s.n + 4) ? s.hsrc[(long long)rho * s.pitch + q] : 0.0;
         }
     }
 }
@@ -226,6 +237,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.out_hi = r0 + R;
     s.store_lane = lane >= TB - 1 && lane <= 32 - TB && s.c0 < g.n && s.c0 < cs + kStripOut;
     s.col_edge = cw < 0 || cw + kWarpCols > g.n;
+    s.hal_ok = R + 6 * TB <= kHalRows2Tb;
     s.virt_top = g.virt_top != 0;
     s.virt_bot = g.virt_bot != 0;
     s.par0 = g.par0 & 1;
@@ -236,7 +248,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.hsrc = g.halo_src + 4 * g.pitch + 4 + s.c0;
     double *hal = reinterpret_cast<double *>(smem_raw + kSmem12) + warp * (kHalRows2Tb * 8);
     s.hal = hal;
-    if (s.col_edge) {
+    if (s.col_edge && s.hal_ok) {
         // stage the caller's halo columns (4 left of column 0, 4 right of column n-1) of the task's rows
         for (int idx = lane; idx < s.nin; idx += 32) {
             const int rho = s.rho0 + idx;

@@ -304,7 +304,7 @@ def test_chunked_copy_overlapped_operator_equals_plain(shape, n, times, chunks, 
 
 
 @pytest.mark.parametrize("shape", ["star2d3r", "star2d1r", "box2d1r"])
-@pytest.mark.parametrize("dims", [(40, 130), (64, 64), (300, 258), (257, 1000), (1000, 130), (9, 8), (2, 2)])
+@pytest.mark.parametrize("dims", [(40, 130), (64, 64), (300, 258), (257, 1000), (1000, 130), (9, 8), (2, 2), (400, 230)])
 def test_temporal_blocking_2d_equals_unfused_launches(shape, dims):
     """2-D sweeps of 3 fused launches (intermediate grids in registers, virtual alternating halo ring on all four
     sides, overlapped strips) give the same bits as one launch per step, and match the oracle, for every launch
@@ -391,3 +391,28 @@ def test_chunked_operator_automatic_boundaries_at_scale(monkeypatch):
     auto = run_dropin(shape, a, p, times, (n,))
     assert ops.last_chunks() >= 4
     assert np.array_equal(auto, plain)
+
+
+@pytest.mark.parametrize("shape", ["star2d3r", "star2d1r"])
+def test_fused_2d_inner_strip_crossing_the_right_edge(shape):
+    """n = 91 x 112 + 6: the last strip is narrower than 8 columns, so the 128-column window of the second-to-last
+    (an INNER strip, which runs as a long task) crosses column n as well -- its halo cells cannot be staged in shared
+    memory (task longer than the staging area) and come from global memory.  Fused == unfused, bit for bit, and a
+    band of rows is checked against the oracle."""
+    import torch
+    dims = (3000, 91 * 112 + 6)
+    plan = ls.Plan(shape, dims)
+    rng = np.random.default_rng(17)
+    a = rng.integers(0, 10, size=plan.padded_shape).astype(np.float64)
+    results = []
+    for tb in (1, 3):
+        plan.temporal_block = tb
+        b0, b1 = torch.from_numpy(a).cuda(), plan.new_buffer()
+        res = plan.run(b0, b1, 6)
+        torch.cuda.synchronize()
+        results.append(res.cpu().numpy())
+    assert np.array_equal(results[0], results[1])
+    # right-hand columns of the first rows against the oracle on a cut-out (6 launches need 18 more rows / columns)
+    sub = np.ascontiguousarray(a[:60 + 8, -(300 + 8):])
+    ref = oracle.run(shape, sub, oracle.effective_params(shape), 6)
+    assert np.array_equal(results[1][4:4 + 30, -(4 + 200):-4], ref[4:4 + 30, -(4 + 200):-4])
