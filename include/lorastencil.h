@@ -104,6 +104,15 @@ int lora_last_chunks(void);
 /* free the device workspace the drop-in operators cache between calls */
 void lora_release_workspace(void);
 
+/* Multi-GPU behind the same surface (new; the reference caller is one process calling one operator,
+ * src/2d/main.cu:268-280): with the environment variable LORA_NGPU=k, or after lora_set_gpus(k), every lora_gpu_* /
+ * gpu_* call cuts its grid into k slabs along the outermost axis, one per GPU of this process (cudaSetDevice + peer
+ * access), and exchanges the ghost zones inside the kernels over NVLink (lora_slabset_* below).  Same buffer
+ * semantics, banner and timed region; bit-identical results.  A grid too thin for k slabs runs on one GPU.
+ * lora_set_gpus returns the previous setting; lora_last_gpus how many GPUs the last call actually used. */
+int lora_set_gpus(int k);
+int lora_last_gpus(void);
+
 /* ------------------------------------------------------------------------------------------
  * Layer 2: device-resident plans
  * ------------------------------------------------------------------------------------------ */
@@ -167,6 +176,58 @@ int lora_plan_step_mirror(lora_plan_t *plan, const double *src, double *dst, lon
 int lora_plan_step_fused_mirror(lora_plan_t *plan, const double *src, double *dst, const double *halo_src, long long lo,
                                 long long hi, int tb, int launches_before, int virt_lo, int virt_hi,
                                 const double *mirror_base, void *stream);
+
+/* ---- slabs: the whole multi-GPU sweep in the library (new) ----
+ * The grid is cut along its outermost axis into `world` contiguous slabs; each keeps the reference's two ping-pong
+ * buffers for its rows plus ghost zones of (stencil radius x deepest temporal block) towards its neighbours and the
+ * reference's storage halo towards the ends of the grid.  One sweep of a slab is ONE kernel launch: the tasks of the
+ * two bands a neighbour needs run first, store their cells a second time straight into the neighbour's ghost zone
+ * (peer memory) and raise a flag there when the band is complete; the interior overlaps that; the next sweep waits
+ * for the neighbours' flags in stream order.  No communication library on the data path.
+ *
+ * lora_slab_*: ONE slab on the current device -- for one-process-per-GPU ranks.  Rank r creates its slab, exports
+ * three 64-byte CUDA IPC handles (buffer 0, buffer 1, flags), receives its neighbours' (any rendezvous: the Python
+ * layer uses torch.distributed) and connects: side 0 = rank r-1, side 1 = rank r+1.  lora_slab_connect_local does the
+ * same for a neighbour slab living in this process (peer access instead of IPC).
+ * info10: {lo, hi (the slab's interior range on the global outermost axis), wl, wr (cells stored before / after the
+ * slab: ghost or halo), off (first slab cell in plan-interior coordinates), local padded sizes [3], deepest temporal
+ * block, ghost width}.  The padded local buffer mirrors global padded rows [lo + halo - wl, hi + halo + wr).
+ * temporal_block 0 = the shape's default.  lora_slab_run is asynchronous on `stream`; after it the result is in
+ * buffer lora_slab_result_index().  After (re)filling the buffers from outside call lora_slab_reset -- and make sure
+ * (device sync + rendezvous) no neighbour is still sweeping. */
+typedef struct lora_slab lora_slab_t;
+int lora_slab_create(lora_slab_t **slab, int shape, int mode, const double *params, const long long *global_dims,
+                     int world, int rank, int temporal_block);
+void lora_slab_destroy(lora_slab_t *slab);
+int lora_slab_info(const lora_slab_t *slab, long long *info10);
+double *lora_slab_buffer(lora_slab_t *slab, int which);
+int lora_slab_export(lora_slab_t *slab, void *handles192);
+int lora_slab_connect_ipc(lora_slab_t *slab, int side, const void *handles192);
+int lora_slab_connect_local(lora_slab_t *slab, int side, lora_slab_t *neighbour);
+int lora_slab_reset(lora_slab_t *slab);
+int lora_slab_sweep(lora_slab_t *slab, int tb, void *stream);
+int lora_slab_run(lora_slab_t *slab, int times, void *stream);
+int lora_slab_schedule(const lora_slab_t *slab, int times, int *blocks_out, int cap);
+int lora_slab_result_index(const lora_slab_t *slab);
+long long lora_slab_launch_count(const lora_slab_t *slab);
+lora_plan_t *lora_slab_plan(lora_slab_t *slab);
+/* host-only: the partition rule (CPU tests).  out8: lo, hi, wl, wr, off, local interior sizes [3] */
+int lora_slab_geometry(int dim, const long long *global_dims, int world, int rank, long long ghost, long long *out8);
+
+/* lora_slabset_*: all slabs of one grid on `ndev` devices of THIS process (devices NULL = 0..ndev-1); what the
+ * drop-in operators use under LORA_NGPU.  load: H2D scatter of a padded host grid (S2: buffer 1 <- zeros);
+ * run: `times` launches on every device, issued sweep by sweep, asynchronous; sync; store: D2H gather of the padded
+ * result (S3). */
+typedef struct lora_slabset lora_slabset_t;
+int lora_slabset_create(lora_slabset_t **set, int shape, int mode, const double *params, const long long *global_dims,
+                        int ndev, const int *devices);
+void lora_slabset_destroy(lora_slabset_t *set);
+int lora_slabset_load(lora_slabset_t *set, const double *host_padded_in);
+int lora_slabset_run(lora_slabset_t *set, int times);
+int lora_slabset_sync(lora_slabset_t *set);
+int lora_slabset_store(lora_slabset_t *set, double *host_padded_out);
+long long lora_slabset_launch_count(const lora_slabset_t *set);
+int lora_slabset_temporal_block(const lora_slabset_t *set);
 
 /* how many kernel launches the plan has issued so far (bench.py's gpu_launches) */
 long long lora_plan_launch_count(const lora_plan_t *plan);

@@ -24,6 +24,12 @@ C_ABI_SYMBOLS = (
     "lora_peer_alloc", "lora_peer_free", "lora_peer_open", "lora_peer_close", "lora_stream_write_flag",
     "lora_stream_wait_flag_geq", "lora_debug_temporal_schedule", "lora_debug_tasks_2dtb", "lora_plan_launch_count", "lora_plan_describe",
     "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
+    "lora_set_gpus", "lora_last_gpus",
+    "lora_slab_create", "lora_slab_destroy", "lora_slab_info", "lora_slab_buffer", "lora_slab_export",
+    "lora_slab_connect_ipc", "lora_slab_connect_local", "lora_slab_reset", "lora_slab_sweep", "lora_slab_run",
+    "lora_slab_schedule", "lora_slab_result_index", "lora_slab_launch_count", "lora_slab_plan", "lora_slab_geometry",
+    "lora_slabset_create", "lora_slabset_destroy", "lora_slabset_load", "lora_slabset_run", "lora_slabset_sync",
+    "lora_slabset_store", "lora_slabset_launch_count", "lora_slabset_temporal_block",
 )
 # the reference's own C++ symbols (include/lorastencil_dropin.hpp)
 CXX_DROPIN_SYMBOLS = (
@@ -131,6 +137,56 @@ def lib() -> ctypes.CDLL:
     L.lora_reference_table.restype = c_int
     L.lora_effective_weights.argtypes = [c_int, c_int, dp, dp]
     L.lora_effective_weights.restype = c_int
+    L.lora_set_gpus.argtypes = [c_int]
+    L.lora_set_gpus.restype = c_int
+    L.lora_last_gpus.restype = c_int
+    llp = POINTER(c_longlong)
+    L.lora_slab_create.argtypes = [POINTER(c_void_p), c_int, c_int, dp, llp, c_int, c_int, c_int]
+    L.lora_slab_create.restype = c_int
+    L.lora_slab_destroy.argtypes = [c_void_p]
+    L.lora_slab_destroy.restype = None
+    L.lora_slab_info.argtypes = [c_void_p, llp]
+    L.lora_slab_info.restype = c_int
+    L.lora_slab_buffer.argtypes = [c_void_p, c_int]
+    L.lora_slab_buffer.restype = c_void_p
+    L.lora_slab_export.argtypes = [c_void_p, c_void_p]
+    L.lora_slab_export.restype = c_int
+    L.lora_slab_connect_ipc.argtypes = [c_void_p, c_int, c_void_p]
+    L.lora_slab_connect_ipc.restype = c_int
+    L.lora_slab_connect_local.argtypes = [c_void_p, c_int, c_void_p]
+    L.lora_slab_connect_local.restype = c_int
+    L.lora_slab_reset.argtypes = [c_void_p]
+    L.lora_slab_reset.restype = c_int
+    L.lora_slab_sweep.argtypes = [c_void_p, c_int, c_void_p]
+    L.lora_slab_sweep.restype = c_int
+    L.lora_slab_run.argtypes = [c_void_p, c_int, c_void_p]
+    L.lora_slab_run.restype = c_int
+    L.lora_slab_schedule.argtypes = [c_void_p, c_int, POINTER(c_int), c_int]
+    L.lora_slab_schedule.restype = c_int
+    L.lora_slab_result_index.argtypes = [c_void_p]
+    L.lora_slab_result_index.restype = c_int
+    L.lora_slab_launch_count.argtypes = [c_void_p]
+    L.lora_slab_launch_count.restype = c_longlong
+    L.lora_slab_plan.argtypes = [c_void_p]
+    L.lora_slab_plan.restype = c_void_p
+    L.lora_slab_geometry.argtypes = [c_int, llp, c_int, c_int, c_longlong, llp]
+    L.lora_slab_geometry.restype = c_int
+    L.lora_slabset_create.argtypes = [POINTER(c_void_p), c_int, c_int, dp, llp, c_int, POINTER(c_int)]
+    L.lora_slabset_create.restype = c_int
+    L.lora_slabset_destroy.argtypes = [c_void_p]
+    L.lora_slabset_destroy.restype = None
+    L.lora_slabset_load.argtypes = [c_void_p, c_void_p]
+    L.lora_slabset_load.restype = c_int
+    L.lora_slabset_run.argtypes = [c_void_p, c_int]
+    L.lora_slabset_run.restype = c_int
+    L.lora_slabset_sync.argtypes = [c_void_p]
+    L.lora_slabset_sync.restype = c_int
+    L.lora_slabset_store.argtypes = [c_void_p, c_void_p]
+    L.lora_slabset_store.restype = c_int
+    L.lora_slabset_launch_count.argtypes = [c_void_p]
+    L.lora_slabset_launch_count.restype = c_longlong
+    L.lora_slabset_temporal_block.argtypes = [c_void_p]
+    L.lora_slabset_temporal_block.restype = c_int
     _LIB = L
     return L
 

@@ -7,7 +7,8 @@
 // Extras the reference ignores: a trailing "--check" (or building with -DCHECK_ERROR) runs the
 // reference's verification protocol -- one direct-tap CPU step against one GPU launch, every interior
 // cell whose absolute difference exceeds 1e-7 is printed, then "Correct!" (src/2d/main.cu:282-328);
-// the process additionally returns 2 when a mismatch was found.
+// the process additionally returns 2 when a mismatch was found.  A trailing "--gpus k" (or LORA_NGPU=k in the
+// environment) cuts the grid into k slabs along its outermost axis, one per GPU, ghost zones exchanged over NVLink.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -132,8 +133,11 @@ int main(int argc, char *argv[]) {
 #if defined(CHECK_ERROR)
     check = true;
 #endif
-    for (int i = kDim + 3; i < argc; i++)
+    for (int i = kDim + 3; i < argc; i++) {
         if (std::strcmp(argv[i], "--check") == 0) check = true;
+        // trailing "--gpus k": slab-decompose the grid over k GPUs of this box (same as LORA_NGPU=k)
+        if (std::strcmp(argv[i], "--gpus") == 0 && i + 1 < argc) lora_set_gpus(atoi(argv[++i]));
+    }
 
 #if LORA_CLI_DIM == 1
     printf("INFO: shape = %s, n = %lld, times = %d\n", sn->info, dims[0], times);

@@ -66,6 +66,27 @@ struct Weights1D {
     double w[9];
 };
 
+// How one launch's range [lo, hi) of the swept (outermost) axis is cut into up to three SEGMENTS, and what a
+// multi-GPU slab does with them (new: the reference is single-GPU).  A plain launch is one segment.  A slab launch
+// that faces neighbours is [lo band][hi band][middle]: the two bands are the cells the neighbours' next sweep
+// reads (ghost-zone width), their tasks are enumerated -- and therefore dispatched -- FIRST, every cell they store
+// at out[x] is stored at out[x + mirror] too (the neighbour's ghost zone, peer memory over NVLink), and when the
+// last task of a band has stored, it raises a 64-bit flag in the neighbour's memory to `seq`.  The middle segment
+// reads this GPU's own cells only.  One kernel launch per sweep: halo transfer, its completion signal and the
+// interior all overlap inside it.
+constexpr int kMaxSegs = 3;
+struct Segs {
+    int nseg;                                // 1..3
+    long long lo[kMaxSegs], hi[kMaxSegs];    // segment ranges on the swept axis (the kernel's own coordinate)
+    long long chunk[kMaxSegs];               // chunk length of the segment's tasks along that axis
+    long long first[kMaxSegs + 1];           // segment s owns tasks (3-D: plane chunks) [first[s], first[s + 1])
+    long long mirror[kMaxSegs];              // != 0: every cell stored at out[x] is also stored at out[x + mirror]
+    unsigned long long *flag[kMaxSegs];      // nullptr, or the flag (peer memory) raised to `seq` when the segment is done
+    unsigned long long *count[kMaxSegs];     // arrival counter of the segment (this GPU's memory, only ever grows)
+    unsigned long long target[kMaxSegs];     // counter value that completes the segment in THIS launch
+    unsigned long long seq;
+};
+
 struct Weights2D {
     double vert[3][7];
     double horiz[3][7];
@@ -82,6 +103,25 @@ struct Weights3D {
     double star[7];           // STAR7: centre, n-1, n+1, m-1, m+1, h-1, h+1
     double direct[27];        // DIRECT27
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int seg_of(const Segs &sg, long long task) {
+    int s = 0;
+    if (sg.nseg > 1 && task >= sg.first[1]) s = 1;
+    if (sg.nseg > 2 && task >= sg.first[2]) s = 2;
+    return s;
+}
+// One thread per task calls this AFTER the task's storing threads have executed __threadfence_system() and been
+// joined (__syncwarp / __syncthreads): the last arrival of the segment publishes `seq` in the neighbour's flag.
+__device__ __forceinline__ void seg_arrive(const Segs &sg, int s) {
+    if (sg.flag[s] == nullptr) return;
+    const unsigned long long old = atomicAdd(sg.count[s], 1ULL);
+    if (old + 1 == sg.target[s]) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sg.flag[s]), "l"(sg.seq) : "memory");
+    }
+}
+#endif
 
 struct Geom1D {
     const double *in;   // padded source
@@ -100,10 +140,9 @@ struct Geom1DTB {
     double *out;             // padded destination (level TB)
     const double *halo_src;  // padded buffer whose halo cells hold the caller's halo (buffer 0 of the ping-pong)
     long long n;             // interior length of the device array
-    long long xlo, xhi;      // cells written by this launch: X in [xlo, xhi)
-    long long rho0, nrows;   // output rows (row r = cells [512 r - 4 TB, +512)) that intersect [xlo, xhi)
+    Segs sg;                 // segments in PADDED coordinates X: segment s writes cells [lo[s], hi[s]); its tasks sweep
+                             // chunk[s] output rows (row r = cells [512 r - 4 TB, +512)) each
     int tb;                  // time steps fused by this launch (1..kMaxTb1)
-    int rows_per_task;       // rows one warp sweeps
     long long ntasks;
     int par0;                // parity of the launch count before level 0 (0: level 0 sees the caller's halo)
     int virt_left, virt_right;  // this end of the array is an end of the global line: halo cells are virtual
@@ -111,19 +150,16 @@ struct Geom1DTB {
     long long xcov;          // level-0 cells X >= xcov are not covered by the load map
     long long out_off;       // the store map starts at cell out_off (= -4 TB mod 16) ...
     long long out_rows;      // ... and covers out_rows rows of 16 cells
-    long long mirror;        // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
 struct Geom2D {
     double *out;
     long long pitch;  // padded columns
     int m, n;
-    int row_lo, row_hi;
-    int rows_per_chunk;
+    Segs sg;          // segments = interior row ranges; a task = (strip, chunk of chunk[s] rows); strips vary fastest
     int nstrips;
     int ntasks;
-    int vec4;  // 256-bit stores allowed (n % 4 == 0 and 32-byte aligned base)
-    long long mirror;  // != 0: every cell stored at out[x] is also stored at out[x + mirror]
+    int vec4;  // 256-bit stores allowed (n % 4 == 0, 32-byte aligned base, mirrors a multiple of 4 doubles away)
 };
 
 // fused 2-D kernel: tasks of the first / last strip stage their rows' caller's-halo columns in shared memory
@@ -138,15 +174,17 @@ struct Geom2DTB {
     const double *halo_src;  // padded buffer whose halo ring holds the caller's halo (buffer 0 of the ping-pong)
     long long pitch;         // padded columns
     int m, n;
-    int row_lo, row_hi;      // interior rows written by this launch
+    Segs sg;                 // band segments (and every segment of a narrow grid): tasks = (strip, chunk of chunk[s] <=
+                             // kEdgeRows2Tb rows), strips fastest.  The LAST segment of a grid with nstrips >= 3 is the
+                             // main one: [row_lo, row_hi) below, cut as decode_task_2dtb describes
+    int row_lo, row_hi;      // interior rows of the main segment
     int rows_per_chunk;
     int nstrips, nchunks;
     int edge_rows, nedge;    // nstrips >= 3: the two edge strips run as 2 * nedge tasks of edge_rows (<= kEdgeRows2Tb) rows
-    int ntasks;              // nstrips >= 3: 2 * nedge + (nstrips - 2) * nchunks; else nstrips * nchunks
+    int ntasks;              // all segments
     int par0;                // parity of the launch count before level 0 (== parity of the source buffer)
     int virt_top, virt_bot;  // rows beyond that end are the global halo ring (virtual halo), not neighbour-slab data
     int vec4;
-    long long mirror;        // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
 // Which strip and rows a warp task of the fused 2-D kernel handles -- shared by the kernel and by the host-side
@@ -156,25 +194,30 @@ struct Geom2DTB {
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline bool decode_task_2dtb(const Geom2DTB &g, int task, int &strip, int &r0, int &R) {
-    if (g.nstrips >= 3) {
+inline bool decode_task_2dtb(const Geom2DTB &g, int task, int &strip, int &r0, int &R, int &seg) {
+    int s = 0;
+    while (s + 1 < g.sg.nseg && task >= g.sg.first[s + 1]) s++;
+    seg = s;
+    const int tt = task - (int)g.sg.first[s];
+    if (g.nstrips >= 3 && s == g.sg.nseg - 1) {  // the main segment
         const int nedge = 2 * g.nedge;
-        if (task < nedge) {
-            strip = (task & 1) ? g.nstrips - 1 : 0;
-            r0 = g.row_lo + (task >> 1) * g.edge_rows;
+        if (tt < nedge) {
+            strip = (tt & 1) ? g.nstrips - 1 : 0;
+            r0 = g.row_lo + (tt >> 1) * g.edge_rows;
             R = g.row_hi - r0 < g.edge_rows ? g.row_hi - r0 : g.edge_rows;
         } else {
-            const int t = task - nedge, inner = g.nstrips - 2;
+            const int t = tt - nedge, inner = g.nstrips - 2;
             strip = 1 + t % inner;
             int chunk = t / inner;
             chunk = chunk == 0 ? 0 : (chunk == 1 ? g.nchunks - 1 : chunk - 1);
             r0 = g.row_lo + chunk * g.rows_per_chunk;
             R = g.row_hi - r0 < g.rows_per_chunk ? g.row_hi - r0 : g.rows_per_chunk;
         }
-    } else {  // narrow grid: every strip is an edge strip (the host keeps rows_per_chunk <= kEdgeRows2Tb)
-        strip = task % g.nstrips;
-        r0 = g.row_lo + (task / g.nstrips) * g.rows_per_chunk;
-        R = g.row_hi - r0 < g.rows_per_chunk ? g.row_hi - r0 : g.rows_per_chunk;
+    } else {  // band segment, or a narrow grid where every strip is an edge strip (the host keeps chunk <= kEdgeRows2Tb)
+        const int ch = (int)g.sg.chunk[s], lo = (int)g.sg.lo[s], hi = (int)g.sg.hi[s];
+        strip = tt % g.nstrips;
+        r0 = lo + (tt / g.nstrips) * ch;
+        R = hi - r0 < ch ? hi - r0 : ch;
     }
     return R > 0;
 }
@@ -184,11 +227,9 @@ struct Geom3D {
     long long row_pitch;    // padded columns
     long long plane_pitch;  // padded rows * padded columns
     int h, m, n;
-    int h_lo, h_hi;
-    int planes_per_chunk;
+    Segs sg;  // segments = interior plane ranges; first[] counts plane chunks (blockIdx.y), a CTA = (tile, chunk)
     int tiles_m, tiles_n;
     int vec4;
-    long long mirror;  // != 0: every cell stored at out[x] is also stored at out[x + mirror]
 };
 
 cudaError_t launch_1d(const Geom1D &g, const Weights1D &w, cudaStream_t s);

@@ -37,7 +37,10 @@ extern "C" int lora_peer_alloc(void **ptr, unsigned long long bytes, void *handl
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) return LORA_ERR_CUDA;
-    if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess) return LORA_ERR_CUDA;
+    if ((e = cudaMemset(p, 0, bytes)) != cudaSuccess) {
+        cudaFree(p);
+        return LORA_ERR_CUDA;
+    }
     cudaIpcMemHandle_t h;
     if ((e = cudaIpcGetMemHandle(&h, p)) != cudaSuccess) {
         cudaFree(p);

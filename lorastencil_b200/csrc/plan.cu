@@ -18,6 +18,7 @@
 #include "../../include/lorastencil.h"
 #include "../../include/lorastencil_dropin.hpp"
 #include "decompose.h"
+#include "exchange.h"
 #include "kernels.h"
 
 using namespace lora;
@@ -43,6 +44,16 @@ static int fail(int code, const char *fmt, ...) {
         if (e__ != cudaSuccess)                                                                   \
             return fail(LORA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
+
+int lora_fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
 
 extern "C" const char *lora_last_error(void) { return g_err.c_str(); }
 
@@ -99,15 +110,41 @@ static bool tb2_form(int form) {
     return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID || form == LORA_FORM_PYRAMID_PRUNED;
 }
 static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
-                         int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base, void *stream);
+                         int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
+                         const double *mirror_base, void *stream);
 
-static std::once_flag g_init_once;
-static cudaError_t g_init_err = cudaSuccess;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current when it runs, and every
+// kernel here needs more than the 48 KB default: the opt-in is done once per DEVICE, not once per process
+constexpr int kMaxDevices = 64;
+static std::mutex g_init_mutex;
+static int g_init_state[kMaxDevices];  // 0 = not yet, 1 = done, 2 = failed
+static cudaError_t g_init_err[kMaxDevices];
 
-static int ensure_init() {
-    std::call_once(g_init_once, [] { g_init_err = kernels_init(); });
-    if (g_init_err != cudaSuccess)
-        return fail(LORA_ERR_CUDA, "kernel attribute setup failed: %s", cudaGetErrorString(g_init_err));
+static int ensure_init(int *device_out = nullptr) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "cudaGetDevice failed: %s", cudaGetErrorString(e));
+    if (dev < 0 || dev >= kMaxDevices) return fail(LORA_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+    if (device_out) *device_out = dev;
+    if (g_init_state[dev] != 1) {
+        std::lock_guard<std::mutex> lk(g_init_mutex);
+        if (g_init_state[dev] == 0) {
+            g_init_err[dev] = kernels_init();
+            g_init_state[dev] = g_init_err[dev] == cudaSuccess ? 1 : 2;
+        }
+        if (g_init_state[dev] != 1)
+            return fail(LORA_ERR_CUDA, "kernel attribute setup failed on device %d: %s", dev, cudaGetErrorString(g_init_err[dev]));
+    }
+    return LORA_OK;
+}
+
+// a plan's tensor maps and task geometry belong to the device it was created on
+static int check_device(const lora_plan *p) {
+    int dev = -1;
+    int rc = ensure_init(&dev);
+    if (rc) return rc;
+    if (dev != p->device)
+        return fail(LORA_ERR_ARG, "plan was created on device %d but device %d is current (cudaSetDevice first)", p->device, dev);
     return LORA_OK;
 }
 
@@ -165,7 +202,7 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         p->form = d.form;
         p->desc = d.desc;
     }
-    cudaGetDevice(&p->device);
+    ensure_init(&p->device);
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device) == cudaSuccess && sms > 0) p->sm_count = sms;
     // task-planning granularity of the 1-D / 2-D kernels, in warp tasks per SM and wave.  12 warps are resident (3 CTAs:
@@ -277,20 +314,77 @@ static long long pick_len(long long total, long long lanes, long long slots, lon
     return max_len;
 }
 
-// mirror_base: nullptr, or the address in a NEIGHBOUR's buffer (peer memory, lora_peer_open) that corresponds to
-// dst[0]: every cell this launch stores at dst[x] is stored at mirror_base[x] too
-static long long mirror_delta(const double *dst, const double *mirror_base) {
-    return mirror_base ? (long long)(mirror_base - dst) : 0;
+// ---------------------------------------------------------------------------------------------
+// segments: how a launch's range is cut when the launch also serves neighbouring slabs (kernels.h: Segs)
+// ---------------------------------------------------------------------------------------------
+struct SegCut {
+    int n = 0;
+    long long lo[kMaxSegs], hi[kMaxSegs], mirror[kMaxSegs];
+    unsigned long long *flag[kMaxSegs], *count[kMaxSegs], *arrived[kMaxSegs];
+    bool band[kMaxSegs];
+    unsigned long long seq = 0;
+    void add(long long a, long long b, long long mir, bool is_band, unsigned long long *f, unsigned long long *c,
+             unsigned long long *arr) {
+        lo[n] = a, hi[n] = b, mirror[n] = mir, band[n] = is_band, flag[n] = f, count[n] = c, arrived[n] = arr;
+        n++;
+    }
+    bool aligned4() const {
+        for (int i = 0; i < n; i++)
+            if (mirror[i] % 4) return false;
+        return true;
+    }
+};
+
+// [lo, hi) -> [lo band][hi band][middle] (bands first: their tasks are dispatched first).  mirror_whole: the
+// older whole-launch form (every cell of the launch is mirrored, no flag).  Coordinates: whatever the caller uses.
+static int cut_segments(long long lo, long long hi, const double *dst, const lora_exchange *ex, const double *mirror_whole,
+                        SegCut &sc) {
+    if (!ex || (ex->band_lo <= 0 && ex->band_hi <= 0)) {
+        sc.add(lo, hi, mirror_whole ? (long long)(mirror_whole - dst) : 0, false, nullptr, nullptr, nullptr);
+        return LORA_OK;
+    }
+    const long long bl = ex->band_lo > 0 ? ex->band_lo : 0, bh = ex->band_hi > 0 ? ex->band_hi : 0;
+    if (bl + bh > hi - lo) return fail(LORA_ERR_ARG, "exchange bands (%lld + %lld) overlap in a range of %lld", bl, bh, hi - lo);
+    if ((bl && !ex->mirror_lo) || (bh && !ex->mirror_hi)) return fail(LORA_ERR_ARG, "exchange band without a mirror address");
+    sc.seq = ex->seq;
+    if (bl) sc.add(lo, lo + bl, (long long)(ex->mirror_lo - dst), true, ex->flag_lo, ex->count_lo, ex->arrived_lo);
+    if (bh) sc.add(hi - bh, hi, (long long)(ex->mirror_hi - dst), true, ex->flag_hi, ex->count_hi, ex->arrived_hi);
+    if (lo + bl < hi - bh) sc.add(lo + bl, hi - bh, 0, false, nullptr, nullptr, nullptr);
+    return LORA_OK;
 }
 
-static int plan_step_impl(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
-                          const double *mirror_base, void *stream) {
+// chunk[] and tasks-per-segment known: fill the kernel's table; band segments with a flag get their arrival target
+static void fill_segs(Segs &sg, const SegCut &sc, const long long *chunk, const long long *tasks, long long arrivals_per_task) {
+    std::memset(&sg, 0, sizeof sg);
+    sg.nseg = sc.n;
+    sg.seq = sc.seq;
+    sg.first[0] = 0;
+    for (int i = 0; i < sc.n; i++) {
+        sg.lo[i] = sc.lo[i];
+        sg.hi[i] = sc.hi[i];
+        sg.chunk[i] = chunk[i];
+        sg.first[i + 1] = sg.first[i] + tasks[i];
+        sg.mirror[i] = sc.mirror[i];
+        if (sc.flag[i] && sc.count[i] && sc.arrived[i]) {
+            *sc.arrived[i] += (unsigned long long)(tasks[i] * arrivals_per_task);
+            sg.flag[i] = sc.flag[i];
+            sg.count[i] = sc.count[i];
+            sg.target[i] = *sc.arrived[i];
+        }
+    }
+}
+
+static int step_unfused(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
+                        const lora_exchange *ex, const double *mirror_base, void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if (lo == hi) return LORA_OK;
+    if (int rc = check_device(p)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (p->dim == 1) {
+        if (ex && (ex->band_lo > 0 || ex->band_hi > 0))
+            return fail(LORA_ERR_UNSUPPORTED, "1-D slab launches go through the temporally blocked kernel (tb >= 1)");
         if (lo % 2) return fail(LORA_ERR_ARG, "1-D range must start at an even index");
         if (reinterpret_cast<uintptr_t>(src) % 16 || reinterpret_cast<uintptr_t>(dst) % 16)
             return fail(LORA_ERR_ARG, "buffers must be 16-byte aligned");
@@ -311,42 +405,53 @@ static int plan_step_impl(lora_plan_t *p, const double *src, double *dst, long l
         g.rows_per_task = (int)pick_len(rows, 1, p->slots, max_rows1, max_rows1 < 16 ? max_rows1 : 16);
         g.ntasks = (rows + g.rows_per_task - 1) / g.rows_per_task;
         g.vec4 = (lo % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
-        g.mirror = mirror_delta(dst, mirror_base);
+        g.mirror = mirror_base ? (long long)(mirror_base - dst) : 0;
         e = launch_1d(g, p->w1, st);
     } else if (p->dim == 2) {
         const CUtensorMap *tm;
         int rc = get_tmap(p, src, &tm);
         if (rc) return rc;
+        SegCut sc;
+        if ((rc = cut_segments(lo, hi, dst, ex, mirror_base, sc))) return rc;
         Geom2D g;
         g.out = dst;
         g.pitch = p->padded[1];
         g.m = (int)p->dims[0];
         g.n = (int)p->dims[1];
-        g.row_lo = (int)lo;
-        g.row_hi = (int)hi;
         g.nstrips = (g.n + kWarpCols - 1) / kWarpCols;
-        // Chunk length: about 8 tasks per resident warp, between 64 and 256 rows (6 warm-up rows per chunk).  Many
-        // short tasks beat whole waves of long ones here: CTAs are dispatched in task order, so the warps that are
-        // resident at any moment work on a few neighbouring row bands (DRAM page and L2 locality) and the tail of
-        // the launch is short.  Measured, box2d 10240^2: 337 (256 rows) / 367 (96) / 376 (64) / 357 (32) GStencil/s;
-        // 40960^2: 397 at 96..256 rows (profiles/r1_chunk_rows_2d.log).
-        long long want = (hi - lo) * g.nstrips / (8 * (long long)p->slots);
-        want = want < 64 ? 64 : (want > 256 ? 256 : want);
-        if (const char *e = getenv("LORA_MAX_ROWS_2D")) {  // tuning knob
-            const long long v = atoll(e);
-            if (v >= 8 && v <= 4096) want = v;
+        long long chunk[kMaxSegs], tasks[kMaxSegs];
+        for (int i = 0; i < sc.n; i++) {
+            const long long rows = sc.hi[i] - sc.lo[i];
+            if (sc.band[i]) {  // a band is a handful of rows: one chunk per strip
+                chunk[i] = rows;
+                tasks[i] = g.nstrips;
+                continue;
+            }
+            // Chunk length: about 8 tasks per resident warp, between 64 and 256 rows (6 warm-up rows per chunk).  Many
+            // short tasks beat whole waves of long ones here: CTAs are dispatched in task order, so the warps that are
+            // resident at any moment work on a few neighbouring row bands (DRAM page and L2 locality) and the tail of
+            // the launch is short.  Measured, box2d 10240^2: 337 (256 rows) / 367 (96) / 376 (64) / 357 (32) GStencil/s;
+            // 40960^2: 397 at 96..256 rows (profiles/r1_chunk_rows_2d.log).
+            long long want = rows * g.nstrips / (8 * (long long)p->slots);
+            want = want < 64 ? 64 : (want > 256 ? 256 : want);
+            if (const char *e = getenv("LORA_MAX_ROWS_2D")) {  // tuning knob
+                const long long v = atoll(e);
+                if (v >= 8 && v <= 4096) want = v;
+            }
+            const long long nch = (rows + want - 1) / want;
+            chunk[i] = (rows + nch - 1) / nch;
+            tasks[i] = ((rows + chunk[i] - 1) / chunk[i]) * g.nstrips;
         }
-        const long long nch = (hi - lo + want - 1) / want;
-        g.rows_per_chunk = (int)((hi - lo + nch - 1) / nch);
-        const int chunks = (int)((hi - lo + g.rows_per_chunk - 1) / g.rows_per_chunk);
-        g.ntasks = chunks * g.nstrips;
-        g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
-        g.mirror = mirror_delta(dst, mirror_base);
+        fill_segs(g.sg, sc, chunk, tasks, 1);
+        g.ntasks = (int)g.sg.first[sc.n];
+        g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0) && sc.aligned4();
         e = launch_2d(p->form, *tm, g, p->w2, p->wd, st);
     } else {
         const CUtensorMap *tm;
         int rc = get_tmap(p, src, &tm);
         if (rc) return rc;
+        SegCut sc;
+        if ((rc = cut_segments(lo, hi, dst, ex, mirror_base, sc))) return rc;
         Geom3D g;
         g.out = dst;
         g.row_pitch = p->padded[2];
@@ -354,8 +459,6 @@ static int plan_step_impl(lora_plan_t *p, const double *src, double *dst, long l
         g.h = (int)p->dims[0];
         g.m = (int)p->dims[1];
         g.n = (int)p->dims[2];
-        g.h_lo = (int)lo;
-        g.h_hi = (int)hi;
         g.tiles_m = (g.m + k3TileRows - 1) / k3TileRows;
         g.tiles_n = (g.n + k3TileCols - 1) / k3TileCols;
         long long max_planes = 64;
@@ -363,14 +466,25 @@ static int plan_step_impl(lora_plan_t *p, const double *src, double *dst, long l
             const long long v = atoll(e);
             if (v >= 2 && v <= 4096) max_planes = v;
         }
-        g.planes_per_chunk = (int)pick_len(hi - lo, (long long)g.tiles_m * g.tiles_n, p->slots, max_planes, max_planes < 8 ? max_planes : 8);
-        g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
-        g.mirror = mirror_delta(dst, mirror_base);
+        long long chunk[kMaxSegs], tasks[kMaxSegs];
+        for (int i = 0; i < sc.n; i++) {
+            const long long planes = sc.hi[i] - sc.lo[i];
+            chunk[i] = sc.band[i] ? planes
+                                  : pick_len(planes, (long long)g.tiles_m * g.tiles_n, p->slots, max_planes, max_planes < 8 ? max_planes : 8);
+            tasks[i] = (planes + chunk[i] - 1) / chunk[i];  // plane chunks (blockIdx.y); every chunk is tiles_m x tiles_n CTAs
+        }
+        fill_segs(g.sg, sc, chunk, tasks, (long long)g.tiles_m * g.tiles_n);
+        g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0) && sc.aligned4();
         e = launch_3d(p->form, *tm, g, p->w3, st);
     }
     if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     p->launches++;
     return LORA_OK;
+}
+
+static int plan_step_impl(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
+                          const double *mirror_base, void *stream) {
+    return step_unfused(p, src, dst, lo, hi, nullptr, mirror_base, stream);
 }
 
 extern "C" int lora_plan_step(lora_plan_t *p, const double *src, double *dst, long long lo, long long hi,
@@ -444,32 +558,48 @@ static void plan_tasks_2dtb(Geom2DTB &g, long long rows, long long slots) {
 
 // 2-D fused launch of kTb2 time steps over interior rows [lo, hi): see stencil2d_tb.cu
 static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
-                         int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base, void *stream) {
+                         int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
+                         const double *mirror_base, void *stream) {
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
-    if (tb == 1) return plan_step_impl(p, src, dst, lo, hi, mirror_base, stream);
+    if (tb == 1) return step_unfused(p, src, dst, lo, hi, ex, mirror_base, stream);
     if (tb != kTb2 || !tb2_form(p->form))
         return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid)", kTb2);
     if (!halo_src) return fail(LORA_ERR_ARG, "fused 2-D launches need halo_src (the buffer holding the caller's halo)");
     if (lo == hi) return LORA_OK;
+    if (int rc = check_device(p)) return rc;
     const CUtensorMap *tm;
     int rc = get_tmap(p, src, &tm);
     if (rc) return rc;
+    SegCut sc;
+    if ((rc = cut_segments(lo, hi, dst, ex, mirror_base, sc))) return rc;
     Geom2DTB g{};
     g.out = dst;
     g.halo_src = halo_src;
     g.pitch = p->padded[1];
     g.m = (int)p->dims[0];
     g.n = (int)p->dims[1];
-    g.row_lo = (int)lo;
-    g.row_hi = (int)hi;
     const int wout = strip_out_cols_2d_tb(tb);
     g.nstrips = (g.n + wout - 1) / wout;
-    plan_tasks_2dtb(g, hi - lo, (long long)p->sm_count * 2 * kWarpsPerCta);
+    long long chunk[kMaxSegs], tasks[kMaxSegs];
+    for (int i = 0; i < sc.n; i++) {
+        const long long rows = sc.hi[i] - sc.lo[i];
+        if (i == sc.n - 1) {  // the main segment (the only one of a plain launch): the planner of plan_tasks_2dtb
+            g.row_lo = (int)sc.lo[i];
+            g.row_hi = (int)sc.hi[i];
+            plan_tasks_2dtb(g, rows, (long long)p->sm_count * 2 * kWarpsPerCta);
+            chunk[i] = g.rows_per_chunk;
+            tasks[i] = g.ntasks;
+        } else {  // a band: short tasks, every strip
+            chunk[i] = rows < kEdgeRows2Tb ? rows : kEdgeRows2Tb;
+            tasks[i] = ((rows + chunk[i] - 1) / chunk[i]) * g.nstrips;
+        }
+    }
+    fill_segs(g.sg, sc, chunk, tasks, 1);
+    g.ntasks = (int)g.sg.first[sc.n];
     g.par0 = launches_before & 1;
     g.virt_top = virt_lo ? 1 : 0;
     g.virt_bot = virt_hi ? 1 : 0;
-    g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
-    g.mirror = mirror_delta(dst, mirror_base);
+    g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0) && sc.aligned4();
     cudaError_t e = launch_2d_tb(p->form, tb, *tm, g, p->w2, p->wd, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     p->launches++;
@@ -479,52 +609,69 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
 extern "C" int lora_plan_temporal_block(const lora_plan_t *p) { return p ? p->max_tb : 0; }
 
 static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const double *halo_src, long long lo,
-                           long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base,
-                           void *stream);
+                           long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
+                           const double *mirror_base, void *stream);
 
 extern "C" int lora_plan_step_fused(lora_plan_t *p, const double *src, double *dst, const double *halo_src,
                                     long long lo, long long hi, int tb, int launches_before, int virt_lo, int virt_hi,
                                     void *stream) {
-    return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, nullptr, stream);
+    return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, nullptr, nullptr, stream);
 }
 
 extern "C" int lora_plan_step_fused_mirror(lora_plan_t *p, const double *src, double *dst, const double *halo_src,
                                            long long lo, long long hi, int tb, int launches_before, int virt_lo,
                                            int virt_hi, const double *mirror_base, void *stream) {
-    return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, mirror_base, stream);
+    return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, nullptr, mirror_base, stream);
+}
+
+int lora_plan_step_exchange(lora_plan_t *p, const double *src, double *dst, const double *halo_src, long long lo,
+                            long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
+                            void *stream) {
+    if (p && p->dim == 3) {
+        if (tb != 1) return fail(LORA_ERR_UNSUPPORTED, "3-D launches advance one time step");
+        return step_unfused(p, src, dst, lo, hi, ex, nullptr, stream);
+    }
+    return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, ex, nullptr, stream);
 }
 
 static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const double *halo_src, long long lo,
-                           long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const double *mirror_base,
-                           void *stream) {
+                           long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
+                           const double *mirror_base, void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
     if (p->dim == 2)
-        return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, mirror_base, stream);
+        return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, ex, mirror_base, stream);
     if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D and 2-D shapes");
     if (tb < 1 || tb > kMaxTb1) return fail(LORA_ERR_ARG, "temporal block must be 1..%d", kMaxTb1);
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if ((virt_lo || virt_hi) && !halo_src) return fail(LORA_ERR_ARG, "virtual halo needs halo_src");
     if (lo == hi) return LORA_OK;
+    if (int rc = check_device(p)) return rc;
     if (reinterpret_cast<uintptr_t>(src) % 16 || reinterpret_cast<uintptr_t>(dst) % 16)
         return fail(LORA_ERR_ARG, "buffers must be 16-byte aligned");
     const long long P = p->dims[0] + 8;  // padded length
+    SegCut sc;
+    if (int rc = cut_segments(4 + lo, 4 + hi, dst, ex, mirror_base, sc)) return rc;  // padded coordinates X
     Geom1DTB g{};
     g.in = src;
     g.out = dst;
     g.halo_src = halo_src ? halo_src : src;
     g.n = p->dims[0];
-    g.xlo = 4 + lo;
-    g.xhi = 4 + hi;
-    // output row r (level tb) covers padded cells [512 r - 4 tb, 512 r - 4 tb + 512)
-    g.rho0 = (g.xlo + 4 * tb) / kTbRowCells;
-    g.nrows = (g.xhi - 1 + 4 * tb) / kTbRowCells - g.rho0 + 1;
     long long max_rows = 128;  // rows per task: whole waves of the longest tasks below this (1 warm-up row each)
     if (const char *e = getenv("LORA_TB1_MAX_ROWS")) {  // tuning knob
         const long long v = atoll(e);
         if (v >= 8 && v <= 4096) max_rows = v;
     }
-    g.rows_per_task = (int)pick_len(g.nrows, 1, (long long)p->sm_count * kTbCtasPerSm * kWarpsPerCta, max_rows, 8);
-    g.ntasks = (g.nrows + g.rows_per_task - 1) / g.rows_per_task;
+    long long chunk[kMaxSegs], tasks[kMaxSegs];
+    for (int i = 0; i < sc.n; i++) {
+        // output row r (level tb) covers padded cells [512 r - 4 tb, 512 r - 4 tb + 512)
+        const long long rho0 = (sc.lo[i] + 4 * tb) / kTbRowCells;
+        const long long nrows = (sc.hi[i] - 1 + 4 * tb) / kTbRowCells - rho0 + 1;
+        chunk[i] = sc.band[i] ? nrows  // a band is one or two rows: one task
+                              : pick_len(nrows, 1, (long long)p->sm_count * kTbCtasPerSm * kWarpsPerCta, max_rows, 8);
+        tasks[i] = (nrows + chunk[i] - 1) / chunk[i];
+    }
+    fill_segs(g.sg, sc, chunk, tasks, 1);
+    g.ntasks = g.sg.first[sc.n];
     g.tb = tb;
     g.par0 = launches_before & 1;
     g.virt_left = virt_lo ? 1 : 0;
@@ -534,7 +681,6 @@ static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const
     g.use_tma = (in_rows >= 1 && out_rows >= 1) ? 1 : 0;
     g.xcov = g.use_tma ? in_rows * 16 : 0;
     g.out_rows = out_rows;
-    g.mirror = mirror_delta(dst, mirror_base);
     CUtensorMap imap, omap;
     std::memset(&imap, 0, sizeof imap);
     std::memset(&omap, 0, sizeof omap);
@@ -597,7 +743,7 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
         int k = 0;
         for (int left = times; left > 0; k++) {
             const int tb = left >= kTb2 ? kTb2 : 1;
-            int rc = step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tb, times - left, 1, 1, nullptr, stream);
+            int rc = step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], tb, times - left, 1, 1, nullptr, nullptr, stream);
             if (rc) return rc;
             left -= tb;
         }
@@ -629,9 +775,15 @@ extern "C" int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count,
     const int wout = strip_out_cols_2d_tb(kTb2);
     g.nstrips = (n + wout - 1) / wout;
     plan_tasks_2dtb(g, hi - lo, (long long)sm_count * 2 * kWarpsPerCta);
+    g.sg.nseg = 1;
+    g.sg.lo[0] = lo;
+    g.sg.hi[0] = hi;
+    g.sg.chunk[0] = g.rows_per_chunk;
+    g.sg.first[0] = 0;
+    g.sg.first[1] = g.ntasks;
     for (int t = 0; t < g.ntasks && t < cap; t++) {
-        int strip = -1, r0 = 0, R = 0;
-        if (!decode_task_2dtb(g, t, strip, r0, R)) R = 0;
+        int strip = -1, r0 = 0, R = 0, seg = 0;
+        if (!decode_task_2dtb(g, t, strip, r0, R, seg)) R = 0;
         out3[3 * t] = strip;
         out3[3 * t + 1] = r0;
         out3[3 * t + 2] = R;
@@ -766,7 +918,10 @@ extern "C" void lora_release_workspace(void) {
 static void ws_reserve(size_t count, size_t bytes) {
     int dev = 0;
     CU_DIE(cudaGetDevice(&dev));
-    if (g_ws_device != dev || g_ws_bytes < bytes) ws_free_locked();
+    // start over on another device, when the cached buffers are too small, and when they are far larger than this
+    // call needs while more of them are wanted (a 13 GB 2-D workspace must not be multiplied by a chunked 1-D call)
+    if (g_ws_device != dev || g_ws_bytes < bytes || (g_ws.size() < count && g_ws_bytes > 2 * bytes + (64u << 20)))
+        ws_free_locked();
     if (g_ws.empty()) {
         g_ws_bytes = bytes + bytes / 8;  // slack: a slightly larger follow-up call does not reallocate everything
         g_ws_device = dev;
@@ -915,11 +1070,87 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
     return true;
 }
 
+// how many GPUs the drop-in operators spread one call over: LORA_NGPU=k (default 1), or lora_set_gpus(k)
+static int g_ngpu = -1;
+extern "C" int lora_set_gpus(int k) {
+    const int prev = g_ngpu;
+    g_ngpu = k;
+    return prev < 0 ? 1 : prev;
+}
+// LORA_DEVICES="0,1,2,3": an explicit device list for the slabs (a device may appear more than once: several slabs
+// then share it, which is how a single-GPU box exercises the whole exchange protocol); otherwise devices 0..k-1
+static int wanted_gpus(std::vector<int> &devices) {
+    devices.clear();
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) return 1;
+    if (const char *e = getenv("LORA_DEVICES")) {
+        if (g_ngpu < 0 || g_ngpu > 1) {
+            for (const char *q = e; *q;) {
+                char *end = nullptr;
+                const long v = strtol(q, &end, 10);
+                if (end == q) break;
+                if (v >= 0 && v < have) devices.push_back((int)v);
+                q = (*end == ',') ? end + 1 : end;
+                if (*end != ',' ) break;
+            }
+            if (devices.size() > 1) return (int)devices.size();
+            devices.clear();
+        }
+    }
+    int k = g_ngpu;
+    if (k < 0) {
+        const char *e = getenv("LORA_NGPU");
+        k = e ? atoi(e) : 1;
+    }
+    if (k <= 1) return 1;
+    k = k < have ? k : have;
+    for (int i = 0; i < k; i++) devices.push_back(i);
+    return k;
+}
+static int g_last_gpus = 1;
+extern "C" int lora_last_gpus(void) { return g_last_gpus; }
+
+// The drop-in operator on k GPUs of this process (LORA_NGPU=k): the padded host grid is cut into k slabs along its
+// outermost axis (slab.cu), every device takes its rows (+ ghost rows) H2D, the launch loop runs on all devices with
+// the ghost zones exchanged inside the kernels over NVLink peer memory, and the slabs come back into `out`.  Same
+// buffer semantics (S2 / S3), same banner, same timed region (launch loop + sync) as the single-GPU path; results
+// are bit-identical to it.  Returns false when the grid is too thin to be cut that many ways (the caller then runs
+// on one GPU).
+static bool run_host_multi_gpu(const std::vector<int> &devices, int shape, int mode, const double *in, double *out,
+                               const double *params, int times, const long long *dims) {
+    using clk = std::chrono::steady_clock;
+    const int k = (int)devices.size();
+    lora_slabset_t *set = nullptr;
+    if (lora_slabset_create(&set, shape, mode, params, dims, k, devices.data()) != LORA_OK) {
+        if (verbose()) fprintf(stderr, "LoRAStencil: %d GPUs not usable for this call (%s); running on one\n", k, lora_last_error());
+        return false;
+    }
+    if (lora_slabset_load(set, in) != LORA_OK) die_plan("multi-GPU H2D");
+    const clk::time_point t0 = clk::now();
+    if (lora_slabset_run(set, times) != LORA_OK) die_plan("multi-GPU launch");
+    if (lora_slabset_sync(set) != LORA_OK) die_plan("multi-GPU sync");
+    const long long us = std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t0).count();
+    g_loop_ms = us / 1e3;
+    if (verbose()) print_banner(shape, shape_dim(shape), dims, times, (double)us);
+    if (lora_slabset_store(set, out) != LORA_OK) die_plan("multi-GPU D2H");
+    lora_slabset_destroy(set);
+    g_last_gpus = k;
+    return true;
+}
+
 extern "C" void lora_gpu_run_host(int shape, int mode, const double *in, double *out, const double *params, int times,
                                   const long long *dims) {
     using clk = std::chrono::steady_clock;
     const clk::time_point t_begin = clk::now();
     g_chunks = 1;
+    g_last_gpus = 1;
+    std::vector<int> devices;
+    const int k = wanted_gpus(devices);
+    if (k > 1 && shape_dim(shape) != 0 && dims && in && out && times >= 0 &&
+        run_host_multi_gpu(devices, shape, mode, in, out, params, times, dims)) {
+        g_total_ms = std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t_begin).count() / 1e3;
+        return;
+    }
     if (shape_dim(shape) == 1 && dims && dims[0] > 0 && in && out &&
         run_host_1d_chunked(shape, mode, in, out, params, times, dims[0])) {
         if (verbose()) print_banner(shape, 1, dims, times, g_loop_ms * 1e3);

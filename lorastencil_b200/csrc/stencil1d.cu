@@ -98,6 +98,7 @@ k_stencil1d(const __grid_constant__ Geom1D g, const __grid_constant__ Weights1D 
         if (rr == kStageRows1 - 1 || r == nrows - 1) {
             __syncwarp();
             if (lane == 0 && st + kStages < nst) issue(st + kStages, slot);
+            __syncwarp();  // lane 0's plain store of an odd tail element is ordered before the other lanes' reads
         }
     }
 }

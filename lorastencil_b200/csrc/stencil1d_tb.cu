@@ -131,8 +131,13 @@ k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__
     double *mailbox = reinterpret_cast<double *>(wsm + kTbRing + kTbOut);      // [level][row parity][8]
     uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + kTbRing + kTbOut + kTbMail);
 
-    const long long rfirst = g.rho0 + task * (long long)g.rows_per_task;       // first output row of the task
-    const int J = (int)min((long long)g.rows_per_task, g.rho0 + g.nrows - rfirst);
+    // segment of this task (band segments first), the cells it may write, its output rows
+    const int seg = seg_of(g.sg, task);
+    const long long xlo = g.sg.lo[seg], xhi = g.sg.hi[seg], mirror = g.sg.mirror[seg];
+    const long long rho0 = (xlo + 4 * TB) / kTbRowCells;
+    const long long nrows = (xhi - 1 + 4 * TB) / kTbRowCells - rho0 + 1;
+    const long long rfirst = rho0 + (task - g.sg.first[seg]) * g.sg.chunk[seg];  // first output row of the task
+    const int J = (int)min(g.sg.chunk[seg], rho0 + nrows - rfirst);
     const int niter = J + 1;  // iteration 0 is the warm-up row rfirst - 1: it only fills the mailboxes
 
     auto issue = [&](int k, int slot) {
@@ -173,7 +178,7 @@ k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__
         if (i >= 1) {
             const long long Xr = X0 - 4 * TB;  // first cell of the output row (level TB)
             const long long rc = (Xr - g.out_off) >> 4;  // row of 16 in the store map (exact when Xr >= out_off)
-            if (g.use_tma && g.mirror == 0 && Xr >= g.xlo && Xr + kRow <= g.xhi && Xr >= g.out_off && rc + 32 <= g.out_rows) {
+            if (g.use_tma && mirror == 0 && Xr >= xlo && Xr + kRow <= xhi && Xr >= g.out_off && rc + 32 <= g.out_rows) {
                 // whole row: stage it (conflict-free STS) and let the TMA write the 4 KB line segment
                 unsigned char *stage = outbuf + (i % kTbOutBufs) * (kRow * 8);
                 if (lane == 0) tma_store_wait_read<kTbOutBufs - 1>();  // the last store issued from this staging row has drained
@@ -193,14 +198,20 @@ k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__
                 const long long x = Xr + kCpl * lane;
 #pragma unroll
                 for (int q = 0; q < kCpl; q++)
-                    if (x + q >= g.xlo && x + q < g.xhi) {
+                    if (x + q >= xlo && x + q < xhi) {
                         g.out[x + q] = cur[q];
-                        if (g.mirror != 0) g.out[x + q + g.mirror] = cur[q];  // neighbour slab's ghost zone (peer memory)
+                        if (mirror != 0) g.out[x + q + mirror] = cur[q];  // neighbour slab's ghost zone (peer memory)
                     }
             }
         }
     }
     if (lane == 0) tma_store_wait_all();  // shared memory must outlive the last TMA stores
+    const int seg_done = seg_of(g.sg, task);  // recomputed: not kept live across the sweep
+    if (g.sg.flag[seg_done] != nullptr) {  // a band task: tell the neighbour once every task of the band has stored
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) seg_arrive(g.sg, seg_done);
+    }
 }
 
 }  // namespace

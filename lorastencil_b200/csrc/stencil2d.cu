@@ -69,10 +69,20 @@ __device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4
             for (int q = 0; q < 4; q++)
                 if (q < s.ncols_left) s.orow[q] = done[q];
         }
-        if (s.mirror != 0) {  // the same row into the neighbour slab's halo rows (peer memory)
+        if (s.mirror != 0) {  // the same row into the neighbour slab's ghost rows (peer memory over NVLink)
+            double *om = s.orow + s.mirror;
+            if (s.ncols_left >= 4) {
+                if (s.vec4) {
+                    st_global_v4(om, done[0], done[1], done[2], done[3]);
+                } else {
+                    st_global_v2(om, done[0], done[1]);
+                    st_global_v2(om + 2, done[2], done[3]);
+                }
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (q < s.ncols_left) s.orow[s.mirror + q] = done[q];
+                for (int q = 0; q < 4; q++)
+                    if (q < s.ncols_left) om[q] = done[q];
+            }
         }
         s.orow += s.pitch;
     }
@@ -98,9 +108,11 @@ k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     const int task = blockIdx.x * kWarpsPerCta + warp;
     if (task >= g.ntasks) return;  // warps never synchronise with each other
 
-    const int strip = task % g.nstrips, chunk = task / g.nstrips;
-    const int r0 = g.row_lo + chunk * g.rows_per_chunk;  // first interior row of this chunk
-    const int R = min(g.rows_per_chunk, g.row_hi - r0);
+    const int seg = seg_of(g.sg, task);  // band segments come first, i.e. are dispatched first
+    const int tt = task - (int)g.sg.first[seg];
+    const int strip = tt % g.nstrips, chunk = tt / g.nstrips;
+    const int r0 = (int)g.sg.lo[seg] + chunk * (int)g.sg.chunk[seg];  // first interior row of this chunk
+    const int R = min((int)g.sg.chunk[seg], (int)g.sg.hi[seg] - r0);
     const int c0 = strip * kWarpCols + 4 * lane;         // first interior column of this lane
 
     Sweep2D s;
@@ -115,7 +127,7 @@ k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     s.ncols_left = g.n - c0;
     s.vec4 = g.vec4 != 0;
     s.pitch = g.pitch;
-    s.mirror = g.mirror;
+    s.mirror = g.sg.mirror[seg];
     s.orow = g.out + (long long)(r0 + 4) * g.pitch + 4 + c0;
 
     if (lane == 0) {
@@ -145,6 +157,12 @@ k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
         if (base + 4 < s.nin) row_phase<FORM, 4>(base + 4, s, A, w, wd);
         if (base + 5 < s.nin) row_phase<FORM, 5>(base + 5, s, A, w, wd);
         if (base + 6 < s.nin) row_phase<FORM, 6>(base + 6, s, A, w, wd);
+    }
+    const int seg_done = seg_of(g.sg, task);  // recomputed: not kept live across the sweep
+    if (g.sg.flag[seg_done] != nullptr) {  // a band task: tell the neighbour once every task of the band has stored
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) seg_arrive(g.sg, seg_done);
     }
 }
 

@@ -158,10 +158,20 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
                 for (int q = 0; q < 4; q++)
                     if (q < left) s.orow[q] = v[q];
             }
-            if (s.mirror != 0) {  // the same row into the neighbour slab's ghost rows (peer memory)
+            if (s.mirror != 0) {  // the same row into the neighbour slab's ghost rows (peer memory over NVLink)
+                double *om = s.orow + s.mirror;
+                if (left >= 4) {
+                    if (s.vec4) {
+                        st_global_v4(om, v[0], v[1], v[2], v[3]);
+                    } else {
+                        st_global_v2(om, v[0], v[1]);
+                        st_global_v2(om + 2, v[2], v[3]);
+                    }
+                } else {
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (q < left) s.orow[s.mirror + q] = v[q];
+                    for (int q = 0; q < 4; q++)
+                        if (q < left) om[q] = v[q];
+                }
             }
         }
         s.orow += s.pitch;
@@ -215,8 +225,8 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     if (task >= g.ntasks) return;  // warps never synchronise with each other
 
     constexpr int kStripOut = kWarpCols - 8 * (TB - 1);  // columns a strip writes
-    int strip, r0, R;
-    if (!decode_task_2dtb(g, task, strip, r0, R)) return;  // task order and lengths: kernels.h
+    int strip, r0, R, seg;
+    if (!decode_task_2dtb(g, task, strip, r0, R, seg)) return;  // task order and lengths: kernels.h
     const int cs = strip * kStripOut;                    // first interior column the strip writes
     const int cw = cs - 4 * (TB - 1);                    // first interior column the warp computes
 
@@ -243,7 +253,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.par0 = g.par0 & 1;
     s.vec4 = g.vec4 != 0;
     s.pitch = g.pitch;
-    s.mirror = g.mirror;
+    s.mirror = g.sg.mirror[seg];
     s.orow = g.out + (long long)(r0 + 4) * g.pitch + 4 + s.c0;
     s.hsrc = g.halo_src + 4 * g.pitch + 4 + s.c0;
     double *hal = reinterpret_cast<double *>(smem_raw + kSmem12) + warp * (kHalRows2Tb * 8);
@@ -276,6 +286,12 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     __syncwarp();
 
     sweep_rows<FORM, TB>(s, w, wd);
+    const int seg_done = seg_of(g.sg, blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5));  // recomputed: not kept live
+    if (g.sg.flag[seg_done] != nullptr) {  // a band task: tell the neighbour once every task of the band has stored
+        __threadfence_system();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) seg_arrive(g.sg, seg_done);
+    }
 }
 
 template <int FORM, int TB>

@@ -157,10 +157,20 @@ __device__ __forceinline__ void plane_phase(int i, Sweep3D &s, double (&A)[3][4]
                     for (int q = 0; q < 4; q++)
                         if (q < s.cols_left) o[q] = done[r][q];
                 }
-                if (s.mirror != 0) {  // the same row into the neighbour slab's halo plane (peer memory)
+                if (s.mirror != 0) {  // the same row into the neighbour slab's ghost plane (peer memory over NVLink)
+                    double *om = o + s.mirror;
+                    if (s.cols_left >= 4) {
+                        if (s.vec4) {
+                            st_global_v4(om, done[r][0], done[r][1], done[r][2], done[r][3]);
+                        } else {
+                            st_global_v2(om, done[r][0], done[r][1]);
+                            st_global_v2(om + 2, done[r][2], done[r][3]);
+                        }
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        if (q < s.cols_left) o[s.mirror + q] = done[r][q];
+                        for (int q = 0; q < 4; q++)
+                            if (q < s.cols_left) om[q] = done[r][q];
+                    }
                 }
             }
         }
@@ -182,8 +192,9 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int tile_n = blockIdx.x % g.tiles_n, tile_m = blockIdx.x / g.tiles_n;
-    const int h0 = g.h_lo + blockIdx.y * g.planes_per_chunk;  // first interior plane of the chunk
-    const int H = min(g.planes_per_chunk, g.h_hi - h0);
+    const int seg = seg_of(g.sg, blockIdx.y);  // band segments come first in blockIdx.y, i.e. in dispatch order
+    const int h0 = (int)(g.sg.lo[seg] + (blockIdx.y - g.sg.first[seg]) * g.sg.chunk[seg]);  // first interior plane of the chunk
+    const int H = (int)min(g.sg.chunk[seg], g.sg.hi[seg] - h0);
     const int nin = H + 2;                                    // input planes h0-1 .. h0+H == padded h0 ..
     const int r_tile = tile_m * k3TileRows, c_tile = tile_n * k3TileCols;
 
@@ -221,7 +232,7 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     s.vec4 = g.vec4 != 0;
     s.row_pitch = g.row_pitch;
     s.plane_pitch = g.plane_pitch;
-    s.mirror = g.mirror;
+    s.mirror = g.sg.mirror[seg];
     s.optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(r0 + 2) * g.row_pitch + 4 + c0;
 
     double A[3][4][4];
@@ -237,13 +248,17 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
         if (base + 1 < nin) plane_phase<FORM, 1>(base + 1, s, A, w);
         if (base + 2 < nin) plane_phase<FORM, 2>(base + 2, s, A, w);
     }
+    if (g.sg.flag[seg] != nullptr) {  // a band chunk: tell the neighbour once every CTA of the band has stored
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) seg_arrive(g.sg, seg);
+    }
 }
 
 template <int FORM>
 cudaError_t launch_form(const CUtensorMap &tmap, const Geom3D &g, const Weights3D &w, cudaStream_t st) {
-    const int planes = g.h_hi - g.h_lo;
-    if (planes <= 0) return cudaSuccess;
-    const int chunks = (planes + g.planes_per_chunk - 1) / g.planes_per_chunk;
+    const int chunks = (int)g.sg.first[g.sg.nseg];
+    if (chunks <= 0) return cudaSuccess;
     dim3 grid(g.tiles_m * g.tiles_n, chunks);
     k_stencil3d<FORM><<<grid, k3Threads, k3Smem, st>>>(tmap, g, w);
     return cudaGetLastError();

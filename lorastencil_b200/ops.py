@@ -109,3 +109,14 @@ def last_total_ms() -> float:
 def last_chunks() -> int:
     """Chunks the last 1-D drop-in call was cut into to overlap its copies with its launches (1 = none)."""
     return int(_lib.lib().lora_last_chunks())
+
+
+def set_gpus(k: int) -> int:
+    """Spread every following drop-in call over k GPUs of this process (slabs along the outermost axis, ghost zones
+    exchanged inside the kernels over NVLink); same as the environment variable LORA_NGPU.  Returns the previous value."""
+    return int(_lib.lib().lora_set_gpus(int(k)))
+
+
+def last_gpus() -> int:
+    """GPUs (slabs) the last drop-in call actually ran on."""
+    return int(_lib.lib().lora_last_gpus())

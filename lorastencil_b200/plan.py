@@ -68,9 +68,21 @@ class Plan:
         _lib.check(_lib.lib().lora_plan_create(byref(self._h), _lib.SHAPE_IDS[shape], int(mode),
                                                None if p is None else _dp(p), d), "lora_plan_create")
 
+    @classmethod
+    def borrowed(cls, handle, shape: str, dims):
+        """A view of a plan that something else owns (a native slab's plan): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.shape = shape
+        self.dims = tuple(int(d) for d in dims)
+        self.dim = len(self.dims)
+        self.padded_shape = tuple(d + 2 * h for d, h in zip(self.dims, HALO[self.dim]))
+        self._h = c_void_p(handle)
+        self._borrowed = True
+        return self
+
     def __del__(self):
         try:
-            if self._h:
+            if self._h and not getattr(self, "_borrowed", False):
                 _lib.lib().lora_plan_destroy(self._h)
                 self._h = c_void_p()
         except Exception:

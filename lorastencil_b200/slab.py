@@ -9,10 +9,11 @@ two ping-pong buffers for its slab, padded with the reference's storage halo (4 
 Per sweep i (src = buf[i%2], dst = buf[(i+1)%2]) a rank
   1. computes its two edge bands (the first and last ghost-width interior rows of dst) on the comm stream,
   2. gets those bands into the neighbours' ghost rows of dst:
-       "p2p"  (default on GPUs): the edge-band kernel itself stores every row a second time, into the neighbour's
-              buffer mapped over NVLink (CUDA IPC; `mirror` argument of lora_plan_step_mirror), then bumps a 64-bit
-              flag in the neighbour's memory in stream order; the neighbour's next edge-band launch waits for it
-              (PeerHalo, csrc/peer.cu).  No communication library on the data path;
+       "p2p"  (default on GPUs): the whole sweep is ONE kernel launch inside the library (NativeSlab, csrc/slab.cu):
+              its band tasks run first and store every cell a second time into the neighbour's buffer mapped over
+              NVLink (CUDA IPC), the last band task raises a 64-bit flag in the neighbour's memory, the interior
+              overlaps all that, and the next sweep's launch waits for the flags in stream order.  No communication
+              library on the data path, no Python per sweep;
        "nccl" (LORA_HALO=nccl, and the CPU tests with gloo): send/recv of the bands (torch.distributed P2P),
   3. computes the rest of the interior on the main stream -- it reads the rank's own rows only and never waits
      for a neighbour,
@@ -106,96 +107,76 @@ class _DevMem:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-class PeerHalo:
-    """Halo exchange without a communication library: the ping-pong buffers and two 64-bit flags of every rank
-    live in CUDA-IPC memory that both neighbours map (NVLink peer access).  A rank's edge-band launch stores its
-    rows straight into the neighbour's ghost rows (`mirror`), then bumps the neighbour's flag in stream order; the
-    neighbour's next edge-band launch waits for the flag in its own stream.  Interior launches never wait."""
+class NativeSlab:
+    """This rank's slab inside the library (csrc/slab.cu, lora_slab_*): buffers, flags, ghost-zone geometry and the
+    sweep loop are native; Python only carries the three CUDA-IPC handles to the neighbours (torch.distributed
+    all_gather_object) and calls lora_slab_run.  One kernel launch per sweep: band tasks first, their cells stored a
+    second time into the neighbour's ghost zone over NVLink, a flag raised there by the last band task."""
 
-    def __init__(self, runner):
+    def __init__(self, runner, temporal_block: int):
         import ctypes
         import torch
         self.L = _lib.lib()
         self.torch = torch
-        g, dist = runner.geo, runner.dist
-        self.elems = int(np.prod(g.local_padded))
-        self.ptrs, handles = [], []
-        self.opened = []
-        self.peer = {}
-        try:
-            for _ in range(3):  # buffer 0, buffer 1, flags
-                nbytes = self.elems * 8 if len(self.ptrs) < 2 else 64
-                ptr, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-                _lib.check(self.L.lora_peer_alloc(ctypes.byref(ptr), nbytes, h), "lora_peer_alloc")
-                self.ptrs.append(ptr.value)
-                handles.append(h.raw)
-        except Exception:  # noqa: BLE001 -- the gather below is collective: every rank has to reach it
-            handles = None
+        dist = runner.dist
+        g = runner.geo
+        self._h = ctypes.c_void_p()
+        d = (ctypes.c_longlong * 3)(*g.dims, *([0] * (3 - g.dim)))
+        p = runner.params
+        pp = None if p is None else p.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        rc = self.L.lora_slab_create(ctypes.byref(self._h), _lib.SHAPE_IDS[runner.shape], int(runner.mode), pp, d,
+                                     runner.world, runner.rank, int(temporal_block))
+        handles = None
+        if rc == 0:
+            hb = ctypes.create_string_buffer(192)
+            if self.L.lora_slab_export(self._h, hb) == 0:
+                handles = hb.raw
+        self.err = None if handles is not None else self.L.lora_last_error().decode()
         everyone = [None] * runner.world
-        dist.all_gather_object(everyone, handles, group=runner.group)
-        if any(h is None for h in everyone):
-            raise _lib.LoraError("lora_peer_alloc failed on some rank")
-        self.buf = [torch.as_tensor(_DevMem(self.ptrs[i], g.local_padded, "<f8"), device=runner.device) for i in range(2)]
-        self.flags_ptr = self.ptrs[2]  # [0]: written by prev, [1]: written by next
-        for name, r in (("prev", g.prev), ("next", g.next)):
-            if r is None:
-                continue
-            ptrs = []
-            for h in everyone[r]:
-                q = ctypes.c_void_p()
-                _lib.check(self.L.lora_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(q)), "lora_peer_open")
-                ptrs.append(q.value)
-                self.opened.append(q.value)
-            self.peer[name] = ptrs
-        # element shift from my outer index to the neighbour's: my first slab rows -> its trailing ghost rows, my
-        # last slab rows -> its leading ghost rows
-        rest = int(np.prod(g.local_padded[1:])) if g.dim > 1 else 1
-        self.shift = {}
-        if g.prev is not None:
-            gp = SlabGeometry(g.dims, g.world, g.prev, align=runner.align, ghost=runner.ghost)
-            self.shift["prev"] = ((gp.wl + gp.slab) - g.wl) * rest
-        if g.next is not None:
-            gn = SlabGeometry(g.dims, g.world, g.next, align=runner.align, ghost=runner.ghost)
-            self.shift["next"] = (gn.wl - g.wl - g.slab) * rest
-        self.seq = 0  # sweeps issued so far: flags only ever grow
+        if runner.world > 1:
+            dist.all_gather_object(everyone, handles, group=runner.group)
+        else:
+            everyone = [handles]
+        if any(h is None for h in everyone):  # collective decision: all ranks give up together
+            self.destroy()
+            raise _lib.LoraError(f"lora_slab_create / export failed on some rank ({self.err})")
+        ok = True
+        for side, r in ((0, g.prev), (1, g.next)):
+            if r is not None and self.L.lora_slab_connect_ipc(self._h, side, ctypes.create_string_buffer(everyone[r], 192)) != 0:
+                self.err = self.L.lora_last_error().decode()
+                ok = False
+        self.ok = ok
+        info = (ctypes.c_longlong * 10)()
+        _lib.check(self.L.lora_slab_info(self._h, info), "lora_slab_info")
+        assert (info[0], info[1], info[2], info[3], info[4]) == (g.lo, g.hi, g.wl, g.wr, g.off), "native and Python slab geometry differ"
+        assert tuple(info[5:5 + g.dim]) == tuple(g.local_padded)
+        self.max_tb = int(info[8])
+        self.buf = [torch.as_tensor(_DevMem(self.L.lora_slab_buffer(self._h, i), g.local_padded, "<f8"), device=runner.device)
+                    for i in range(2)]
 
-    def mirror(self, side: str, which: int):
-        """Address in the neighbour's buffer `which` that corresponds to element 0 of mine."""
-        if side not in self.peer:
-            return None
-        return self.peer[side][which] + 8 * self.shift[side]
-
-    def wait_neighbours(self, stream):
-        """Block `stream` until both neighbours have finished the edge bands of the previous sweep: their rows are in
-        my ghost zones, and they no longer read the ghost zones I am about to overwrite."""
+    def run(self, times: int, stream):
         from ctypes import c_void_p
-        for k, side in enumerate(("prev", "next")):
-            if side in self.peer and self.seq > 0:
-                _lib.check(self.L.lora_stream_wait_flag_geq(c_void_p(stream.cuda_stream), c_void_p(self.flags_ptr + 8 * k),
-                                                            self.seq), "lora_stream_wait_flag_geq")
+        _lib.check(self.L.lora_slab_run(self._h, int(times), c_void_p(stream.cuda_stream)), "lora_slab_run")
 
-    def signal_neighbours(self, stream):
+    def sweep(self, tb: int, stream):
         from ctypes import c_void_p
-        self.seq += 1
-        if "prev" in self.peer:  # I am prev's `next`
-            _lib.check(self.L.lora_stream_write_flag(c_void_p(stream.cuda_stream), c_void_p(self.peer["prev"][2] + 8),
-                                                     self.seq), "lora_stream_write_flag")
-        if "next" in self.peer:  # I am next's `prev`
-            _lib.check(self.L.lora_stream_write_flag(c_void_p(stream.cuda_stream), c_void_p(self.peer["next"][2]),
-                                                     self.seq), "lora_stream_write_flag")
+        _lib.check(self.L.lora_slab_sweep(self._h, int(tb), c_void_p(stream.cuda_stream)), "lora_slab_sweep")
 
-    def close(self):
-        self.torch.cuda.synchronize()
-        for q in self.opened:
-            self.L.lora_peer_close(q)
-        self.opened = []
+    def reset(self):
+        _lib.check(self.L.lora_slab_reset(self._h), "lora_slab_reset")
 
-    def abandon(self):
-        """Give everything back after a failed collective set-up."""
-        self.close()
-        for ptr in self.ptrs:
-            self.L.lora_peer_free(ptr)
-        self.ptrs = []
+    @property
+    def result_index(self) -> int:
+        return int(self.L.lora_slab_result_index(self._h))
+
+    @property
+    def plan_handle(self):
+        return self.L.lora_slab_plan(self._h)
+
+    def destroy(self):
+        if self._h:
+            self.L.lora_slab_destroy(self._h)
+            self._h = None
 
 
 class SlabRunner:
@@ -207,7 +188,8 @@ class SlabRunner:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.shape = shape
+        self.shape, self.mode = shape, mode
+        self.params = None if params is None else np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
         dim = len(global_dims)
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self.cuda = self.device.type == "cuda"
@@ -237,45 +219,52 @@ class SlabRunner:
             ghost = 3 * self.max_tb
         self.ghost, self.align = ghost, (16 if dim == 1 else 1)
         self.geo = SlabGeometry(global_dims, self.world, self.rank, align=self.align, ghost=ghost)
-        if not injected:
-            from .plan import Plan
-            self.plan = Plan(shape, self.geo.local_dims, params=params, mode=mode)
-            if dim == 2:
-                self.plan.temporal_block = self.max_tb
-            step_fn, fused_fn = self.plan.step, self.plan.step_fused
-        else:
-            self.plan = None
-        self.step_fn, self.fused_fn = step_fn, fused_fn
-        # halo exchange: "p2p" = edge bands stored straight into the neighbours' ghost rows over NVLink peer memory
-        # (PeerHalo); "nccl" = ncclSend/ncclRecv of the bands (torch.distributed); CPU tests always use the latter
-        self.halo_mode = "nccl"
-        self.peer = None
         g = self.geo
-        if self.cuda and self.world > 1 and not injected and os.environ.get("LORA_HALO", "p2p") == "p2p":
+        # halo exchange: "p2p" (default on GPUs) = the native slab driver (NativeSlab / csrc/slab.cu): band cells stored
+        # straight into the neighbours' ghost zones over NVLink peer memory by the sweep's own kernel launch;
+        # "nccl" (LORA_HALO=nccl, cross-check) = edge-band launches + ncclSend/ncclRecv of the bands
+        # (torch.distributed); the CPU tests (gloo, injected compute) always take the latter route
+        self.halo_mode = "nccl"
+        self.native = None
+        self.plan = None
+        if self.cuda and not injected and os.environ.get("LORA_HALO", "p2p") == "p2p":
             thin = [SlabGeometry(global_dims, self.world, r, align=self.align, ghost=ghost) for r in range(self.world)]
-            if all(t.slab >= t.wl + t.wr for t in thin):  # bands of neighbouring sides must not overlap
+            if self.world == 1 or all(t.slab >= t.wl + t.wr for t in thin):  # bands of the two sides must not overlap
                 self.halo_mode = "p2p"
         if self.halo_mode == "p2p":
             # all ranks switch together: if CUDA IPC / peer mapping fails anywhere (container without IPC, GPUs
             # without peer access), everybody falls back to NCCL send/recv
             err = None
             try:
-                self.peer = PeerHalo(self)
+                self.native = NativeSlab(self, self.max_tb)
+                if not self.native.ok:
+                    err = self.native.err
             except Exception as e:  # noqa: BLE001 -- whatever went wrong, the collective decision is what matters
                 err = e
             ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if self.world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
             if int(ok.item()) == 1:
-                self.buf = self.peer.buf
+                from .plan import Plan
+                self.buf = self.native.buf
+                self.plan = Plan.borrowed(self.native.plan_handle, shape, g.local_dims)
+                assert self.native.max_tb == self.max_tb
             else:
-                if self.peer is not None:
-                    self.peer.abandon()
-                    self.peer = None
+                if self.native is not None:
+                    self.native.destroy()
+                    self.native = None
                 self.halo_mode = "nccl"
                 if self.rank == 0:
                     print(f"lorastencil_b200.slab: peer-memory halo exchange unavailable ({err}); using NCCL", flush=True)
         if self.halo_mode != "p2p":
+            if not injected:
+                from .plan import Plan
+                self.plan = Plan(shape, g.local_dims, params=params, mode=mode)
+                if dim == 2:
+                    self.plan.temporal_block = self.max_tb
+                step_fn, fused_fn = self.plan.step, self.plan.step_fused
             self.buf = [torch.zeros(g.local_padded, dtype=torch.float64, device=self.device) for _ in range(2)]
+        self.step_fn, self.fused_fn = step_fn, fused_fn
         self.launch = 0   # kernel sweeps issued: the result sits in buf[launch % 2]
         self.time = 0     # time steps applied
         if self.cuda:
@@ -284,28 +273,30 @@ class SlabRunner:
             self.ev_comm = torch.cuda.Event()
 
     def close(self):
-        """Unmap the neighbours' buffers and free the peer memory (p2p mode); the runner is unusable afterwards."""
-        if self.peer is not None:
-            self.sync_ranks()
-            self.peer.close()
-            self.sync_ranks()
+        """Unmap the neighbours' buffers and free the slab (p2p mode); the runner is unusable afterwards."""
+        if self.native is not None:
+            self.sync_ranks()   # nobody is still storing into anybody's ghost zone
             self.buf = None
-            for ptr in self.peer.ptrs:
-                self.peer.L.lora_peer_free(ptr)
-            self.peer = None
+            self.plan = None
+            self.native.destroy()
+            self.native = None
+            self.sync_ranks()
 
     # ---- data movement helpers (tests / parity; not on the timed path) ----
     def load_global(self, a_global: np.ndarray):
         """Every rank takes its slab (with halo / ghost rows) out of the same global padded array."""
+        self.sync_ranks()  # a neighbour's band tasks of an earlier run may still be storing into my ghost zone
         t = self.torch.from_numpy(np.ascontiguousarray(a_global[self.geo.global_rows()]))
         self.buf[0].copy_(t)
         self.buf[1].zero_()
         self.launch = self.time = 0
+        if self.native is not None:
+            self.native.reset()
         self.sync_ranks()
 
     def sync_ranks(self):
-        """Host-side rendezvous after the buffers were (re)filled from outside: no neighbour may store into my ghost
-        rows before I have finished writing them myself (p2p mode)."""
+        """Host-side rendezvous around (re)filling the buffers from outside: no neighbour may store into my ghost
+        rows while I am writing them myself (p2p mode)."""
         if self.cuda:
             self.torch.cuda.synchronize(self.device)
         if self.world > 1:
@@ -354,21 +345,22 @@ class SlabRunner:
 
     def _sweep(self, tb: int):
         """One kernel sweep of `tb` time steps over the slab + exchange of the edge bands."""
+        if self.native is not None:
+            self.native.sweep(tb, self.torch.cuda.current_stream(self.device))
+            self.launch += 1
+            self.time += tb
+            return
         g = self.geo
         src, dst = self.buf[self.launch % 2], self.buf[(self.launch + 1) % 2]
         lo, hi = g.off, g.off + g.slab  # the slab in plan-interior coordinates
 
         if self.max_tb > 1:
-            def compute(a, b, stream=None, mirror=None):
+            def compute(a, b, stream=None):
                 kw = {} if stream is None else {"stream": stream}
-                if mirror:
-                    kw["mirror"] = mirror
                 self.fused_fn(src, dst, self.buf[0], a, b, tb, self.time, g.prev is None, g.next is None, **kw)
         else:
-            def compute(a, b, stream=None, mirror=None):
+            def compute(a, b, stream=None):
                 kw = {} if stream is None else {"stream": stream}
-                if mirror:
-                    kw["mirror"] = mirror
                 self.step_fn(src, dst, a, b, **kw)
 
         if self.world == 1 or not self.cuda:
@@ -383,20 +375,11 @@ class SlabRunner:
             top = min(lo + g.wl, hi) if g.prev is not None else lo
             bot = max(hi - g.wr, top) if g.next is not None else hi
             with torch.cuda.stream(self.comm_stream):
-                if self.peer is not None:
-                    which = (self.launch + 1) % 2
-                    self.peer.wait_neighbours(self.comm_stream)
-                    if top > lo:
-                        compute(lo, top, self.comm_stream, self.peer.mirror("prev", which))
-                    if bot < hi:
-                        compute(bot, hi, self.comm_stream, self.peer.mirror("next", which))
-                    self.peer.signal_neighbours(self.comm_stream)
-                else:
-                    if top > lo:
-                        compute(lo, top, self.comm_stream)
-                    if bot < hi:
-                        compute(bot, hi, self.comm_stream)
-                    self._exchange(dst)
+                if top > lo:
+                    compute(lo, top, self.comm_stream)
+                if bot < hi:
+                    compute(bot, hi, self.comm_stream)
+                self._exchange(dst)
                 self.ev_comm.record(self.comm_stream)
             if bot > top:
                 compute(top, bot, main)
@@ -409,6 +392,17 @@ class SlabRunner:
 
     def run(self, times: int):
         """`times` launches of the reference operator; the result is in buf[times % 2] like the reference's."""
+        if self.native is not None:
+            self.native.run(times, self.torch.cuda.current_stream(self.device))  # the whole sweep loop is native
+            if self.world == 1 and self.launch % 2 == 0 and self.time % 2 == 0:
+                self.launch += times  # lora_slab_run hands a whole grid on one device to lora_plan_run
+            elif self.geo.dim == 1:
+                self.launch += len(temporal_schedule(times, self.max_tb))
+            else:
+                self.launch += len(temporal_schedule_2d(times, self.max_tb))
+            self.time += times
+            assert self.launch % 2 == self.native.result_index
+            return self.result()
         if self.world == 1 and self.plan is not None and self.launch % 2 == 0 and self.time % 2 == 0:
             res = self.plan.run(self.buf[0], self.buf[1], times)  # whole line on one device: the plan schedules it
             self.launch += times
