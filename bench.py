@@ -19,7 +19,14 @@ Numbers on the JSON line:
              SURVEY.md section 8d) / its average launch duration, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the reference's own test_cpu (oracle/_ref, compiled from its main.cu) on the host cores,
              timed on a bounded sample (a few launches over the same 2^28-point line).
-  shapes     the other seven shapes at their BASELINE sizes (device-resident, 1 GPU), same definitions.
+  shapes     all eight shapes at their BASELINE sizes on 1 GPU: device-resident GStencil/s (best and median of 5
+             repetitions, clocks sampled per shape), e2e through the drop-in operator with pinned and with pageable host
+             buffers, and the reference's test_cpu on 1 core and on all host cores; `worst_shape_frac` = the smallest
+             fixed-16-B roofline fraction among them.
+  parity     (every N) small grids of all shapes through the same slab driver the timed run uses, gathered and compared
+             with the CPU oracle on rank 0 -- multi-GPU correctness travels with the scaling record.
+  scaling_extra  (every N) BASELINE.json configs[4]: box2d1r 40960^2 and box3d1r 1024^3 strong scaling (global grid
+             fixed, N slabs), and per-GPU-constant 2-D / 3-D slabs (weak scaling), with the bytes exchanged per step.
 """
 import argparse
 import ctypes
@@ -43,6 +50,16 @@ HEADLINE = ("1d2r", (1 << 28,), 1000)
 SHAPE_TABLE = [("1d1r", (1 << 28,), 50), ("1d2r", (1 << 28,), 50), ("star2d1r", (10240, 10240), 100),
                ("box2d1r", (10240, 10240), 100), ("star2d3r", (10240, 10240), 100), ("box2d3r", (10240, 10240), 100),
                ("box3d1r", (512, 512, 512), 100), ("star3d1r", (512, 512, 512), 100)]
+
+
+def headline_config():
+    """config of the JSON line -- the SAME dict in both arms (ours and --impl reference), so the driver can match them."""
+    shape, dims, times = HEADLINE
+    return {"workload": f"lorastencil_1d {shape} {dims[0]} {times} (BASELINE.json configs[1])", "shape": shape,
+            "points_per_gpu": dims[0], "launches_per_job": times,
+            "step": "our arm: one step = the whole job (all launches); reference arm: one step = a bounded sample of "
+                    "it (1 launch over the same line); both values are cells x launches / s",
+            "l2": "inputs (2.1 GB per buffer) larger than L2; no flush needed"}
 
 
 def measured_traffic(kernel_key):
@@ -152,7 +169,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference CPU arm / cpu_baseline: the reference's verbatim test_cpu on all host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_runner(shape, dims):
+def cpu_reference_runner(shape, dims, cores=None):
     """Returns (run_once, cores, kind): run_once() does ONE launch over the whole grid with the reference's
     test_cpu (oracle/_ref) split over `cores` host threads along the outermost axis; falls back to the
     OpenMP oracle port when oracle/_ref is absent."""
@@ -164,10 +181,11 @@ def cpu_reference_runner(shape, dims):
     a = rng.integers(0, mod, size=padded).astype(np.float64)
     out = np.zeros_like(a)
     params = np.ascontiguousarray(oracle.reference_params(shape))
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
+    if cores is None:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
     h0 = oracle.HALO[d][0]
     rest = int(np.prod(padded[1:])) if d > 1 else 1
     if oracle.ref_available("cpu", d):
@@ -198,8 +216,8 @@ def cpu_reference_runner(shape, dims):
     return run_once, cores, "port"
 
 
-def time_cpu(shape, dims, min_seconds=15.0, max_launches=60):
-    run_once, cores, kind = cpu_reference_runner(shape, dims)
+def time_cpu(shape, dims, min_seconds=15.0, max_launches=60, cores=None):
+    run_once, cores, kind = cpu_reference_runner(shape, dims, cores)
     run_once()  # warm (page-faults the output)
     n, t0 = 0, time.perf_counter()
     while True:
@@ -233,8 +251,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "GStencil/s", "value": v, "unit": "GStencil/s (cells x launches / s / 1e9)",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"lorastencil_1d {shape} {dims[0]} {times} (BASELINE.json configs[1])", "shape": shape,
-                   "points_per_gpu": dims[0], "launches_per_job": times},
+        "config": headline_config(),
         "cpu_baseline": {"value": v, "unit": "GStencil/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -248,34 +265,160 @@ def device_fill(torch, shape_padded, mod, device, seed):
     return torch.randint(0, mod, shape_padded, generator=g, device=device).double()
 
 
-def measure_shape(torch, ls, shape, dims, launches, hbm_gbs, reps=3):
-    """Device-resident GStencil/s of one shape on the current device (CUDA events, best of reps)."""
+def measure_shape(torch, ls, ops, shape, dims, launches, hbm_gbs, device_index, reps=5, e2e=True, cpu=True):
+    """One row of the per-shape table: device-resident GStencil/s (CUDA events, best and median of `reps`, NVML clocks
+    sampled during the repetitions), e2e through the reference-facing operator (pinned and pageable host buffers),
+    the reference's test_cpu on 1 core and on all host cores."""
     plan = ls.Plan(shape, dims)
     d = len(dims)
     b0 = device_fill(torch, plan.padded_shape, 10000 if d == 1 else 100, "cuda", 1)
     b1 = plan.new_buffer()
     plan.run(b0, b1, 3)
     torch.cuda.synchronize()
-    best = None
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        plan.run(b0, b1, launches)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        best = ms if best is None else min(best, ms)
+    ms_all = []
+    with ClockSampler(device_index) as clk:
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.run(b0, b1, launches)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_all.append(e0.elapsed_time(e1))
     cells = float(np.prod(dims))
+    best, med = min(ms_all), statistics.median(ms_all)
     per_launch_s = best / 1e3 / launches
     gst = cells / per_launch_s / 1e9
     ach = cells * 16 / per_launch_s / 1e9
-    desc = plan.describe
-    tb = plan.temporal_block
+    row = {"shape": shape, "dims": list(dims), "launches": launches, "gstencils": gst,
+           "gstencils_median": cells * launches / (med / 1e3) / 1e9, "reps": reps,
+           "gstencils_artifact_units": gst * ARTIFACT_K[shape], "us_per_launch": per_launch_s * 1e6,
+           "hbm_gbs_algorithmic": ach, "roofline_frac": ach / hbm_gbs, "roofline_frac_median": ach / hbm_gbs * best / med,
+           "form": plan.describe, "temporal_block": plan.temporal_block, "clocks": clk.summary()}
     del plan, b0, b1
     torch.cuda.empty_cache()
-    return {"shape": shape, "dims": list(dims), "launches": launches, "gstencils": gst,
-            "gstencils_artifact_units": gst * ARTIFACT_K[shape], "us_per_launch": per_launch_s * 1e6,
-            "hbm_gbs_algorithmic": ach, "roofline_frac": ach / hbm_gbs, "form": desc, "temporal_block": tb}
+    if e2e:
+        # the drop-in operator gpu_X(in, out, params, times, dims...) with HOST buffers: H2D, all launches, D2H inside
+        # the timed region.  Pinned buffers (what an application that cares would pass) and pageable ones (what the
+        # reference's main.cu mallocs, src/2d/main.cu:224-225).
+        padded = tuple(x + 2 * h for x, h in zip(dims, HALO[d]))
+        params = ls.reference_table(shape)
+        times = 1000 if d == 1 else 100
+        nel = int(np.prod(padded))
+        src = torch.randint(0, 10000 if d == 1 else 100, padded).double()
+        for kind in ("pinned", "pageable"):
+            if kind == "pinned":
+                hin, hout = src.pin_memory(), torch.empty(padded, dtype=torch.float64).pin_memory()
+            else:
+                hin, hout = src.numpy(), np.empty(padded, dtype=np.float64)
+                hout.fill(0.0)  # fault the pages in, as a caller that reuses its arrays would have
+            ops.BY_SHAPE[shape](hin, hout, params, times, *dims)  # warm: device workspace, page faults
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ops.BY_SHAPE[shape](hin, hout, params, times, *dims)
+                ts.append(time.perf_counter() - t0)
+            el = min(ts)
+            row["e2e" if kind == "pinned" else "e2e_pageable"] = {
+                "value": cells * times / el / 1e9, "unit": "GStencil/s", "launches": times, "ms_per_call": el * 1e3,
+                "launch_loop_ms": ops.last_loop_ms(), "h2d_bytes_per_step": nel * 8, "d2h_bytes_per_step": nel * 8 - (8 if d == 1 else 0),
+                "host_buffers": kind, "api": f"lorastencil_b200.ops.{ops.BY_SHAPE[shape].__name__} -> lora_{ops.BY_SHAPE[shape].__name__} (C ABI)"}
+            del hin, hout
+        del src
+        ops.release_workspace()
+    if cpu:
+        one = time_cpu(shape, dims, min_seconds=1.0, max_launches=1, cores=1)
+        allc = time_cpu(shape, dims, min_seconds=4.0, max_launches=8)
+        row["cpu_baseline"] = {"one_core": one, "all_cores": allc}
+    return row
+
+
+def exchange_bytes_per_step(shape, dims, tb):
+    """Bytes one slab sends to ONE neighbour per time step (its ghost zone, once per sweep of tb launches)."""
+    d = len(dims)
+    if d == 1:
+        return 4 * tb * 8 / tb
+    if d == 2:
+        rows = 3 * tb if tb > 1 else 4  # fused: radius x tb rows per sweep; unfused: the 4-row storage halo per launch
+        return rows * (dims[1] + 8) * 8 / tb
+    return (dims[1] + 4) * (dims[2] + 8) * 8
+
+
+def parity_probe(torch, dist, SlabRunner, dev, world, rank):
+    """Small grids of every shape through the slab driver (the timed path), gathered on rank 0 and compared with the
+    CPU oracle: bit-identical while the integers stay exact, <= 1e-12 relative afterwards."""
+    cases = [("1d2r", (1 << 20,), 20), ("1d1r", (300000,), 7), ("box2d1r", (512, 640), 5), ("box2d3r", (384, 258), 4),
+             ("star2d3r", (600, 516), 7), ("star2d1r", (512, 256), 6), ("box3d1r", (64, 64, 128), 5),
+             ("star3d1r", (48, 40, 136), 4)]
+    exact_upto = {"1d1r": 8, "1d2r": 8, "box2d1r": 5, "box2d3r": 5, "star2d1r": 6, "star2d3r": 9, "box3d1r": 8, "star3d1r": 15}
+    out = []
+    ok_all = True
+    for shape, dims, times in cases:
+        d = len(dims)
+        padded = tuple(x + 2 * h for x, h in zip(dims, HALO[d]))
+        a = np.random.default_rng(77).integers(0, 100, size=padded).astype(np.float64)
+        r = SlabRunner(shape, dims, device=dev)
+        r.load_global(a)
+        r.run(times)
+        torch.cuda.synchronize()
+        got = r.gather_global(a.shape)
+        mode = r.halo_mode
+        r.close()
+        if rank == 0:
+            import oracle
+            ref = oracle.run(shape, a, oracle.effective_params(shape), times)
+            if d == 1:
+                got, ref = got[:-1], ref[:-1]
+            if times <= exact_upto[shape]:
+                ok = bool(np.array_equal(got, ref))
+                how = "bit-identical" if ok else "MISMATCH"
+            else:
+                err = float(np.abs(got - ref).max() / np.abs(ref).max())
+                ok = err <= 1e-12
+                how = f"max rel err {err:.2g}"
+            ok_all &= ok
+            out.append({"shape": shape, "dims": list(dims), "launches": times, "result": how})
+    return {"ok": bool(ok_all), "against": "CPU oracle (oracle/oracle.c, pinned to the reference's test_cpu)", "n_gpus": world,
+            "halo": mode, "cases": out}
+
+
+def scaling_extra(torch, dist, SlabRunner, dev, world, rank):
+    """BASELINE.json configs[4] (strong scaling of the two named grids) and per-GPU-constant 2-D / 3-D slabs (weak)."""
+    table = [("box2d1r", (40960, 40960), 30, "strong"), ("box3d1r", (1024, 1024, 1024), 30, "strong"),
+             ("box2d1r", (10240, 10240), 60, "weak"), ("star2d3r", (10240, 10240), 60, "weak"),
+             ("box3d1r", (512, 512, 512), 60, "weak"), ("star3d1r", (512, 512, 512), 60, "weak")]
+    rows = []
+    for shape, dims, launches, mode in table:
+        gdims = tuple(dims) if mode == "strong" else (dims[0] * world,) + tuple(dims[1:])
+        r = SlabRunner(shape, gdims, device=dev)
+        r.buf[0].copy_(device_fill(torch, r.geo.local_padded, 100, dev, 99 + rank))
+        r.sync_ranks()
+        r.run(4 if r.max_tb == 1 else 6)  # even number of sweeps: the timed run starts from a parity-consistent state
+        r.sync_ranks()
+        best = None
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r.sync_ranks()
+            e0.record()
+            r.run(launches)
+            e1.record()
+            r.sync_ranks()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            best = ms if best is None else min(best, ms)
+        cells = float(np.prod(gdims))
+        tb = r.max_tb
+        rows.append({"shape": shape, "mode": mode, "global_dims": list(gdims), "launches": launches,
+                     "value": cells * launches / (best / 1e3) / 1e9, "unit": "GStencil/s", "ms_per_step": best / launches,
+                     "temporal_block": tb, "halo": r.halo_mode,
+                     "exchange_bytes_per_step": 0 if world == 1 else exchange_bytes_per_step(shape, gdims, tb) * 2 * (world - 1)})
+        r.close()
+        del r
+        torch.cuda.empty_cache()
+    return rows
 
 
 def main():
@@ -288,6 +431,8 @@ def main():
     ap.add_argument("--no-shapes", action="store_true", help="skip the per-shape table")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the slab-vs-oracle parity probe")
+    ap.add_argument("--no-extra", action="store_true", help="skip scaling_extra (config e strong / 2-D, 3-D weak scaling)")
     # other BASELINE.json configs (parity-test cases by default, measurable on request): e.g. config e
     #   --shape box2d1r --dims 40960,40960 --times 100 --scaling strong     (global grid cut into N slabs)
     ap.add_argument("--shape", default=None, help="measure this shape instead of the headline 1d2r job")
@@ -326,7 +471,7 @@ def main():
         shape = args.shape
         dims = tuple(int(x) for x in args.dims.split(","))
         args.no_shapes = args.no_cpu = True
-        args.no_e2e = True
+        args.no_e2e = args.no_parity = args.no_extra = True
     times = args.times
     n = dims[0]
     if args.scaling == "weak":
@@ -424,6 +569,34 @@ def main():
             t = torch.tensor([el], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
+            # the limiter: all ranks moving their segments H2D and D2H at the same time, no launches at all -- what the
+            # host side (PCIe root complexes, the NUMA node the pinned pages live on) can sustain for N GPUs at once
+            dbuf = torch.empty(nseg, dtype=torch.float64, device=dev)
+            dbuf2 = torch.empty(nseg, dtype=torch.float64, device=dev)
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+            barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                dbuf.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                hout.copy_(dbuf2, non_blocking=True)
+            barrier()
+            tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            copy_s = float(tc.item())
+            del dbuf, dbuf2
+            e2e_detail["host_copy_only_ms"] = copy_s * 1e3
+            e2e_detail["host_copy_ceiling"] = cells_per_gpu * world * times / copy_s / 1e9
+            e2e_detail["host_copy_note"] = ("all ranks copying their segment H2D and D2H concurrently with no launches: the "
+                                            "e2e figure cannot exceed host_copy_ceiling on this box; the launch loop alone "
+                                            "is the device-timed `value`")
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+                e2e_detail["gpu_numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(hnd))
+            except Exception:  # noqa: BLE001
+                pass
         e2e = {"value": cells_per_gpu * world * times * k_e2e / el / 1e9, "unit": "GStencil/s",
                "h2d_bytes_per_step": nloc * 8 * world, "d2h_bytes_per_step": (nloc - 1) * 8 * world,
                "steps": k_e2e, "ms_per_step": el / k_e2e * 1e3,
@@ -431,70 +604,96 @@ def main():
                       "lorastencil_b200.slab.run_host_segment -> ops.gpu_1d2r -> lora_gpu_1d2r (C ABI) per rank, pinned host buffers", **e2e_detail}
         del hin, hout
 
+    halo_mode_used, plan_describe, geo = runner.halo_mode, plan.describe, runner.geo
+    runner_max_tb = runner.max_tb
+    runner.close()
+    del runner
+    torch.cuda.empty_cache()
+    parity = None if args.no_parity else parity_probe(torch, dist, SlabRunner, dev, world, rank)
+    extra = None if args.no_extra else scaling_extra(torch, dist, SlabRunner, dev, world, rank)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
 
-    halo_how = {"p2p": "edge bands stored straight into the neighbours' ghost rows over NVLink peer memory (CUDA IPC), "
-                       "64-bit flags in stream order; interior launches never wait",
-                "nccl": "NCCL send/recv of the edge bands on a side stream"}[runner.halo_mode]
+    halo_how = {"p2p": "one kernel launch per sweep: its band tasks run first and store their cells a second time straight "
+                       "into the neighbours' ghost zones over NVLink peer memory (CUDA IPC), the last band task raises a "
+                       "64-bit flag there, the next sweep waits for the flags in stream order; no communication library "
+                       "on the data path",
+                "nccl": "NCCL send/recv of the edge bands on a side stream"}[halo_mode_used]
     dimname = {1: "1d", 2: "2d", 3: "3d"}[len(dims)]
-    buf_gb = float(np.prod(runner.geo.local_padded)) * 8 / 1e9
-    line = {
-        "metric": "GStencil/s", "value": value, "unit": "GStencil/s (cells x launches / s / 1e9)",
-        "value_artifact_units": value * ARTIFACT_K[shape],
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"lorastencil_{dimname} {shape} {' '.join(map(str, dims))} {times} "
-                               + ("per GPU" if args.scaling == "weak" else "global grid")
-                               + (" (BASELINE.json configs[1])" if not custom else ""),
-                   "shape": shape, "points_per_gpu": int(cells_per_gpu), "launches_per_step": times,
-                   "global_dims": list(global_dims),
-                   "decomposition": "single device" if world == 1 else
-                   f"{world} slabs along the outermost axis, {runner.geo.wl if runner.geo.prev is not None else runner.geo.wr}"
-                   f"-deep ghost zones exchanged once per sweep of {runner.max_tb} launch(es): " + halo_how,
-                   "l2": f"inputs ({buf_gb:.1f} GB per buffer) larger than L2; no flush needed",
-                   "values": "reference weights: FP64 overflows to inf after ~130-340 launches exactly as in the reference run; timing only",
-                   "kernel_form": plan.describe, "temporal_block": runner.max_tb},
-        "gpu_launches": gpu_launches,
-        "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
-                     "traffic": (measured_traffic(f"{shape}:{'x'.join(map(str, dims))}:tb{runner.max_tb}") or {}).get("bytes"),
-                     "traffic_source": (measured_traffic(f"{shape}:{'x'.join(map(str, dims))}:tb{runner.max_tb}") or {}).get("source"),
-                     "kernel": (f"k_stencil1d_tb (tb = {runner.max_tb})" if runner.max_tb > 1 else "k_stencil1d")
-                     if len(dims) == 1 else f"k_stencil{len(dims)}d",
-                     "us_per_launch": us_per_launch,
-                     "algorithmic_bytes_per_launch": cells_per_gpu * 16 * steps_per_launch,
-                     "time_steps_per_launch": steps_per_launch, "peak_source": peak_src,
-                     "note": "fixed 16 B per cell per time step; temporal blocking moves fewer DRAM bytes than that, so "
-                             "frac can exceed 1 -- `traffic` is the measured DRAM bytes per launch",
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
-    }
-    # the honest ceilings of a temporally blocked sweep: the DRAM bytes it really moves, and the FP64 pipe
-    traffic = line["roofline"]["traffic"]
+    buf_gb = float(np.prod(geo.local_padded)) * 8 / 1e9
+    if custom:
+        config = {"workload": f"lorastencil_{dimname} {shape} {' '.join(map(str, dims))} {times} "
+                              + ("per GPU" if args.scaling == "weak" else "global grid"), "shape": shape,
+                  "points_per_gpu": int(cells_per_gpu), "launches_per_job": times}
+    else:
+        config = headline_config()
+    detail = {"global_dims": list(global_dims), "scaling": args.scaling,
+              "decomposition": "single device" if world == 1 else
+              f"{world} slabs along the outermost axis, {geo.wl if geo.prev is not None else geo.wr}"
+              f"-deep ghost zones exchanged once per sweep of {runner_max_tb} launch(es): " + halo_how,
+              "buffer_gb": buf_gb,
+              "values": "reference weights: FP64 overflows to inf after ~130-340 launches exactly as in the reference run; timing only",
+              "kernel_form": plan_describe, "temporal_block": runner_max_tb}
+    tkey = f"{shape}:{'x'.join(map(str, dims))}:tb{runner_max_tb}"
+    traffic = (measured_traffic(tkey) or {}).get("bytes")
+    kernel = ((f"k_stencil1d_tb (tb = {runner_max_tb})" if runner_max_tb > 1 else "k_stencil1d")
+              if len(dims) == 1 else f"k_stencil{len(dims)}d")
+    hbm = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+           "traffic": traffic, "traffic_source": (measured_traffic(tkey) or {}).get("source"),
+           "algorithmic_bytes_per_launch": cells_per_gpu * 16 * steps_per_launch,
+           "time_steps_per_launch": steps_per_launch, "peak_source": peak_src,
+           "frac_of_nominal_8TBs": achieved / 8000.0,
+           "note": "SURVEY.md 8(d) convention: fixed 16 B per cell per time step; a temporally blocked sweep moves fewer "
+                   "DRAM bytes than that, so this fraction can exceed 1 -- dram_frac is what the DRAM really does"}
     if traffic:
         dram_gbs = traffic / (us_per_launch * 1e-6) / 1e9
-        line["roofline"]["dram_achieved_gbs"] = dram_gbs
-        line["roofline"]["dram_frac"] = dram_gbs / hbm_gbs
+        hbm["dram_achieved_gbs"] = dram_gbs
+        hbm["dram_frac"] = dram_gbs / hbm_gbs
     flop_per_cell = {1: 18.0}.get(len(dims))  # 9 taps = 9 FP64 FMA per cell per time step
     try:
         fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r1_fp64_pipes.json")))["dfma_tflops"])
     except (OSError, ValueError, KeyError):
         fp64_peak = None
-    if flop_per_cell and fp64_peak:
+    if flop_per_cell and fp64_peak and runner_max_tb > 1:
+        # the fused sweep is bound by the FP64 pipe, not by HBM: that is the roofline reported first; the fixed-16-B
+        # HBM figure of the SURVEY convention sits beside it
         tf = value / world * flop_per_cell / 1e3
-        line["roofline"]["fp64"] = {"achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
-                                    "peak_source": "measured DFMA stream on this pool (profiles/r1_fp64_pipes.json)",
-                                    "note": "9 FMA per cell per time step is the floor for general 9-tap weights; with "
-                                            "15 launches fused per sweep this pipe, not HBM, bounds the kernel"}
+        roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                    "traffic": traffic, "kernel": kernel, "us_per_launch": us_per_launch,
+                    "peak_source": "measured DFMA stream on this pool (profiles/r1_fp64_pipes.json; MEASURED_PEAKS.json has no "
+                                   "FP64 figure): FP64 FMA and FP64 DMMA share one pipe at 36.5-37.1 TFLOP/s",
+                    "note": "9 FMA per cell per time step is the floor for general 9-tap weights; with "
+                            f"{runner_max_tb} launches fused per sweep this pipe, not HBM, bounds the kernel",
+                    "hbm_fixed16": hbm}
+    else:
+        roofline = dict(hbm, kernel=kernel, us_per_launch=us_per_launch)
+    line = {
+        "metric": "GStencil/s", "value": value, "unit": "GStencil/s (cells x launches / s / 1e9)",
+        "value_artifact_units": value * ARTIFACT_K[shape],
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config, "detail": detail,
+        "gpu_launches": gpu_launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+    }
     if e2e:
         line["e2e"] = e2e
+    if parity is not None:
+        line["parity"] = parity
+    if extra is not None:
+        line["scaling_extra"] = extra
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = time_cpu(shape, dims)
     if world == 1 and not args.no_shapes:
-        line["shapes"] = [measure_shape(torch, ls, s, d, l, hbm_gbs) for s, d, l in SHAPE_TABLE]
+        line["shapes"] = [measure_shape(torch, ls, ops, s, d, l, hbm_gbs, local) for s, d, l in SHAPE_TABLE]
+        worst = min(line["shapes"], key=lambda r: r["roofline_frac"])
+        line["worst_shape_frac"] = worst["roofline_frac"]
+        line["worst_shape"] = worst["shape"]
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
     if world > 1:

@@ -232,6 +232,17 @@ struct Geom3D {
     int vec4;
 };
 
+// direct-tap kernels without TMA (stencil_direct.cu): grids with an odd number of padded columns
+struct GeomDirect {
+    const double *in;
+    double *out;
+    long long pitch, plane_pitch;  // padded columns; padded rows * padded columns (3-D)
+    int m, n;                      // rows (3-D: per plane), columns
+    int col_blocks;                // blocks of 256 columns
+    Segs sg;  // segments = interior rows (2-D) / planes (3-D); first[] counts rows / planes; arrivals: one per CTA
+};
+cudaError_t launch_direct(int dim, const GeomDirect &g, const WeightsDirect49 &w, cudaStream_t s);
+
 cudaError_t launch_1d(const Geom1D &g, const Weights1D &w, cudaStream_t s);
 cudaError_t launch_1d_tb(const CUtensorMap &imap, const CUtensorMap &omap, const Geom1DTB &g, const Weights1D &w,
                          cudaStream_t s);

@@ -103,6 +103,8 @@ struct lora_plan {
     int slots = 148 * 16;  // concurrently resident warp workers (1-D / 2-D) or CTAs (3-D)
     int device = 0;
     int max_tb = 1;        // deepest temporal block lora_plan_run may fuse (1 = one launch per time step)
+    bool odd_cols = false; // 2-D / 3-D with an odd number of padded columns: no tensor map possible, direct-tap kernel
+    WeightsDirect49 eff{}; // the effective direct taps (49, or 27 in 3-D) the chosen form equals
 };
 
 constexpr int kTb2 = 3;  // the 2-D temporal block (odd, so that time parity == buffer parity at every sweep)
@@ -189,6 +191,7 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         p->w2.centre = d.centre;
         std::memcpy(p->w2.residual, d.residual, sizeof d.residual);
         std::memcpy(p->wd.w, d.direct, sizeof d.direct);
+        std::memcpy(p->eff.w, d.effective, sizeof d.effective);
         p->form = d.form;
         p->desc = d.desc;
     } else {
@@ -199,8 +202,14 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         std::memcpy(p->w3.c, d.c, sizeof d.c);
         std::memcpy(p->w3.star, d.star, sizeof d.star);
         std::memcpy(p->w3.direct, d.direct, sizeof d.direct);
+        std::memcpy(p->eff.w, d.effective, sizeof d.effective);
         p->form = d.form;
         p->desc = d.desc;
+    }
+    if (dim >= 2 && p->padded[dim - 1] % 2) {
+        // odd row length: rows are not 16-byte aligned, no TMA descriptor exists for this grid (stencil_direct.cu)
+        p->odd_cols = true;
+        p->desc += " [odd column count: direct taps without TMA]";
     }
     ensure_init(&p->device);
     int sms = 0;
@@ -215,7 +224,7 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         if (v >= 1 && v <= 64) warps_per_sm = v;
     }
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
-    if (dim == 2 && tb2_form(p->form)) {
+    if (dim == 2 && tb2_form(p->form) && !p->odd_cols) {
         // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 560 vs 335 GStencil/s unfused, diamond 387 vs
         // 327); the pyramid form is FP64-bound already and loses (223 vs 339), so it stays at one launch per step
         p->max_tb = (p->form == LORA_FORM_CROSS || p->form == LORA_FORM_DIAMOND) ? kTb2 : 1;
@@ -407,6 +416,21 @@ static int step_unfused(lora_plan_t *p, const double *src, double *dst, long lon
         g.vec4 = (lo % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
         g.mirror = mirror_base ? (long long)(mirror_base - dst) : 0;
         e = launch_1d(g, p->w1, st);
+    } else if (p->odd_cols) {
+        SegCut sc;
+        if (int rc = cut_segments(lo, hi, dst, ex, mirror_base, sc)) return rc;
+        GeomDirect g;
+        g.in = src;
+        g.out = dst;
+        g.pitch = p->padded[p->dim - 1];
+        g.plane_pitch = p->dim == 3 ? p->padded[1] * p->padded[2] : 0;
+        g.m = (int)p->dims[p->dim - 2];
+        g.n = (int)p->dims[p->dim - 1];
+        g.col_blocks = (g.n + 255) / 256;
+        long long chunk[kMaxSegs], tasks[kMaxSegs];
+        for (int i = 0; i < sc.n; i++) chunk[i] = 1, tasks[i] = sc.hi[i] - sc.lo[i];
+        fill_segs(g.sg, sc, chunk, tasks, (long long)g.col_blocks * (p->dim == 3 ? g.m : 1));
+        e = launch_direct(p->dim, g, p->eff, st);
     } else if (p->dim == 2) {
         const CUtensorMap *tm;
         int rc = get_tmap(p, src, &tm);
@@ -502,7 +526,7 @@ extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
     if (p->dim == 1)
         p->max_tb = tb < kMaxTb1 ? tb : kMaxTb1;
     else if (p->dim == 2)
-        p->max_tb = (tb >= kTb2 && tb2_form(p->form)) ? kTb2 : 1;  // 2-D fuses exactly 3 launches or none
+        p->max_tb = (tb >= kTb2 && tb2_form(p->form) && !p->odd_cols) ? kTb2 : 1;  // 2-D fuses exactly 3 launches or none
     else
         p->max_tb = 1;
     return LORA_OK;
@@ -562,8 +586,8 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
                          const double *mirror_base, void *stream) {
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if (tb == 1) return step_unfused(p, src, dst, lo, hi, ex, mirror_base, stream);
-    if (tb != kTb2 || !tb2_form(p->form))
-        return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid)", kTb2);
+    if (tb != kTb2 || !tb2_form(p->form) || p->odd_cols)
+        return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid; even column counts)", kTb2);
     if (!halo_src) return fail(LORA_ERR_ARG, "fused 2-D launches need halo_src (the buffer holding the caller's halo)");
     if (lo == hi) return LORA_OK;
     if (int rc = check_device(p)) return rc;

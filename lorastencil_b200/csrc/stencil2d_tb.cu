@@ -106,15 +106,20 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
         x[2 * k] = v.x;
         x[2 * k + 1] = v.y;
     }
+    push_row<FORM, PH>(x, A[0], w, wd);
+    // Refill the stage only AFTER the push has consumed x[]: the FP64 operations cannot issue before the LDS data has
+    // arrived, so once every lane is past them (__syncwarp) no read of this stage is still in flight.  Issuing the TMA
+    // right after the loads were *issued* is not enough: the TMA unit is not ordered behind the warp's LDS queue, and
+    // with several grids sharing the SMs a refill that hits in L2 was observed (about once per 10^6 refills) to land
+    // before a delayed LDS of the stage's last row had read it -- the lanes then saw the row 16 rows further down.
     if (rr == kRowsPerStage - 1 || i == s.nin - 1) {
-        __syncwarp();  // every lane has read this stage
+        __syncwarp();  // every lane has consumed this stage
         if (s.lane == 0 && st + kStages < s.nst) {
             mbar_arrive_expect_tx(&s.bars[slot], kStageElems * 8);
             tma_load_2d(s.ring + slot * kStageElems, s.tmap, s.boxcol, s.row0_padded + (st + kStages) * kRowsPerStage,
                         &s.bars[slot]);
         }
     }
-    push_row<FORM, PH>(x, A[0], w, wd);
 
     double v[4];
 #pragma unroll

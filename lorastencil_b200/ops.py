@@ -120,3 +120,8 @@ def set_gpus(k: int) -> int:
 def last_gpus() -> int:
     """GPUs (slabs) the last drop-in call actually ran on."""
     return int(_lib.lib().lora_last_gpus())
+
+
+def release_workspace() -> None:
+    """Free the device buffers the drop-in operators cache between calls."""
+    _lib.lib().lora_release_workspace()

@@ -277,3 +277,24 @@ def test_general_3d_effective_weights_equal_the_table_for_every_structure():
         for T in (sep, star, full):
             eff = ls.effective_weights("box3d1r", ls.WEIGHTS_GENERAL, T.reshape(-1)).reshape(3, 3, 3)
             assert np.abs(eff - T).max() <= 1e-12 * max(1.0, np.abs(T).max())
+
+
+def test_native_slab_partition_equals_the_python_mirror():
+    """lora_slab_geometry (csrc/slab.cu, what the multi-GPU drivers cut the grid with) against
+    lorastencil_b200.slab.SlabGeometry (what the CPU / gloo tests exercise): same bounds, ghost widths, local sizes; too
+    thin a slab is an error on both sides."""
+    import ctypes
+    from lorastencil_b200.slab import SlabGeometry
+    L = ls.lib()
+    out = (ctypes.c_longlong * 8)()
+    cases = [((1 << 28,), 8, 60), ((100003,), 3, 60), ((100000,), 4, 4), ((40960, 40960), 8, 4), ((10240, 10240), 4, 9),
+             ((300, 258), 2, 9), ((1024, 1024, 1024), 8, 1), ((33, 40, 136), 3, 1), ((512, 512, 512), 1, 1)]
+    for dims, world, ghost in cases:
+        d = (ctypes.c_longlong * 3)(*dims, *([0] * (3 - len(dims))))
+        for rank in range(world):
+            g = SlabGeometry(dims, world, rank, align=16 if len(dims) == 1 else 1, ghost=ghost)
+            assert L.lora_slab_geometry(len(dims), d, world, rank, ghost, out) == 0, L.lora_last_error()
+            assert (out[0], out[1], out[2], out[3], out[4]) == (g.lo, g.hi, g.wl, g.wr, g.off)
+            assert tuple(out[5:5 + len(dims)]) == tuple(g.local_dims)
+    d = (ctypes.c_longlong * 3)(40, 64, 0)
+    assert L.lora_slab_geometry(2, d, 8, 3, 9, out) != 0 and b"thinner" in L.lora_last_error()

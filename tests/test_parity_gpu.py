@@ -60,6 +60,9 @@ CASES = [
     ("box2d1r", (1024, 1024)),
     ("box3d1r", (16, 16, 64)), ("box3d1r", (5, 9, 30)), ("box3d1r", (70, 40, 136)), ("box3d1r", (1, 1, 2)),
     ("star3d1r", (16, 16, 64)), ("star3d1r", (7, 33, 132)), ("star3d1r", (64, 64, 64)),
+    # odd column counts: no 16-byte row pitch, so no tensor map -- the direct-tap kernels (stencil_direct.cu)
+    ("box2d3r", (50, 71)), ("star2d1r", (33, 129)), ("star2d3r", (300, 1)), ("box2d1r", (7, 1001)),
+    ("box3d1r", (5, 9, 31)), ("star3d1r", (7, 6, 5)), ("box3d1r", (33, 20, 257)),
 ]
 
 

@@ -34,7 +34,8 @@ def _devices(k):
 CASES = [("1d2r", (1 << 20,), 47, 2), ("1d1r", (100000,), 4, 3), ("1d2r", (40000,), 16, 4), ("box2d1r", (512, 640), 6, 2),
          ("box2d3r", (300, 258), 5, 3), ("star2d3r", (300, 258), 5, 2), ("star2d1r", (256, 256), 25, 4),
          ("star2d3r", (2048, 1024), 31, 8), ("star2d1r", (90, 70), 7, 3), ("box3d1r", (64, 64, 128), 5, 2),
-         ("star3d1r", (33, 40, 136), 4, 3), ("box3d1r", (96, 32, 64), 21, 8), ("star3d1r", (8, 20, 30), 6, 4)]
+         ("star3d1r", (33, 40, 136), 4, 3), ("box3d1r", (96, 32, 64), 21, 8), ("star3d1r", (8, 20, 30), 6, 4),
+         ("box2d3r", (120, 71), 5, 3), ("star2d3r", (64, 129), 4, 2), ("box3d1r", (12, 9, 31), 4, 3)]  # odd columns
 
 
 @pytest.mark.parametrize("shape,dims,times,k", CASES, ids=lambda v: v if isinstance(v, str) else str(v).replace(" ", ""))
@@ -51,7 +52,10 @@ def test_slabs_identical_to_single_gpu_and_oracle(shape, dims, times, k, monkeyp
     many = np.full_like(a, -7.0)
     ops.BY_SHAPE[shape](a, many, p, times, *dims)
     assert ops.last_gpus() == k
-    assert np.array_equal(many, one), (shape, dims, times, k)
+    if not np.array_equal(many, one):
+        bad = np.argwhere(many != one)
+        raise AssertionError((shape, dims, times, k, "first / last mismatching index", bad[0].tolist(), bad[-1].tolist(),
+                              "count", len(bad), "rows", sorted(set(bad[:, 0].tolist()))[:40]))
     ref = oracle.run(shape, a, oracle.effective_params(shape, p), times)
     if oracle.dim_of(shape) == 1:
         assert many[-1] == -7.0
