@@ -141,7 +141,9 @@ int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void
  * bit-identical to unfused launches, halo semantics (S2) included.  Default: 15 (the maximum) for the 1-D
  * shapes (or the environment variable LORA_TB).  2-D: 3 launches can be fused (tb >= 3 selects it, anything less
  * means one launch per step); default 3 for the cross and diamond forms, 1 for the FP64-bound pyramid / direct
- * forms (environment variable LORA_TB2=3|1).  3-D: always 1.  */
+ * forms (environment variable LORA_TB2=3|1).  For large cross / diamond grids the default is only provisional: the first
+ * lora_plan_run times 3 single launches against 1 fused sweep on a scratch grid of the same width and keeps the winner
+ * (cached per form, size and device; an explicit lora_plan_set_temporal_block or LORA_TB2 is final).  3-D: always 1.  */
 int lora_plan_set_temporal_block(lora_plan_t *plan, int tb);
 int lora_plan_temporal_block(const lora_plan_t *plan);
 
@@ -245,6 +247,9 @@ const char *lora_last_error(void);
  * lora_debug_tasks_2dtb: the warp tasks (strip, first row, rows) of one fused 2-D launch over rows [lo, hi) of an
  * m x n grid on a GPU with sm_count SMs, in launch order; returns the number of tasks. */
 int lora_debug_temporal_schedule(int times, int max_tb, int *blocks_out, int cap);
+/* what the last fused-or-not probe of a 2-D plan measured (milliseconds for 3 single launches / for 1 fused sweep of
+ * 3 on the scratch grid); returns the number of cached verdicts */
+int lora_debug_tb2_probe(double *ms_unfused3, double *ms_fused);
 int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int *strip_row_rows_out, int cap);
 
 /* ------------------------------------------------------------------------------------------

@@ -11,7 +11,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -19,6 +21,7 @@
 #include "../../include/lorastencil_dropin.hpp"
 #include "decompose.h"
 #include "exchange.h"
+#include "hostmove.h"
 #include "kernels.h"
 
 using namespace lora;
@@ -103,6 +106,7 @@ struct lora_plan {
     int slots = 148 * 16;  // concurrently resident warp workers (1-D / 2-D) or CTAs (3-D)
     int device = 0;
     int max_tb = 1;        // deepest temporal block lora_plan_run may fuse (1 = one launch per time step)
+    bool tb_auto = false;  // 2-D cross / diamond: max_tb is the form's default until lora_plan_run has measured both ways
     bool odd_cols = false; // 2-D / 3-D with an odd number of padded columns: no tensor map possible, direct-tap kernel
     WeightsDirect49 eff{}; // the effective direct taps (49, or 27 in 3-D) the chosen form equals
 };
@@ -228,7 +232,12 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 560 vs 335 GStencil/s unfused, diamond 387 vs
         // 327); the pyramid form is FP64-bound already and loses (223 vs 339), so it stays at one launch per step
         p->max_tb = (p->form == LORA_FORM_CROSS || p->form == LORA_FORM_DIAMOND) ? kTb2 : 1;
-        if (const char *e = getenv("LORA_TB2")) p->max_tb = (atoi(e) >= kTb2) ? kTb2 : 1;
+        // ... and where fusion is on by default, a large grid settles it by measurement on first use (probe_tb2)
+        p->tb_auto = p->max_tb == kTb2 && p->elems >= (1LL << 22) && p->dims[0] >= 512;
+        if (const char *e = getenv("LORA_TB2")) {
+            p->max_tb = (atoi(e) >= kTb2) ? kTb2 : 1;
+            p->tb_auto = false;
+        }
     }
     if (dim == 1) {
         p->max_tb = kDefaultTb1;
@@ -523,6 +532,7 @@ extern "C" int lora_plan_step_mirror(lora_plan_t *p, const double *src, double *
 
 extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
     if (!p || tb < 1) return fail(LORA_ERR_ARG, "bad argument");
+    p->tb_auto = false;  // an explicit choice is final
     if (p->dim == 1)
         p->max_tb = tb < kMaxTb1 ? tb : kMaxTb1;
     else if (p->dim == 2)
@@ -757,8 +767,89 @@ static int run_fused_1d(lora_plan *p, double *buf0, double *buf1, int times, int
     return LORA_OK;
 }
 
+// Fused or not?  The fused 2-D kernel runs at the edge of the register file (255 registers, 8 warps per SM), and
+// whether 3 launches per sweep beat 3 single launches has differed between boxes for the diamond form (387 vs 337
+// GStencil/s on one, 322 vs 330 on another).  So the first lora_plan_run of a large cross / diamond plan measures both
+// on a scratch grid of the same width (up to 3072 rows), keeps the winner and caches the verdict per (form, columns,
+// rows, device) for the life of the process.  Results are bit-identical either way.
+struct Tb2Key {
+    int form, device;
+    long long n, rows;
+    bool operator<(const Tb2Key &o) const {
+        return std::tie(form, device, n, rows) < std::tie(o.form, o.device, o.n, o.rows);
+    }
+};
+static std::mutex g_tb2_mutex;
+static std::map<Tb2Key, int> g_tb2_cache;
+static double g_tb2_last_ms[2] = {0, 0};  // what the last probe measured: {3 unfused launches, 1 fused sweep}
+
+extern "C" int lora_debug_tb2_probe(double *ms_unfused3, double *ms_fused) {
+    if (ms_unfused3) *ms_unfused3 = g_tb2_last_ms[0];
+    if (ms_fused) *ms_fused = g_tb2_last_ms[1];
+    return (int)g_tb2_cache.size();
+}
+
+static void probe_tb2(lora_plan *p) {
+    p->tb_auto = false;
+    const long long rows = p->dims[0] < 3072 ? p->dims[0] : 3072;
+    const Tb2Key key{p->form, p->device, p->dims[1], rows};
+    std::lock_guard<std::mutex> lk(g_tb2_mutex);
+    auto it = g_tb2_cache.find(key);
+    if (it != g_tb2_cache.end()) {
+        p->max_tb = it->second;
+        return;
+    }
+    lora_plan q = *p;  // same weights and form, fewer rows, no cached tensor maps
+    q.maps.clear();
+    q.maps1d.clear();
+    q.dims[0] = rows;
+    q.padded[0] = rows + 8;
+    q.elems = q.padded[0] * q.padded[1];
+    q.launches = 0;
+    double *b[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool ok = cudaMalloc(&b[0], (size_t)q.elems * 8) == cudaSuccess && cudaMalloc(&b[1], (size_t)q.elems * 8) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreate(&ev[0]) == cudaSuccess &&
+              cudaEventCreate(&ev[1]) == cudaSuccess && cudaMemsetAsync(b[0], 0, (size_t)q.elems * 8, st) == cudaSuccess &&
+              cudaMemsetAsync(b[1], 0, (size_t)q.elems * 8, st) == cudaSuccess;
+    float best[2] = {1e30f, 1e30f};
+    for (int rep = 0; ok && rep < 4; rep++) {  // rep 0 warms up
+        for (int fused = 0; ok && fused < 2; fused++) {
+            ok = cudaEventRecord(ev[0], st) == cudaSuccess;
+            if (fused) {
+                ok = ok && step_fused_2d(&q, b[0], b[1], b[0], 0, rows, kTb2, 0, 1, 1, nullptr, nullptr, st) == LORA_OK;
+            } else {
+                for (int i = 0; ok && i < kTb2; i++)
+                    ok = step_unfused(&q, b[i % 2], b[(i + 1) % 2], 0, rows, nullptr, nullptr, st) == LORA_OK;
+            }
+            ok = ok && cudaEventRecord(ev[1], st) == cudaSuccess && cudaEventSynchronize(ev[1]) == cudaSuccess;
+            float ms = 0;
+            ok = ok && cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess;
+            if (ok && rep > 0 && ms < best[fused]) best[fused] = ms;
+        }
+    }
+    if (ev[0]) cudaEventDestroy(ev[0]);
+    if (ev[1]) cudaEventDestroy(ev[1]);
+    if (st) cudaStreamDestroy(st);
+    if (b[0]) cudaFree(b[0]);
+    if (b[1]) cudaFree(b[1]);
+    if (!ok) {  // out of memory for the scratch grid, ...: keep the form's default, do not cache
+        cudaGetLastError();
+        return;
+    }
+    g_tb2_last_ms[0] = best[0];
+    g_tb2_last_ms[1] = best[1];
+    p->max_tb = best[1] < 0.98f * best[0] ? kTb2 : 1;
+    g_tb2_cache[key] = p->max_tb;
+}
+
 extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int times, void *stream) {
     if (!p || !buf0 || !buf1) return fail(LORA_ERR_ARG, "null argument");
+    if (p->tb_auto && times >= kTb2) {
+        if (int rc = check_device(p)) return rc;
+        probe_tb2(p);
+    }
     if (p->dim == 1 && p->max_tb > 1 && times > 1) return run_fused_1d(p, buf0, buf1, times, 1, 1, stream);
     double *buf[2] = {buf0, buf1};
     if (p->dim == 2 && p->max_tb == kTb2 && times >= kTb2) {
@@ -957,6 +1048,13 @@ static void ws_reserve(size_t count, size_t bytes) {
     }
 }
 
+// pinned staging + worker threads for pageable caller buffers (hostmove.h); created on first use, never destroyed
+// (its threads must not outlive-or-race the CUDA runtime's own teardown at exit)
+static HostMover &mover() {
+    static HostMover *m = new HostMover;
+    return *m;
+}
+
 static void print_banner(int shape, int dim, const long long *dims, int times, double loop_us) {
     double cells = 1;
     for (int i = 0; i < dim; i++) cells *= (double)dims[i];
@@ -1031,7 +1129,7 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
         cudaStream_t sc = s_comp[c % NCS];
         if (c >= NP) CU_DIE(cudaStreamWaitEvent(s_in, out_done[c - NP], 0));  // the pair's previous tenant has drained
         // S2 per chunk: buffer 0 <- the padded input segment, buffer 1 <- zeros
-        CU_DIE(cudaMemcpyAsync(b0, in + (lo - gl), bytes, cudaMemcpyHostToDevice, s_in));
+        CU_DIE(mover().h2d(b0, in + (lo - gl), bytes, s_in));  // pageable `in`: staged through pinned slots by worker threads
         CU_DIE(cudaMemsetAsync(b1, 0, bytes, s_in));
         CU_DIE(cudaEventRecord(in_done[c], s_in));
 
@@ -1053,10 +1151,11 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
         }
         if (c == K - 1) cnt += 3;
         CU_DIE(cudaStreamWaitEvent(s_out, comp_done[c], 0));
-        CU_DIE(cudaMemcpyAsync(out + dst_off, res + src_off, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+        CU_DIE(mover().d2h(out + dst_off, res + src_off, (size_t)cnt * sizeof(double), s_out));
         CU_DIE(cudaEventRecord(out_done[c], s_out));
     }
     CU_DIE(cudaStreamSynchronize(s_out));
+    CU_DIE(mover().finish());  // pageable `out`: the last staged pieces have been copied out
     for (auto &st : s_comp) CU_DIE(cudaStreamSynchronize(st));
     CU_DIE(cudaStreamSynchronize(s_in));
     // The reference's timed region is its launch loop (src/1d/gpu_1r.cu:118-126).  Here the chunks' launch loops
@@ -1092,6 +1191,155 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
     g_loop_ms = ms;
     g_chunks = (int)K;
     return true;
+}
+
+// the sweeps lora_plan_run would issue for `times` launches (temporal blocks; their count has the parity of `times`)
+static std::vector<int> plan_schedule(const lora_plan *p, int times) {
+    if (p->dim == 1 && p->max_tb > 1 && times > 1) return temporal_schedule(times, p->max_tb);
+    std::vector<int> tbs;
+    if (p->dim == 2 && p->max_tb == kTb2 && times >= kTb2) {
+        for (int left = times; left > 0;) {
+            const int tb = left >= kTb2 ? kTb2 : 1;
+            tbs.push_back(tb);
+            left -= tb;
+        }
+        return tbs;
+    }
+    tbs.assign(times, 1);
+    return tbs;
+}
+
+// one sweep of `tb` launches over interior range [lo, hi) of the outermost axis (sweep index k, `done` launches before it)
+static int sweep_range(lora_plan *p, double *buf0, double *buf1, int k, int tb, int done, long long lo, long long hi, void *stream) {
+    double *buf[2] = {buf0, buf1};
+    if (lo >= hi) return LORA_OK;
+    if (p->dim == 1 && (tb > 1 || p->max_tb > 1))
+        return lora_plan_step_fused(p, buf[k % 2], buf[(k + 1) % 2], buf0, lo, hi, tb, done, 1, 1, stream);
+    if (p->dim == 2 && tb > 1) return step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, lo, hi, tb, done, 1, 1, nullptr, nullptr, stream);
+    return lora_plan_step(p, buf[k % 2], buf[(k + 1) % 2], lo, hi, stream);
+}
+
+// The drop-in operator on one GPU with its copies OVERLAPPED with its launch loop (the reference does
+// cudaMemcpy -> launch loop -> cudaMemcpy back to back, src/2d/gpu.cu:396-421).  The padded grid is cut into K bands
+// along the outermost axis: the first sweep runs band by band as the bands arrive H2D (a band's rows can be swept once
+// the rows radius x tb below it are on the device), the sweeps in the middle run over the whole grid, and the last
+// sweep runs band by band again with every band's D2H copy queued behind it, so that only the first band's upload and
+// the last band's download are exposed.  Same launches on the same operands: results are bit-identical to the plain
+// sequence.  Pageable caller buffers are staged through pinned memory by worker threads (hostmove.h).
+static void run_host_pipelined(lora_plan *p, const double *in, double *out, int times) {
+    const size_t bytes = (size_t)p->elems * sizeof(double);
+    const long long rows = p->padded[0], rest = p->elems / p->padded[0];
+    const long long h0 = (p->padded[0] - p->dims[0]) / 2, n0 = p->dims[0];
+    static const int radius0[4] = {0, 4, 3, 1};
+    std::lock_guard<std::mutex> lk(g_ws_mutex);
+    ws_reserve(2, bytes);
+    double *b0 = g_ws[0], *b1 = g_ws[1];
+    if (p->tb_auto && times >= kTb2) probe_tb2(p);
+    const std::vector<int> tbs = plan_schedule(p, times);
+    const int nsweeps = (int)tbs.size();
+    long long K = (long long)(bytes >> 26);  // bands of about 64 MB
+    K = K < 1 ? 1 : (K > 16 ? 16 : K);
+    if (const char *e = getenv("LORA_BANDS")) {  // tuning knob; 1 = copy, loop, copy back to back
+        const long long v = atoll(e);
+        if (v >= 1 && v <= 64) K = v;
+    }
+    if (K > n0) K = n0;
+    cudaStream_t s_in, s_comp, s_out;
+    CU_DIE(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    CU_DIE(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    CU_DIE(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> in_done(K), comp_done(K);
+    for (long long k = 0; k < K; k++) {
+        CU_DIE(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
+        CU_DIE(cudaEventCreateWithFlags(&comp_done[k], cudaEventDisableTiming));
+    }
+    cudaEvent_t t_first, t_last;
+    CU_DIE(cudaEventCreate(&t_first));
+    CU_DIE(cudaEventCreate(&t_last));
+    // S2: buffer 1 <- zeros (its interior is overwritten by the first sweep; its halo ring must read as zero)
+    CU_DIE(cudaMemsetAsync(b1, 0, bytes, s_comp));
+    // interior ranges of the first sweep, one per uploaded band: what can be computed once padded rows < R are there
+    const long long reach = nsweeps ? (long long)radius0[p->dim] * tbs[0] : 0;
+    long long done_rows = 0, prev_hi = 0;
+    int launched = 0;
+    for (long long k = 0; k < K; k++) {
+        const long long R = (k == K - 1) ? rows : (rows * (k + 1) / K);
+        // S2: buffer 0 <- the padded input, halo included (src/2d/gpu.cu:396-400), band by band
+        size_t cnt = (size_t)(R - done_rows) * rest;
+        CU_DIE(mover().h2d(b0 + done_rows * rest, in + done_rows * rest, cnt * sizeof(double), s_in));
+        CU_DIE(cudaEventRecord(in_done[k], s_in));
+        done_rows = R;
+        if (nsweeps == 0) continue;
+        long long hi = (k == K - 1) ? n0 : R - h0 - reach;
+        hi = hi < prev_hi ? prev_hi : (hi > n0 ? n0 : hi);
+        CU_DIE(cudaStreamWaitEvent(s_comp, in_done[k], 0));
+        if (k == 0) CU_DIE(cudaEventRecord(t_first, s_comp));  // the first band is on the device: the launch loop starts
+        if (sweep_range(p, b0, b1, 0, tbs[0], 0, prev_hi, hi, s_comp) != LORA_OK) die_plan("launch");
+        if (nsweeps == 1) CU_DIE(cudaEventRecord(comp_done[k], s_comp));
+        prev_hi = hi;
+    }
+    launched = nsweeps ? tbs[0] : 0;
+    // the sweeps in the middle: whole grid
+    for (int k = 1; k + 1 < nsweeps; k++) {
+        if (sweep_range(p, b0, b1, k, tbs[k], launched, 0, n0, s_comp) != LORA_OK) die_plan("launch");
+        launched += tbs[k];
+    }
+    // the last sweep: band by band, every band's download queued behind it.  All launches are issued before the first
+    // D2H call, so a D2H that has to wait for a staging slot never delays a launch.
+    std::vector<long long> cut(K + 1, 0);
+    for (long long k = 0; k <= K; k++) cut[k] = n0 * k / K;
+    if (nsweeps >= 2) {
+        for (long long k = 0; k < K; k++) {
+            if (sweep_range(p, b0, b1, nsweeps - 1, tbs[nsweeps - 1], launched, cut[k], cut[k + 1], s_comp) != LORA_OK)
+                die_plan("launch");
+            CU_DIE(cudaEventRecord(comp_done[k], s_comp));
+        }
+    } else if (nsweeps == 1) {
+        // the single sweep ran in upload bands [.., hi_k): band k's rows of the result are final once comp_done[k] fired;
+        // download in the same bands
+        long long acc = 0;
+        for (long long k = 0; k < K; k++) {
+            const long long R = (k == K - 1) ? rows : (rows * (k + 1) / K);
+            long long hi = (k == K - 1) ? n0 : R - h0 - reach;
+            hi = hi < acc ? acc : (hi > n0 ? n0 : hi);
+            cut[k] = acc;
+            cut[k + 1] = hi;
+            acc = hi;
+        }
+    }
+    if (nsweeps == 0) CU_DIE(cudaEventRecord(t_first, s_comp));
+    CU_DIE(cudaEventRecord(t_last, s_comp));
+    // S3: the whole padded buffer times%2 comes back; 1-D leaves the last double alone (src/1d/gpu_1r.cu:134)
+    const double *res = (nsweeps % 2 == 0) ? b0 : b1;
+    for (long long k = 0; k < K; k++) {
+        long long r_lo = cut[k] + h0, r_hi = cut[k + 1] + h0;  // padded rows of the band's interior rows
+        if (k == 0) r_lo = 0;                                  // + the halo rows at either end of the grid
+        if (k == K - 1) r_hi = rows;
+        if (r_hi <= r_lo) continue;
+        size_t cnt = (size_t)(r_hi - r_lo) * rest;
+        if (p->dim == 1 && k == K - 1) cnt -= 1;
+        if (nsweeps >= 1) CU_DIE(cudaStreamWaitEvent(s_out, comp_done[k], 0));
+        else CU_DIE(cudaStreamWaitEvent(s_out, in_done[K - 1], 0));
+        CU_DIE(mover().d2h(out + r_lo * rest, res + r_lo * rest, cnt * sizeof(double), s_out));
+    }
+    CU_DIE(cudaStreamSynchronize(s_out));
+    CU_DIE(cudaStreamSynchronize(s_comp));
+    CU_DIE(cudaStreamSynchronize(s_in));
+    CU_DIE(mover().finish());
+    // the reference's timed region is its launch loop + sync (src/2d/gpu.cu:408-414); here it is the span from the
+    // first launch being issued to the last one finishing, which includes waiting for the bands of the first sweep
+    float ms = 0;
+    CU_DIE(cudaEventElapsedTime(&ms, t_first, t_last));
+    g_loop_ms = ms;
+    for (long long k = 0; k < K; k++) {
+        cudaEventDestroy(in_done[k]);
+        cudaEventDestroy(comp_done[k]);
+    }
+    cudaEventDestroy(t_first);
+    cudaEventDestroy(t_last);
+    cudaStreamDestroy(s_in);
+    cudaStreamDestroy(s_comp);
+    cudaStreamDestroy(s_out);
 }
 
 // how many GPUs the drop-in operators spread one call over: LORA_NGPU=k (default 1), or lora_set_gpus(k)
@@ -1183,26 +1431,8 @@ extern "C" void lora_gpu_run_host(int shape, int mode, const double *in, double 
     }
     lora_plan *p = nullptr;
     if (lora_plan_create(&p, shape, mode, params, dims) != LORA_OK) die_plan("plan");
-    const size_t bytes = (size_t)p->elems * sizeof(double);
-
-    std::lock_guard<std::mutex> lk(g_ws_mutex);
-    ws_reserve(2, bytes);
-    // S2: buffer 0 <- the whole padded input (halo included), buffer 1 <- zeros (src/2d/gpu.cu:396-400)
-    CU_DIE(cudaMemcpy(g_ws[0], in, bytes, cudaMemcpyHostToDevice));
-    CU_DIE(cudaMemset(g_ws[1], 0, bytes));
-    CU_DIE(cudaDeviceSynchronize());
-
-    // timed region of the reference: launch loop + device sync (src/2d/gpu.cu:408-414)
-    const clk::time_point t0 = clk::now();
-    if (lora_plan_run(p, g_ws[0], g_ws[1], times, nullptr) != LORA_OK) die_plan("launch");
-    CU_DIE(cudaDeviceSynchronize());
-    const clk::time_point t1 = clk::now();
-    const long long us = std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
-    g_loop_ms = us / 1e3;
-    if (verbose()) print_banner(shape, p->dim, p->dims, times, (double)us);
-    // S3: the whole padded buffer times%2 comes back; 1-D leaves the last double alone (src/1d/gpu_1r.cu:134)
-    const size_t back = (p->dim == 1) ? bytes - sizeof(double) : bytes;
-    CU_DIE(cudaMemcpy(out, g_ws[times % 2 == 0 ? 0 : 1], back, cudaMemcpyDeviceToHost));
+    run_host_pipelined(p, in, out, times);
+    if (verbose()) print_banner(shape, p->dim, p->dims, times, g_loop_ms * 1e3);
     lora_plan_destroy(p);
     g_total_ms = std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t_begin).count() / 1e3;
 }

@@ -419,3 +419,37 @@ def test_fused_2d_inner_strip_crossing_the_right_edge(shape):
     sub = np.ascontiguousarray(a[:60 + 8, -(300 + 8):])
     ref = oracle.run(shape, sub, oracle.effective_params(shape), 6)
     assert np.array_equal(results[1][4:4 + 30, -(4 + 200):-4], ref[4:4 + 30, -(4 + 200):-4])
+
+
+@pytest.mark.parametrize("shape,dims,times", [("box2d3r", (3000, 3072), 4), ("star2d3r", (2500, 4100), 7), ("star2d1r", (4096, 2048), 1),
+                                              ("box3d1r", (200, 256, 256), 5), ("star3d1r", (130, 200, 264), 2), ("1d2r", (3000000,), 9),
+                                              ("box2d1r", (4000, 2050), 0)])
+def test_copy_overlapped_operator_equals_plain_sequence(shape, dims, times, monkeypatch):
+    """The 2-D / 3-D drop-in operators upload band by band under the first sweep and download band by band behind
+    the last one (run_host_pipelined); pageable buffers go through pinned staging slots filled by worker threads
+    (hostmove.cu).  LORA_BANDS=1 is the plain copy -> launch loop -> copy sequence: same bits, for pageable (numpy) and
+    pinned (torch) caller buffers, halo rows included; and the oracle agrees."""
+    import torch
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 100, size=oracle.padded_shape(shape, dims)).astype(np.float64)
+    p = oracle.reference_params(shape)
+    monkeypatch.setenv("LORA_BANDS", "1")
+    monkeypatch.setenv("LORA_CHUNKS", "0")
+    plain = run_dropin(shape, a, p, times, dims)
+    outs = []
+    for bands in ("7", None):
+        if bands:
+            monkeypatch.setenv("LORA_BANDS", bands)
+        else:
+            monkeypatch.delenv("LORA_BANDS")
+        outs.append(run_dropin(shape, a, p, times, dims))
+        hin = torch.from_numpy(a).pin_memory()
+        hout = torch.full(a.shape, -7.0, dtype=torch.float64).pin_memory()
+        ops.BY_SHAPE[shape](hin, hout, p, times, *dims)
+        outs.append(hout.numpy().copy())
+    for o in outs:
+        assert np.array_equal(o, plain), (shape, dims, times)
+    if times in (1, 2):
+        ref = np.full_like(a, -7.0)
+        oracle.run(shape, a, oracle.effective_params(shape, p), times, out=ref)
+        assert np.array_equal(plain, ref)
