@@ -311,7 +311,8 @@ def measure_shape(torch, ls, ops, shape, dims, launches, hbm_gbs, device_index, 
             else:
                 hin, hout = src.numpy(), np.empty(padded, dtype=np.float64)
                 hout.fill(0.0)  # fault the pages in, as a caller that reuses its arrays would have
-            ops.BY_SHAPE[shape](hin, hout, params, times, *dims)  # warm: device workspace, page faults
+            for _ in range(2):  # warm: device workspace, page faults, pinned staging slots
+                ops.BY_SHAPE[shape](hin, hout, params, times, *dims)
             ts = []
             for _ in range(3):
                 torch.cuda.synchronize()
@@ -321,7 +322,7 @@ def measure_shape(torch, ls, ops, shape, dims, launches, hbm_gbs, device_index, 
             el = min(ts)
             row["e2e" if kind == "pinned" else "e2e_pageable"] = {
                 "value": cells * times / el / 1e9, "unit": "GStencil/s", "launches": times, "ms_per_call": el * 1e3,
-                "launch_loop_ms": ops.last_loop_ms(), "h2d_bytes_per_step": nel * 8, "d2h_bytes_per_step": nel * 8 - (8 if d == 1 else 0),
+                "launch_loop_ms": ops.last_loop_ms(), "bands": ops.last_bands(), "chunks": ops.last_chunks(), "h2d_bytes_per_step": nel * 8, "d2h_bytes_per_step": nel * 8 - (8 if d == 1 else 0),
                 "host_buffers": kind, "api": f"lorastencil_b200.ops.{ops.BY_SHAPE[shape].__name__} -> lora_{ops.BY_SHAPE[shape].__name__} (C ABI)"}
             del hin, hout
         del src

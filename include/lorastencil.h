@@ -101,6 +101,14 @@ double lora_last_total_ms(void);
  * disables the overlap, LORA_CHUNKS=k forces k chunks. */
 int lora_last_chunks(void);
 
+/* Every other drop-in call (2-D, 3-D, short 1-D lines) overlaps its copies with its launch loop too: the grid is cut
+ * into time-skewed bands along the outermost axis (sweep s of band k covers rows [B_k - s r, B_k+1 - s r), r = the
+ * reach of one sweep), so a band depends only on bands before it and runs all its sweeps as soon as it is uploaded
+ * while the next band uploads and the previous one downloads -- the same launches on the same operands, bit-identical
+ * results, no redundant work.  Pageable host buffers are staged through pinned memory by worker threads.  Returns how
+ * many bands the last call used (1 = copy -> launch loop -> copy).  Environment: LORA_BANDS=k forces k bands. */
+int lora_last_bands(void);
+
 /* free the device workspace the drop-in operators cache between calls */
 void lora_release_workspace(void);
 

@@ -18,7 +18,7 @@ WEIGHTS_GENERAL = 1
 C_ABI_SYMBOLS = (
     "lora_gpu_1d1r", "lora_gpu_1d2r", "lora_gpu_star_2d1r", "lora_gpu_star_2d3r", "lora_gpu_box_2d3r",
     "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
-    "lora_last_total_ms", "lora_last_chunks", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
+    "lora_last_total_ms", "lora_last_chunks", "lora_last_bands", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
     "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_set_temporal_block",
     "lora_plan_temporal_block", "lora_plan_step_fused", "lora_plan_step_mirror", "lora_plan_step_fused_mirror",
     "lora_peer_alloc", "lora_peer_free", "lora_peer_open", "lora_peer_close", "lora_stream_write_flag",
@@ -87,6 +87,7 @@ def lib() -> ctypes.CDLL:
     L.lora_last_loop_ms.restype = c_double
     L.lora_last_total_ms.restype = c_double
     L.lora_last_chunks.restype = c_int
+    L.lora_last_bands.restype = c_int
     L.lora_release_workspace.restype = None
     L.lora_plan_create.argtypes = [POINTER(c_void_p), c_int, c_int, dp, POINTER(c_longlong)]
     L.lora_plan_create.restype = c_int

@@ -968,6 +968,7 @@ extern "C" int lora_effective_weights(int shape, int mode, const double *params,
 static int g_verbose = -1;
 static double g_loop_ms = 0, g_total_ms = 0;
 static int g_chunks = 1;  // chunks the last drop-in call was cut into (1-D copy/compute overlap)
+static int g_bands = 1;   // time-skewed bands of the last call that took the band pipeline (run_host_pipelined)
 static std::mutex g_ws_mutex;
 static std::vector<double *> g_ws;  // device workspace the drop-in operators cache between calls (equal-sized buffers)
 static size_t g_ws_bytes = 0;
@@ -993,6 +994,7 @@ static bool verbose() {
 extern "C" double lora_last_loop_ms(void) { return g_loop_ms; }
 extern "C" double lora_last_total_ms(void) { return g_total_ms; }
 extern "C" int lora_last_chunks(void) { return g_chunks; }
+extern "C" int lora_last_bands(void) { return g_bands; }
 
 static void ws_free_locked() {
     for (double *b : g_ws)
@@ -1220,12 +1222,15 @@ static int sweep_range(lora_plan *p, double *buf0, double *buf1, int k, int tb, 
 }
 
 // The drop-in operator on one GPU with its copies OVERLAPPED with its launch loop (the reference does
-// cudaMemcpy -> launch loop -> cudaMemcpy back to back, src/2d/gpu.cu:396-421).  The padded grid is cut into K bands
-// along the outermost axis: the first sweep runs band by band as the bands arrive H2D (a band's rows can be swept once
-// the rows radius x tb below it are on the device), the sweeps in the middle run over the whole grid, and the last
-// sweep runs band by band again with every band's D2H copy queued behind it, so that only the first band's upload and
-// the last band's download are exposed.  Same launches on the same operands: results are bit-identical to the plain
-// sequence.  Pageable caller buffers are staged through pinned memory by worker threads (hostmove.h).
+// cudaMemcpy -> launch loop -> cudaMemcpy back to back, src/2d/gpu.cu:396-421).  The grid is cut into K bands along
+// the outermost axis and the bands are TIME-SKEWED: sweep s of band k covers rows [B_k - s r, B_k+1 - s r), r = the
+// widest reach of one sweep (radius x temporal block).  Band k then depends only on itself and on bands < k (what it
+// reads at sweep s was written at sweep s-1 by band k, or by band k-1 further up), and what it overwrites in the
+// ping-pong buffer is exactly what band k+1 no longer needs -- so every band can run ALL its sweeps as soon as it has
+// been uploaded, on one stream, band after band: same launches on the same operands as the plain sequence (results
+// bit-identical), not one redundant cell.  Band k+1 uploads while band k computes, band k-1 downloads; only the first
+// band's upload and the last band's download are exposed.  (A band's rows also stay L2-warm from sweep to sweep.)
+// Pageable caller buffers are staged through pinned memory by worker threads (hostmove.h).
 static void run_host_pipelined(lora_plan *p, const double *in, double *out, int times) {
     const size_t bytes = (size_t)p->elems * sizeof(double);
     const long long rows = p->padded[0], rest = p->elems / p->padded[0];
@@ -1236,107 +1241,84 @@ static void run_host_pipelined(lora_plan *p, const double *in, double *out, int 
     double *b0 = g_ws[0], *b1 = g_ws[1];
     if (p->tb_auto && times >= kTb2) probe_tb2(p);
     const std::vector<int> tbs = plan_schedule(p, times);
-    const int nsweeps = (int)tbs.size();
+    const int S = (int)tbs.size();
+    long long rmax = 0;
+    for (int tb : tbs) rmax = std::max(rmax, (long long)radius0[p->dim] * tb);
     long long K = (long long)(bytes >> 26);  // bands of about 64 MB
     K = K < 1 ? 1 : (K > 16 ? 16 : K);
     if (const char *e = getenv("LORA_BANDS")) {  // tuning knob; 1 = copy, loop, copy back to back
         const long long v = atoll(e);
         if (v >= 1 && v <= 64) K = v;
     }
-    if (K > n0) K = n0;
+    // the skew moves every band boundary S x rmax rows: keep it below half the grid, and bands wider than two reaches
+    if (S * rmax > n0 / 2) K = 1;
+    while (K > 1 && (n0 - S * rmax) / K < 2 * rmax + 1) K--;
+    // final (download) partition F_k is uniform; the initial boundaries sit S x rmax further down
+    std::vector<long long> B(K + 1, 0);
+    for (long long k = 1; k < K; k++) B[k] = std::min(n0, (n0 - S * rmax) * k / K + S * rmax);
+    B[K] = n0;
+    auto lo_of = [&](long long k, int s) { return k == 0 ? 0LL : std::max(0LL, B[k] - s * rmax); };
+    auto hi_of = [&](long long k, int s) { return k == K - 1 ? n0 : std::max(0LL, B[k + 1] - s * rmax); };
     cudaStream_t s_in, s_comp, s_out;
     CU_DIE(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
     CU_DIE(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
     CU_DIE(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> in_done(K), comp_done(K);
+    std::vector<cudaEvent_t> in_done(K), comp_done(K), t0(K);
     for (long long k = 0; k < K; k++) {
         CU_DIE(cudaEventCreateWithFlags(&in_done[k], cudaEventDisableTiming));
-        CU_DIE(cudaEventCreateWithFlags(&comp_done[k], cudaEventDisableTiming));
+        CU_DIE(cudaEventCreate(&comp_done[k]));  // timed: end of the band's launch loop
+        CU_DIE(cudaEventCreate(&t0[k]));         // timed: its start
     }
-    cudaEvent_t t_first, t_last;
-    CU_DIE(cudaEventCreate(&t_first));
-    CU_DIE(cudaEventCreate(&t_last));
     // S2: buffer 1 <- zeros (its interior is overwritten by the first sweep; its halo ring must read as zero)
     CU_DIE(cudaMemsetAsync(b1, 0, bytes, s_comp));
-    // interior ranges of the first sweep, one per uploaded band: what can be computed once padded rows < R are there
-    const long long reach = nsweeps ? (long long)radius0[p->dim] * tbs[0] : 0;
-    long long done_rows = 0, prev_hi = 0;
-    int launched = 0;
-    for (long long k = 0; k < K; k++) {
-        const long long R = (k == K - 1) ? rows : (rows * (k + 1) / K);
-        // S2: buffer 0 <- the padded input, halo included (src/2d/gpu.cu:396-400), band by band
-        size_t cnt = (size_t)(R - done_rows) * rest;
-        CU_DIE(mover().h2d(b0 + done_rows * rest, in + done_rows * rest, cnt * sizeof(double), s_in));
+    auto upload = [&](long long k) {  // S2: buffer 0 <- the padded input, halo included (src/2d/gpu.cu:396-400)
+        const long long u0 = k == 0 ? 0 : std::min(rows, B[k] + h0), u1 = k == K - 1 ? rows : std::min(rows, B[k + 1] + h0);
+        if (u1 > u0) CU_DIE(mover().h2d(b0 + u0 * rest, in + u0 * rest, (size_t)(u1 - u0) * rest * sizeof(double), s_in));
         CU_DIE(cudaEventRecord(in_done[k], s_in));
-        done_rows = R;
-        if (nsweeps == 0) continue;
-        long long hi = (k == K - 1) ? n0 : R - h0 - reach;
-        hi = hi < prev_hi ? prev_hi : (hi > n0 ? n0 : hi);
-        CU_DIE(cudaStreamWaitEvent(s_comp, in_done[k], 0));
-        if (k == 0) CU_DIE(cudaEventRecord(t_first, s_comp));  // the first band is on the device: the launch loop starts
-        if (sweep_range(p, b0, b1, 0, tbs[0], 0, prev_hi, hi, s_comp) != LORA_OK) die_plan("launch");
-        if (nsweeps == 1) CU_DIE(cudaEventRecord(comp_done[k], s_comp));
-        prev_hi = hi;
-    }
-    launched = nsweeps ? tbs[0] : 0;
-    // the sweeps in the middle: whole grid
-    for (int k = 1; k + 1 < nsweeps; k++) {
-        if (sweep_range(p, b0, b1, k, tbs[k], launched, 0, n0, s_comp) != LORA_OK) die_plan("launch");
-        launched += tbs[k];
-    }
-    // the last sweep: band by band, every band's download queued behind it.  All launches are issued before the first
-    // D2H call, so a D2H that has to wait for a staging slot never delays a launch.
-    std::vector<long long> cut(K + 1, 0);
-    for (long long k = 0; k <= K; k++) cut[k] = n0 * k / K;
-    if (nsweeps >= 2) {
-        for (long long k = 0; k < K; k++) {
-            if (sweep_range(p, b0, b1, nsweeps - 1, tbs[nsweeps - 1], launched, cut[k], cut[k + 1], s_comp) != LORA_OK)
-                die_plan("launch");
-            CU_DIE(cudaEventRecord(comp_done[k], s_comp));
-        }
-    } else if (nsweeps == 1) {
-        // the single sweep ran in upload bands [.., hi_k): band k's rows of the result are final once comp_done[k] fired;
-        // download in the same bands
-        long long acc = 0;
-        for (long long k = 0; k < K; k++) {
-            const long long R = (k == K - 1) ? rows : (rows * (k + 1) / K);
-            long long hi = (k == K - 1) ? n0 : R - h0 - reach;
-            hi = hi < acc ? acc : (hi > n0 ? n0 : hi);
-            cut[k] = acc;
-            cut[k + 1] = hi;
-            acc = hi;
-        }
-    }
-    if (nsweeps == 0) CU_DIE(cudaEventRecord(t_first, s_comp));
-    CU_DIE(cudaEventRecord(t_last, s_comp));
-    // S3: the whole padded buffer times%2 comes back; 1-D leaves the last double alone (src/1d/gpu_1r.cu:134)
-    const double *res = (nsweeps % 2 == 0) ? b0 : b1;
-    for (long long k = 0; k < K; k++) {
-        long long r_lo = cut[k] + h0, r_hi = cut[k + 1] + h0;  // padded rows of the band's interior rows
-        if (k == 0) r_lo = 0;                                  // + the halo rows at either end of the grid
+    };
+    const double *res = (S % 2 == 0) ? b0 : b1;
+    auto download = [&](long long k) {  // S3: padded buffer times%2; 1-D leaves the last double alone (src/1d/gpu_1r.cu:134)
+        long long r_lo = lo_of(k, S) + h0, r_hi = hi_of(k, S) + h0;
+        if (k == 0) r_lo = 0;           // + the halo rows at either end of the grid
         if (k == K - 1) r_hi = rows;
-        if (r_hi <= r_lo) continue;
+        if (r_hi <= r_lo) return;
         size_t cnt = (size_t)(r_hi - r_lo) * rest;
         if (p->dim == 1 && k == K - 1) cnt -= 1;
-        if (nsweeps >= 1) CU_DIE(cudaStreamWaitEvent(s_out, comp_done[k], 0));
-        else CU_DIE(cudaStreamWaitEvent(s_out, in_done[K - 1], 0));
+        CU_DIE(cudaStreamWaitEvent(s_out, comp_done[k], 0));
         CU_DIE(mover().d2h(out + r_lo * rest, res + r_lo * rest, cnt * sizeof(double), s_out));
+    };
+    upload(0);
+    for (long long k = 0; k < K; k++) {
+        if (k + 1 < K) upload(k + 1);  // in flight while band k computes (a pageable source blocks this thread only for
+                                       // the staging memcpy; band k-1's launches are still queued on the GPU meanwhile)
+        CU_DIE(cudaStreamWaitEvent(s_comp, in_done[k], 0));
+        CU_DIE(cudaEventRecord(t0[k], s_comp));
+        int launched = 0;
+        for (int s = 1; s <= S; s++) {
+            if (sweep_range(p, b0, b1, s - 1, tbs[s - 1], launched, lo_of(k, s), hi_of(k, s), s_comp) != LORA_OK) die_plan("launch");
+            launched += tbs[s - 1];
+        }
+        CU_DIE(cudaEventRecord(comp_done[k], s_comp));
+        if (k >= 1) download(k - 1);  // after band k's launches were queued: a wait for staging slots delays no launch
     }
+    download(K - 1);
     CU_DIE(cudaStreamSynchronize(s_out));
     CU_DIE(cudaStreamSynchronize(s_comp));
     CU_DIE(cudaStreamSynchronize(s_in));
     CU_DIE(mover().finish());
-    // the reference's timed region is its launch loop + sync (src/2d/gpu.cu:408-414); here it is the span from the
-    // first launch being issued to the last one finishing, which includes waiting for the bands of the first sweep
-    float ms = 0;
-    CU_DIE(cudaEventElapsedTime(&ms, t_first, t_last));
-    g_loop_ms = ms;
+    // the reference's timed region is its launch loop + sync (src/2d/gpu.cu:408-414): here the bands' launch loops,
+    // which run one after the other on one stream -- waiting for a band's upload is not in it
+    float total = 0;
     for (long long k = 0; k < K; k++) {
+        float ms = 0;
+        CU_DIE(cudaEventElapsedTime(&ms, t0[k], comp_done[k]));
+        total += ms;
         cudaEventDestroy(in_done[k]);
         cudaEventDestroy(comp_done[k]);
+        cudaEventDestroy(t0[k]);
     }
-    cudaEventDestroy(t_first);
-    cudaEventDestroy(t_last);
+    g_loop_ms = total;
+    g_bands = (int)K;
     cudaStreamDestroy(s_in);
     cudaStreamDestroy(s_comp);
     cudaStreamDestroy(s_out);
@@ -1415,6 +1397,7 @@ extern "C" void lora_gpu_run_host(int shape, int mode, const double *in, double 
     using clk = std::chrono::steady_clock;
     const clk::time_point t_begin = clk::now();
     g_chunks = 1;
+    g_bands = 1;
     g_last_gpus = 1;
     std::vector<int> devices;
     const int k = wanted_gpus(devices);

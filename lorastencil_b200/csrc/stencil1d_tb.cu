@@ -37,6 +37,10 @@ namespace {
 constexpr int kCpl = kTbCellsPerLane;  // 16
 constexpr int kRow = kTbRowCells;      // 512
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef LORA_TB_UNROLL
+#define LORA_TB_UNROLL 1
+#endif
+constexpr int kTbUnroll = LORA_TB_UNROLL;  // levels per iteration of the level loop (tuning experiments only)
 
 // virtual halo of one level: padded cells 0..3 and n+4..n+7 take (level time even ? caller's halo : 0)
 __device__ __forceinline__ void fix_halo(double (&v)[kCpl], long long X, int level, const Geom1DTB &g) {
@@ -80,7 +84,7 @@ __device__ __forceinline__ void sweep_row(const unsigned char *stage, double *ma
     const int TB = g.tb;
     // the level loop is deliberately NOT unrolled: one level is ~200 instructions, a fully unrolled row would
     // not fit the instruction cache (measured: 1349 -> 1431 GStencil/s at TB = 8 when rolled)
-#pragma unroll 1
+#pragma unroll(kTbUnroll)
     for (int s = 1; s <= TB; s++) {
         double win[kCpl + 8];
 #pragma unroll

@@ -125,3 +125,8 @@ def last_gpus() -> int:
 def release_workspace() -> None:
     """Free the device buffers the drop-in operators cache between calls."""
     _lib.lib().lora_release_workspace()
+
+
+def last_bands() -> int:
+    """Time-skewed bands the last drop-in call was cut into to overlap its copies with its launches (1 = none)."""
+    return int(_lib.lib().lora_last_bands())

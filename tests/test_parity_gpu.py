@@ -443,6 +443,7 @@ def test_copy_overlapped_operator_equals_plain_sequence(shape, dims, times, monk
         else:
             monkeypatch.delenv("LORA_BANDS")
         outs.append(run_dropin(shape, a, p, times, dims))
+        assert ops.last_bands() == (7 if bands else ops.last_bands())
         hin = torch.from_numpy(a).pin_memory()
         hout = torch.full(a.shape, -7.0, dtype=torch.float64).pin_memory()
         ops.BY_SHAPE[shape](hin, hout, p, times, *dims)
