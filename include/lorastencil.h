@@ -155,6 +155,16 @@ int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void
 int lora_plan_set_temporal_block(lora_plan_t *plan, int tb);
 int lora_plan_temporal_block(const lora_plan_t *plan);
 
+/* Boundary modes (new; the reference has exactly one).  LORA_BOUNDARY_REFERENCE: the reference's ping-pong -- no
+ * launch writes a halo cell, buffer 0 holds the caller's halo, buffer 1 zeros, so even launches see the caller's halo
+ * and odd launches a zero halo (S2: src/2d/gpu.cu:396-400, store offsets :106).  LORA_BOUNDARY_DIRICHLET: the caller's
+ * halo values are the boundary condition of EVERY launch (lora_plan_run copies the halo ring of buf0 into buf1 first).
+ * LORA_BOUNDARY_ZERO: zero halo for every launch (the ring of both buffers is cleared, buf0's included).  Applies to
+ * lora_plan_run / lora_plan_step*; the drop-in operators and the slab drivers always use REFERENCE. */
+enum { LORA_BOUNDARY_REFERENCE = 0, LORA_BOUNDARY_DIRICHLET = 1, LORA_BOUNDARY_ZERO = 2 };
+int lora_plan_set_boundary(lora_plan_t *plan, int mode);
+int lora_plan_boundary(const lora_plan_t *plan);
+
 /* One FUSED launch of `tb` time steps over interior range [lo, hi) of the outermost axis.
  * 2-D (tb = 1 or 3): rows [lo, hi); the ring of src must be the one its time parity calls for (caller's halo at even
  * `launches_before`, zeros at odd -- what the ping-pong gives when every sweep advances an odd number of steps),
@@ -272,8 +282,11 @@ enum {
     LORA_FORM_SEP3 = 5,       /* 3-D box: one rank-1 term a (x) b (x) c */
     LORA_FORM_STAR7 = 6,      /* 3-D star: 7 taps */
     LORA_FORM_DIRECT27 = 7,   /* 3-D: all 27 taps */
-    LORA_FORM_PYRAMID_PRUNED = 8 /* PYRAMID whose middle term is zero at offsets +-1 and whose centre remainder is
+    LORA_FORM_PYRAMID_PRUNED = 8, /* PYRAMID whose middle term is zero at offsets +-1 and whose centre remainder is
                                     zero (true for the reference's box table): those taps are not computed at all */
+    LORA_FORM_RANK2 = 9,      /* 2-D: sum of 2 rank-1 terms of full support 7 (LU / cross approximation with full
+                                 pivoting) -- any rank-2 table that is not pyramidal: 28 instead of 49 taps */
+    LORA_FORM_RANK3 = 10      /* 2-D: sum of 3 such terms: 42 taps */
 };
 
 typedef struct {

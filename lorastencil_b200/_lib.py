@@ -20,7 +20,7 @@ C_ABI_SYMBOLS = (
     "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
     "lora_last_total_ms", "lora_last_chunks", "lora_last_bands", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
     "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_set_temporal_block",
-    "lora_plan_temporal_block", "lora_plan_step_fused", "lora_plan_step_mirror", "lora_plan_step_fused_mirror",
+    "lora_plan_temporal_block", "lora_plan_set_boundary", "lora_plan_boundary", "lora_plan_step_fused", "lora_plan_step_mirror", "lora_plan_step_fused_mirror",
     "lora_peer_alloc", "lora_peer_free", "lora_peer_open", "lora_peer_close", "lora_stream_write_flag",
     "lora_stream_wait_flag_geq", "lora_debug_temporal_schedule", "lora_debug_tasks_2dtb", "lora_debug_tb2_probe", "lora_plan_launch_count", "lora_plan_describe",
     "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
@@ -103,6 +103,10 @@ def lib() -> ctypes.CDLL:
     L.lora_plan_set_temporal_block.restype = c_int
     L.lora_plan_temporal_block.argtypes = [c_void_p]
     L.lora_plan_temporal_block.restype = c_int
+    L.lora_plan_set_boundary.argtypes = [c_void_p, c_int]
+    L.lora_plan_set_boundary.restype = c_int
+    L.lora_plan_boundary.argtypes = [c_void_p]
+    L.lora_plan_boundary.restype = c_int
     L.lora_plan_step_fused.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int,
                                        c_int, c_int, c_void_p]
     L.lora_plan_step_fused.restype = c_int

@@ -145,6 +145,8 @@ struct Geom1DTB {
     int tb;                  // time steps fused by this launch (1..kMaxTb1)
     long long ntasks;
     int par0;                // parity of the launch count before level 0 (0: level 0 sees the caller's halo)
+    int par_mask;            // 1: the halo alternates caller's / zero from level to level (the reference, S2); 0: every
+                             // level sees what par0 says (fixed caller's halo = Dirichlet, or fixed zero)
     int virt_left, virt_right;  // this end of the array is an end of the global line: halo cells are virtual
     int use_tma;             // 0: array too small for the tensor maps, everything goes through plain accesses
     long long xcov;          // level-0 cells X >= xcov are not covered by the load map
@@ -183,6 +185,7 @@ struct Geom2DTB {
     int edge_rows, nedge;    // nstrips >= 3: the two edge strips run as 2 * nedge tasks of edge_rows (<= kEdgeRows2Tb) rows
     int ntasks;              // all segments
     int par0;                // parity of the launch count before level 0 (== parity of the source buffer)
+    int par_mask;            // 1: alternating halo (reference, S2); 0: every level sees what par0 says (Dirichlet / zero)
     int virt_top, virt_bot;  // rows beyond that end are the global halo ring (virtual halo), not neighbour-slab data
     int vec4;
 };

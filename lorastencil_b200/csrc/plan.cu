@@ -106,6 +106,7 @@ struct lora_plan {
     int slots = 148 * 16;  // concurrently resident warp workers (1-D / 2-D) or CTAs (3-D)
     int device = 0;
     int max_tb = 1;        // deepest temporal block lora_plan_run may fuse (1 = one launch per time step)
+    int boundary = LORA_BOUNDARY_REFERENCE;  // what the halo ring means from launch to launch (lora_plan_set_boundary)
     bool tb_auto = false;  // 2-D cross / diamond: max_tb is the form's default until lora_plan_run has measured both ways
     bool odd_cols = false; // 2-D / 3-D with an odd number of padded columns: no tensor map possible, direct-tap kernel
     WeightsDirect49 eff{}; // the effective direct taps (49, or 27 in 3-D) the chosen form equals
@@ -222,7 +223,8 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     // the per-warp TMA ring, and the registers of the pyramid / direct forms); planning the cheap forms for 16 --
     // i.e. more, shorter tasks than resident warps -- measured 8 % faster (dynamic CTA dispatch evens out the tail)
     int warps_per_sm =
-        (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_PYRAMID_PRUNED || p->form == LORA_FORM_DIRECT49) ? 12 : 16;
+        (p->form == LORA_FORM_PYRAMID || p->form == LORA_FORM_PYRAMID_PRUNED || p->form == LORA_FORM_DIRECT49 ||
+         p->form == LORA_FORM_RANK2 || p->form == LORA_FORM_RANK3) ? 12 : 16;
     if (const char *e = getenv("LORA_SLOTS_PER_SM")) {  // tuning knob
         const int v = atoi(e);
         if (v >= 1 && v <= 64) warps_per_sm = v;
@@ -330,6 +332,24 @@ static long long pick_len(long long total, long long lanes, long long slots, lon
         if (len <= max_len) return len < min_len ? min_len : len;
     }
     return max_len;
+}
+
+// 3-D plane chunks: a CTA streams its chunk of L planes through the tile (L + 2 plane loads, ~2 more plane times to
+// fill its pipeline), and CTAs run in waves of `slots` (one per SM).  Pick the chunk count that minimises
+// waves x (L + 4) among chunks of at most max_len planes: 512^3 -> 9 chunks of 57 (3.9 waves); a slab of 126 planes x
+// 256 tiles (1024^3 on 8 GPUs) -> 4 chunks of 32 (6.9 waves) instead of 2 chunks of 63 (3.5 waves: a quarter of the
+// last wave idle for 65 plane times).
+static long long pick_chunk_3d(long long planes, long long tiles, long long slots, long long max_len) {
+    long long best_len = planes < max_len ? planes : max_len, best_cost = -1;
+    for (long long c = 1; c <= planes; c++) {
+        const long long L = (planes + c - 1) / c;
+        if (L > max_len) continue;
+        if (L < 8 && c > 1) break;
+        const long long waves = (c * tiles + slots - 1) / slots;
+        const long long cost = waves * (L + 4);
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, best_len = L;
+    }
+    return best_len;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -494,7 +514,7 @@ static int step_unfused(lora_plan_t *p, const double *src, double *dst, long lon
         g.n = (int)p->dims[2];
         g.tiles_m = (g.m + k3TileRows - 1) / k3TileRows;
         g.tiles_n = (g.n + k3TileCols - 1) / k3TileCols;
-        long long max_planes = 64;
+        long long max_planes = 64;  // longer chunks lose: 1024^3 with 4 chunks of 256 planes ran at 364 GStencil/s, 16 x 64 at 389
         if (const char *e = getenv("LORA_MAX_PLANES_3D")) {  // tuning knob
             const long long v = atoll(e);
             if (v >= 2 && v <= 4096) max_planes = v;
@@ -502,8 +522,7 @@ static int step_unfused(lora_plan_t *p, const double *src, double *dst, long lon
         long long chunk[kMaxSegs], tasks[kMaxSegs];
         for (int i = 0; i < sc.n; i++) {
             const long long planes = sc.hi[i] - sc.lo[i];
-            chunk[i] = sc.band[i] ? planes
-                                  : pick_len(planes, (long long)g.tiles_m * g.tiles_n, p->slots, max_planes, max_planes < 8 ? max_planes : 8);
+            chunk[i] = sc.band[i] ? planes : pick_chunk_3d(planes, (long long)g.tiles_m * g.tiles_n, p->slots, max_planes);
             tasks[i] = (planes + chunk[i] - 1) / chunk[i];  // plane chunks (blockIdx.y); every chunk is tiles_m x tiles_n CTAs
         }
         fill_segs(g.sg, sc, chunk, tasks, (long long)g.tiles_m * g.tiles_n);
@@ -630,7 +649,8 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
     }
     fill_segs(g.sg, sc, chunk, tasks, 1);
     g.ntasks = (int)g.sg.first[sc.n];
-    g.par0 = launches_before & 1;
+    g.par0 = p->boundary == LORA_BOUNDARY_REFERENCE ? (launches_before & 1) : (p->boundary == LORA_BOUNDARY_ZERO ? 1 : 0);
+    g.par_mask = p->boundary == LORA_BOUNDARY_REFERENCE ? 1 : 0;
     g.virt_top = virt_lo ? 1 : 0;
     g.virt_bot = virt_hi ? 1 : 0;
     g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0) && sc.aligned4();
@@ -707,7 +727,8 @@ static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const
     fill_segs(g.sg, sc, chunk, tasks, 1);
     g.ntasks = g.sg.first[sc.n];
     g.tb = tb;
-    g.par0 = launches_before & 1;
+    g.par0 = p->boundary == LORA_BOUNDARY_REFERENCE ? (launches_before & 1) : (p->boundary == LORA_BOUNDARY_ZERO ? 1 : 0);
+    g.par_mask = p->boundary == LORA_BOUNDARY_REFERENCE ? 1 : 0;
     g.virt_left = virt_lo ? 1 : 0;
     g.virt_right = virt_hi ? 1 : 0;
     g.out_off = (16 - (4 * tb) % 16) % 16;
@@ -763,6 +784,49 @@ static int run_fused_1d(lora_plan *p, double *buf0, double *buf1, int times, int
                                       stream);
         if (rc) return rc;
         done += tbs[k];
+    }
+    return LORA_OK;
+}
+
+// ---- boundary modes (new).  The reference knows one behaviour: its kernels write the
+// interior only, buffer A starts as the caller's padded array and buffer B as zeros, so the halo a launch sees
+// alternates caller's / zero (S2).  DIRICHLET keeps the caller's halo values fixed for every launch, ZERO keeps a zero
+// halo: both ping-pong buffers then carry the same ring, and the fused kernels' virtual halo stops alternating.
+extern "C" int lora_plan_set_boundary(lora_plan_t *p, int mode) {
+    if (!p || (mode != LORA_BOUNDARY_REFERENCE && mode != LORA_BOUNDARY_DIRICHLET && mode != LORA_BOUNDARY_ZERO))
+        return fail(LORA_ERR_ARG, "bad boundary mode");
+    p->boundary = mode;
+    return LORA_OK;
+}
+extern "C" int lora_plan_boundary(const lora_plan_t *p) { return p ? p->boundary : -1; }
+
+// halo ring of dst <- halo ring of src (src == nullptr: zeros), everything outside the interior, nothing inside
+static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStream_t st) {
+    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
+    const int dim = p->dim;
+    const long long P0 = p->padded[0], rest = p->elems / P0, h0 = halo[dim][0];
+    auto flat = [&](long long off, long long cnt) -> cudaError_t {
+        if (cnt <= 0) return cudaSuccess;
+        return src ? cudaMemcpyAsync(dst + off, src + off, (size_t)cnt * 8, cudaMemcpyDeviceToDevice, st)
+                   : cudaMemsetAsync(dst + off, 0, (size_t)cnt * 8, st);
+    };
+    auto strided = [&](long long off, long long width, long long height, long long pitch) -> cudaError_t {
+        if (width <= 0 || height <= 0) return cudaSuccess;
+        return src ? cudaMemcpy2DAsync(dst + off, (size_t)pitch * 8, src + off, (size_t)pitch * 8, (size_t)width * 8, (size_t)height,
+                                       cudaMemcpyDeviceToDevice, st)
+                   : cudaMemset2DAsync(dst + off, (size_t)pitch * 8, 0, (size_t)width * 8, (size_t)height, st);
+    };
+    CU_TRY(flat(0, h0 * rest));                  // leading halo rows / planes (1-D: cells)
+    CU_TRY(flat((P0 - h0) * rest, h0 * rest));   // trailing ones
+    if (dim == 2) {
+        CU_TRY(strided(0, 4, P0, p->padded[1]));                  // left halo columns of every row
+        CU_TRY(strided(p->padded[1] - 4, 4, P0, p->padded[1]));   // right halo columns
+    } else if (dim == 3) {
+        const long long pitch = p->padded[2], plane = p->padded[1] * pitch;
+        CU_TRY(strided(0, 2 * pitch, P0, plane));                       // 2 leading halo rows of every plane
+        CU_TRY(strided(plane - 2 * pitch, 2 * pitch, P0, plane));       // 2 trailing halo rows
+        CU_TRY(strided(0, 4, P0 * p->padded[1], pitch));                // left halo columns of every row of every plane
+        CU_TRY(strided(pitch - 4, 4, P0 * p->padded[1], pitch));        // right halo columns
     }
     return LORA_OK;
 }
@@ -849,6 +913,13 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
     if (p->tb_auto && times >= kTb2) {
         if (int rc = check_device(p)) return rc;
         probe_tb2(p);
+    }
+    if (p->boundary != LORA_BOUNDARY_REFERENCE) {  // both buffers carry the same ring: the caller's, or zeros
+        if (int rc = check_device(p)) return rc;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (p->boundary == LORA_BOUNDARY_ZERO)
+            if (int rc = copy_ring(p, buf0, nullptr, st)) return rc;
+        if (int rc = copy_ring(p, buf1, p->boundary == LORA_BOUNDARY_ZERO ? nullptr : buf0, st)) return rc;
     }
     if (p->dim == 1 && p->max_tb > 1 && times > 1) return run_fused_1d(p, buf0, buf1, times, 1, 1, stream);
     double *buf[2] = {buf0, buf1};
@@ -1244,8 +1315,11 @@ static void run_host_pipelined(lora_plan *p, const double *in, double *out, int 
     const int S = (int)tbs.size();
     long long rmax = 0;
     for (int tb : tbs) rmax = std::max(rmax, (long long)radius0[p->dim] * tb);
-    long long K = (long long)(bytes >> 26);  // bands of about 64 MB
-    K = K < 1 ? 1 : (K > 16 ? 16 : K);
+    // few, large bands: every band is swept launch by launch, and launches over a few hundred rows fill the GPU badly
+    // (10240^2 x 100 launches: 12 bands -> 45 ms of launches, the whole grid at once 28 ms); about 200 MB per band, at
+    // most 6, leaves a quarter to a sixth of one copy exposed at either end
+    long long K = bytes < (128u << 20) ? 1 : (long long)((bytes + (100u << 20)) / (200u << 20));
+    K = K < 1 ? 1 : (K > 6 ? 6 : K);
     if (const char *e = getenv("LORA_BANDS")) {  // tuning knob; 1 = copy, loop, copy back to back
         const long long v = atoll(e);
         if (v >= 1 && v <= 64) K = v;

@@ -179,6 +179,7 @@ extern "C" int lora_slab_create(lora_slab_t **out, int shape, int mode, const do
     {
         lora_plan_t *probe = nullptr;
         long long d[3] = {64, 64, 64};
+        for (int i = 1; i < dim; i++) d[i] = global_dims[i];  // an odd column count rules fusion out: same columns as the grid
         int rc = lora_plan_create(&probe, shape, mode, params, d);
         if (rc) {
             delete s;

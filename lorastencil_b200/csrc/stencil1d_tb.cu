@@ -44,7 +44,7 @@ constexpr int kTbUnroll = LORA_TB_UNROLL;  // levels per iteration of the level 
 
 // virtual halo of one level: padded cells 0..3 and n+4..n+7 take (level time even ? caller's halo : 0)
 __device__ __forceinline__ void fix_halo(double (&v)[kCpl], long long X, int level, const Geom1DTB &g) {
-    const bool use_h = ((g.par0 + level) & 1) == 0;
+    const bool use_h = ((g.par0 + (level & g.par_mask)) & 1) == 0;
 #pragma unroll
     for (int q = 0; q < kCpl; q++) {
         const long long x = X + q;

@@ -100,7 +100,8 @@ __device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4
 
 template <int FORM>
 __global__ void __launch_bounds__(32 * kWarpsPerCta,
-                                  (FORM == LORA_FORM_PYRAMID || FORM == LORA_FORM_PYRAMID_PRUNED || FORM == LORA_FORM_DIRECT49) ? 3 : 4)
+                                  (FORM == LORA_FORM_PYRAMID || FORM == LORA_FORM_PYRAMID_PRUNED || FORM == LORA_FORM_DIRECT49 ||
+                                   FORM == LORA_FORM_RANK2 || FORM == LORA_FORM_RANK3) ? 3 : 4)
 k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2D g,
             const __grid_constant__ Weights2D w, const __grid_constant__ WeightsDirect49 wd) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -189,6 +190,8 @@ cudaError_t kernels_init_2d() {
     if ((e = opt_in<LORA_FORM_CROSS>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_DIAMOND>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_DIRECT49>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_RANK2>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_RANK3>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -200,6 +203,8 @@ cudaError_t launch_2d(int form, const CUtensorMap &tmap, const Geom2D &g, const 
         case LORA_FORM_CROSS: return launch_form<LORA_FORM_CROSS>(tmap, g, w, wd, s);
         case LORA_FORM_DIAMOND: return launch_form<LORA_FORM_DIAMOND>(tmap, g, w, wd, s);
         case LORA_FORM_DIRECT49: return launch_form<LORA_FORM_DIRECT49>(tmap, g, w, wd, s);
+        case LORA_FORM_RANK2: return launch_form<LORA_FORM_RANK2>(tmap, g, w, wd, s);
+        case LORA_FORM_RANK3: return launch_form<LORA_FORM_RANK3>(tmap, g, w, wd, s);
         default: return cudaErrorInvalidValue;
     }
 }

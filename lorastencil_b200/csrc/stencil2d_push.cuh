@@ -43,6 +43,25 @@ __device__ __forceinline__ void push_row(const double (&x)[12], double (&A)[NACC
                 }
             }
         }
+    } else if constexpr (FORM == LORA_FORM_RANK2 || FORM == LORA_FORM_RANK3) {
+        // sum of 2 / 3 rank-1 terms of full support (host: lowrank_lu): 14 FP64 operations per term and cell
+        constexpr int NT = FORM == LORA_FORM_RANK2 ? 2 : 3;
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                double h = w.horiz[t][0] * x[4 + q - 3];
+#pragma unroll
+                for (int dc = -2; dc <= 3; dc++) h = fma(w.horiz[t][3 + dc], x[4 + q + dc], h);
+#pragma unroll
+                for (int dr = -3; dr <= 3; dr++) {
+                    if (dr == -3 && t == 0)
+                        ACC(dr)[q] = w.vert[t][3 + dr] * h;  // birth of the output row 3 below
+                    else
+                        ACC(dr)[q] = fma(w.vert[t][3 + dr], h, ACC(dr)[q]);
+                }
+            }
+        }
     } else if constexpr (FORM == LORA_FORM_PYRAMID) {
 #pragma unroll
         for (int t = 0; t < 3; t++) {

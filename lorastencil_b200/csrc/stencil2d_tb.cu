@@ -49,7 +49,7 @@ struct SweepTB {
     bool col_edge;          // the strip has cells outside [0, n): intermediate levels need column patching
     bool hal_ok;            // ... and the task is short enough for its halo columns to be staged in s.hal
     bool virt_top, virt_bot;  // rows above 0 / below m are the global halo ring (virtual), not a neighbour slab's rows
-    int par0;               // time parity before level 0
+    int par0, par_mask;     // time parity before level 0; 1 = the halo alternates with the level (reference), 0 = fixed
     bool vec4;
 };
 
@@ -60,7 +60,7 @@ struct SweepTB {
 //     columns of all the task's rows were staged in shared memory when the task started (s.hal: 4 left + 4 right
 //     doubles per row), so the patch is a predicated LDS, not an L2 / DRAM round trip per row.
 __device__ __forceinline__ void patch_row(double (&v)[4], int i_row, int rho, int level, const SweepTB &s) {
-    const bool caller = ((s.par0 + level) & 1) == 0;  // warp-uniform: at even times the ring holds the caller's halo
+    const bool caller = ((s.par0 + (level & s.par_mask)) & 1) == 0;  // warp-uniform: at even times the ring holds the caller's halo
     const bool row_out = (s.virt_top && rho < 0) || (s.virt_bot && rho >= s.m);  // warp-uniform
     if (row_out) {
 #pragma unroll
@@ -256,6 +256,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.virt_top = g.virt_top != 0;
     s.virt_bot = g.virt_bot != 0;
     s.par0 = g.par0 & 1;
+    s.par_mask = g.par_mask & 1;
     s.vec4 = g.vec4 != 0;
     s.pitch = g.pitch;
     s.mirror = g.sg.mirror[seg];

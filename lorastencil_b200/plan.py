@@ -11,8 +11,9 @@ from . import _lib
 HALO = {1: (4,), 2: (4, 4), 3: (1, 2, 4)}  # S1: src/1d/main.cu:96, src/2d/main.cu:217-218, src/3d/main.cu:21-23
 MAX_TB_1D = 15     # deepest temporal block of the 1-D kernel (kMaxTb1 in csrc/kernels.h)
 DEFAULT_TB_1D = 15  # kDefaultTb1
+BOUNDARY_NAMES = ["reference", "dirichlet", "zero"]
 FORM_NAMES = {0: "taps9", 1: "cross", 2: "pyramid", 3: "diamond", 4: "direct49", 5: "sep3", 6: "star7", 7: "direct27",
-              8: "pyramid_pruned"}
+              8: "pyramid_pruned", 9: "rank2", 10: "rank3"}
 
 
 def _dp(a: np.ndarray):
@@ -104,6 +105,16 @@ class Plan:
     @temporal_block.setter
     def temporal_block(self, tb: int):
         _lib.check(_lib.lib().lora_plan_set_temporal_block(self._h, int(tb)), "lora_plan_set_temporal_block")
+
+    @property
+    def boundary(self) -> str:
+        """'reference' (the reference's alternating caller's / zero halo, S2), 'dirichlet' (the caller's halo is the
+        boundary condition of every launch) or 'zero' (zero halo for every launch)."""
+        return BOUNDARY_NAMES[int(_lib.lib().lora_plan_boundary(self._h))]
+
+    @boundary.setter
+    def boundary(self, mode: str):
+        _lib.check(_lib.lib().lora_plan_set_boundary(self._h, BOUNDARY_NAMES.index(mode)), "lora_plan_set_boundary")
 
     def step_fused(self, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream=None, mirror=None):
         """One fused launch of `tb` time steps: see lora_plan_step_fused in include/lorastencil.h.  ``mirror``: device

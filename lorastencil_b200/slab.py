@@ -199,7 +199,8 @@ class SlabRunner:
                 temporal_block = int(os.environ.get("LORA_TB", str(DEFAULT_TB_1D)))
             elif dim == 2 and not injected:
                 from .plan import Plan
-                temporal_block = Plan(shape, (16, 16), params=params, mode=mode).temporal_block  # 3 for star forms
+                # 3 for the star forms -- unless the column count is odd (no tensor map: direct-tap kernel, no fusion)
+                temporal_block = Plan(shape, (16, int(global_dims[1])), params=params, mode=mode).temporal_block
             else:
                 temporal_block = 1
         if dim == 1:

@@ -198,6 +198,9 @@ def _reconstruct_2d(d):
         row = d["horiz"][1].copy()
         row[3] = 0.0                                 # row arm, centre excluded
         T[3, :] += row
+    elif f in ("rank2", "rank3"):
+        for t in range(int(f[-1])):
+            T += np.outer(d["vert"][t], d["horiz"][t])
     elif f in ("pyramid", "pyramid_pruned"):
         for t in range(3):
             T += np.outer(d["vert"][t], d["horiz"][t])
@@ -223,7 +226,7 @@ def test_general_decomposition_reconstructs_random_tables_of_every_structure():
 
     @st.composite
     def tables(draw):
-        kind = draw(st.sampled_from(["cross", "pyramid", "diamond", "random"]))
+        kind = draw(st.sampled_from(["cross", "pyramid", "diamond", "lowrank", "random"]))
         T = np.zeros((7, 7))
         if kind == "cross":
             T[:, 3] = [draw(vals) for _ in range(7)]
@@ -235,6 +238,9 @@ def test_general_decomposition_reconstructs_random_tables_of_every_structure():
                 v[t:7 - t] = [draw(nz) for _ in range(7 - 2 * t)]
                 T += np.outer(u, v)
             T[3, 3] += draw(vals)
+        elif kind == "lowrank":  # rank 2 or 3, full support, no pyramidal structure: the LU / cross-approximation fallback
+            for _ in range(draw(st.integers(min_value=2, max_value=3))):
+                T += np.outer([draw(nz) for _ in range(7)], [draw(nz) for _ in range(7)])
         elif kind == "diamond":
             u, v = np.zeros(7), np.zeros(7)
             u[1:6] = [draw(nz) for _ in range(5)]

@@ -126,6 +126,9 @@ def test_general_mode_honours_every_weight():
     dia[3, 0] = 0.25
     dia[1, 1] = -3.0
     tables2.append(("diamond", dia.ravel()))
+    # rank 2 / rank 3 with full support and no pyramidal structure: the LU (cross approximation) fallback, 28 / 42 taps
+    for r in (2, 3):
+        tables2.append((f"rank{r}", sum(np.outer(rng.uniform(0.5, 1.5, 7), rng.standard_normal(7)) for _ in range(r)).ravel()))
     for form, w in tables2:
         assert ls.decompose_2d("box2d3r", w)["form"] == form
         out = np.zeros_like(a2)
