@@ -277,6 +277,11 @@ cudaError_t HostMover::d2h(void *dst_host, const void *src_dev, size_t bytes, cu
     return cudaSuccess;
 }
 
+HostMover &global_mover() {
+    static HostMover *m = new HostMover;
+    return *m;
+}
+
 cudaError_t HostMover::finish() {
     Impl &I = *impl_;
     std::unique_lock<std::mutex> lk(I.m);

@@ -35,4 +35,8 @@ class HostMover {
     Impl *impl_;
 };
 
+// the process-wide instance (created on first use, never destroyed: its threads must not race the CUDA runtime's own
+// teardown at exit)
+HostMover &global_mover();
+
 }  // namespace lora

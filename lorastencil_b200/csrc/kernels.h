@@ -80,7 +80,9 @@ struct Segs {
     long long lo[kMaxSegs], hi[kMaxSegs];    // segment ranges on the swept axis (the kernel's own coordinate)
     long long chunk[kMaxSegs];               // chunk length of the segment's tasks along that axis
     long long first[kMaxSegs + 1];           // segment s owns tasks (3-D: plane chunks) [first[s], first[s + 1])
-    long long mirror[kMaxSegs];              // != 0: every cell stored at out[x] is also stored at out[x + mirror]
+    long long mirror[kMaxSegs];              // != 0: cells of [mlo, mhi) stored at out[x] are also stored at out[x + mirror]
+    long long mlo[kMaxSegs], mhi[kMaxSegs];  // the mirrored part of the segment on the swept axis (default: all of it)
+    int early[kMaxSegs];                     // 3-D: arrive right after index mhi - 1 was stored, not at the end of the task
     unsigned long long *flag[kMaxSegs];      // nullptr, or the flag (peer memory) raised to `seq` when the segment is done
     unsigned long long *count[kMaxSegs];     // arrival counter of the segment (this GPU's memory, only ever grows)
     unsigned long long target[kMaxSegs];     // counter value that completes the segment in THIS launch

@@ -357,13 +357,16 @@ static long long pick_chunk_3d(long long planes, long long tiles, long long slot
 // ---------------------------------------------------------------------------------------------
 struct SegCut {
     int n = 0;
-    long long lo[kMaxSegs], hi[kMaxSegs], mirror[kMaxSegs];
+    long long lo[kMaxSegs], hi[kMaxSegs], mirror[kMaxSegs], mlo[kMaxSegs], mhi[kMaxSegs];
     unsigned long long *flag[kMaxSegs], *count[kMaxSegs], *arrived[kMaxSegs];
     bool band[kMaxSegs];
+    int early[kMaxSegs];
+    long long flag_tasks[kMaxSegs];  // >= 0: only this many tasks of the segment arrive on its flag (default: all)
     unsigned long long seq = 0;
     void add(long long a, long long b, long long mir, bool is_band, unsigned long long *f, unsigned long long *c,
              unsigned long long *arr) {
         lo[n] = a, hi[n] = b, mirror[n] = mir, band[n] = is_band, flag[n] = f, count[n] = c, arrived[n] = arr;
+        mlo[n] = a, mhi[n] = b, early[n] = 0, flag_tasks[n] = -1;
         n++;
     }
     bool aligned4() const {
@@ -403,8 +406,11 @@ static void fill_segs(Segs &sg, const SegCut &sc, const long long *chunk, const 
         sg.chunk[i] = chunk[i];
         sg.first[i + 1] = sg.first[i] + tasks[i];
         sg.mirror[i] = sc.mirror[i];
+        sg.mlo[i] = sc.mlo[i];
+        sg.mhi[i] = sc.mhi[i];
+        sg.early[i] = sc.early[i];
         if (sc.flag[i] && sc.count[i] && sc.arrived[i]) {
-            *sc.arrived[i] += (unsigned long long)(tasks[i] * arrivals_per_task);
+            *sc.arrived[i] += (unsigned long long)((sc.flag_tasks[i] >= 0 ? sc.flag_tasks[i] : tasks[i]) * arrivals_per_task);
             sg.flag[i] = sc.flag[i];
             sg.count[i] = sc.count[i];
             sg.target[i] = *sc.arrived[i];
@@ -503,8 +509,6 @@ static int step_unfused(lora_plan_t *p, const double *src, double *dst, long lon
         const CUtensorMap *tm;
         int rc = get_tmap(p, src, &tm);
         if (rc) return rc;
-        SegCut sc;
-        if ((rc = cut_segments(lo, hi, dst, ex, mirror_base, sc))) return rc;
         Geom3D g;
         g.out = dst;
         g.row_pitch = p->padded[2];
@@ -514,16 +518,42 @@ static int step_unfused(lora_plan_t *p, const double *src, double *dst, long lon
         g.n = (int)p->dims[2];
         g.tiles_m = (g.m + k3TileRows - 1) / k3TileRows;
         g.tiles_n = (g.n + k3TileCols - 1) / k3TileCols;
+        const long long tiles = (long long)g.tiles_m * g.tiles_n;
         long long max_planes = 64;  // longer chunks lose: 1024^3 with 4 chunks of 256 planes ran at 364 GStencil/s, 16 x 64 at 389
         if (const char *e = getenv("LORA_MAX_PLANES_3D")) {  // tuning knob
             const long long v = atoll(e);
             if (v >= 2 && v <= 4096) max_planes = v;
         }
+        SegCut sc;
         long long chunk[kMaxSegs], tasks[kMaxSegs];
-        for (int i = 0; i < sc.n; i++) {
-            const long long planes = sc.hi[i] - sc.lo[i];
-            chunk[i] = sc.band[i] ? planes : pick_chunk_3d(planes, (long long)g.tiles_m * g.tiles_n, p->slots, max_planes);
-            tasks[i] = (planes + chunk[i] - 1) / chunk[i];  // plane chunks (blockIdx.y); every chunk is tiles_m x tiles_n CTAs
+        const long long bl = ex && ex->band_lo > 0 ? ex->band_lo : 0, bh = ex && ex->band_hi > 0 ? ex->band_hi : 0;
+        const long long L = pick_chunk_3d(hi - lo, tiles, p->slots, max_planes);
+        const long long nchunks = (hi - lo + L - 1) / L, last_lo = lo + (nchunks - 1) * L;
+        if ((bl || bh) && nchunks >= 2 && bl <= L && bh <= hi - last_lo && !getenv("LORA_BAND_CHUNKS_3D")) {
+            // Bands FOLDED into the ordinary plane chunks: no extra CTAs.  The last chunk goes first in dispatch order --
+            // its last planes are the hi band, mirrored as they are stored, flag raised when its CTAs finish (one chunk
+            // time into the launch).  The first chunk comes next -- its first planes are the lo band, flag raised
+            // right after they are stored.  Then the chunks in between.
+            if ((bl && !ex->mirror_lo) || (bh && !ex->mirror_hi)) return fail(LORA_ERR_ARG, "exchange band without a mirror address");
+            sc.seq = ex->seq;
+            sc.add(last_lo, hi, bh ? (long long)(ex->mirror_hi - dst) : 0, false, bh ? ex->flag_hi : nullptr,
+                   bh ? ex->count_hi : nullptr, bh ? ex->arrived_hi : nullptr);
+            sc.mlo[0] = hi - bh, sc.mhi[0] = hi;
+            sc.add(lo, lo + L, bl ? (long long)(ex->mirror_lo - dst) : 0, false, bl ? ex->flag_lo : nullptr,
+                   bl ? ex->count_lo : nullptr, bl ? ex->arrived_lo : nullptr);
+            sc.mlo[1] = lo, sc.mhi[1] = lo + bl, sc.early[1] = 1;
+            if (nchunks > 2) sc.add(lo + L, last_lo, 0, false, nullptr, nullptr, nullptr);
+            for (int i = 0; i < sc.n; i++) {
+                chunk[i] = L;
+                tasks[i] = (sc.hi[i] - sc.lo[i] + L - 1) / L;
+            }
+        } else {
+            if ((rc = cut_segments(lo, hi, dst, ex, mirror_base, sc))) return rc;
+            for (int i = 0; i < sc.n; i++) {
+                const long long planes = sc.hi[i] - sc.lo[i];
+                chunk[i] = sc.band[i] ? planes : pick_chunk_3d(planes, tiles, p->slots, max_planes);
+                tasks[i] = (planes + chunk[i] - 1) / chunk[i];  // plane chunks (blockIdx.y); every chunk is tiles_m x tiles_n CTAs
+            }
         }
         fill_segs(g.sg, sc, chunk, tasks, (long long)g.tiles_m * g.tiles_n);
         g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0) && sc.aligned4();
@@ -1123,10 +1153,7 @@ static void ws_reserve(size_t count, size_t bytes) {
 
 // pinned staging + worker threads for pageable caller buffers (hostmove.h); created on first use, never destroyed
 // (its threads must not outlive-or-race the CUDA runtime's own teardown at exit)
-static HostMover &mover() {
-    static HostMover *m = new HostMover;
-    return *m;
-}
+static HostMover &mover() { return global_mover(); }
 
 static void print_banner(int shape, int dim, const long long *dims, int times, double loop_us) {
     double cells = 1;

@@ -31,6 +31,7 @@
 #include "../../include/lorastencil.h"
 #include "decompose.h"
 #include "exchange.h"
+#include "hostmove.h"
 #include "kernels.h"
 
 using namespace lora;
@@ -448,7 +449,7 @@ extern "C" int lora_slabset_load(lora_slabset_t *set, const double *in) {
         lora_slab *s = set->slabs[r];
         SL_TRY(cudaSetDevice(set->devices[r]));
         const long long row0 = s->g.lo + s->g.halo - s->g.wl;  // first global padded row this slab mirrors
-        SL_TRY(cudaMemcpyAsync(s->buf[0], in + row0 * s->g.rest, (size_t)s->elems * 8, cudaMemcpyHostToDevice, set->streams[r]));
+        SL_TRY(global_mover().h2d(s->buf[0], in + row0 * s->g.rest, (size_t)s->elems * 8, set->streams[r]));  // pageable: staged
         SL_TRY(cudaMemsetAsync(s->buf[1], 0, (size_t)s->elems * 8, set->streams[r]));
         lora_slab_reset(s);
     }
@@ -514,12 +515,13 @@ extern "C" int lora_slabset_store(lora_slabset_t *set, double *out) {
         if (r == set->ndev - 1) rows += g.halo;
         long long cnt = rows * g.rest;
         if (set->dim == 1 && r == set->ndev - 1) cnt -= 1;
-        SL_TRY(cudaMemcpyAsync(out + dst_row * g.rest, res + src_row * g.rest, (size_t)cnt * 8, cudaMemcpyDeviceToHost, set->streams[r]));
+        SL_TRY(global_mover().d2h(out + dst_row * g.rest, res + src_row * g.rest, (size_t)cnt * 8, set->streams[r]));
     }
     for (int r = 0; r < set->ndev; r++) {
         SL_TRY(cudaSetDevice(set->devices[r]));
         SL_TRY(cudaStreamSynchronize(set->streams[r]));
     }
+    SL_TRY(global_mover().finish());  // pageable `out`: the last staged pieces have been copied out
     if (cur >= 0) cudaSetDevice(cur);
     return LORA_OK;
 }

@@ -100,6 +100,11 @@ struct Sweep3D {
     int nin, warp, lane;
     int rows_left, cols_left;  // how many of the 4 micro-tile rows / columns exist
     bool vec4;
+    int hout;                  // interior plane index of the next plane to be stored
+    int mlo, mhi;              // planes [mlo, mhi) are stored a second time at + mirror (a neighbour slab's ghost planes)
+    int early_plane;           // >= 0: after this plane has been stored the CTA reports to the segment's flag (lo band)
+    const Segs *sg;
+    int seg;
 };
 
 template <int FORM, int PH>
@@ -157,7 +162,7 @@ __device__ __forceinline__ void plane_phase(int i, Sweep3D &s, double (&A)[3][4]
                     for (int q = 0; q < 4; q++)
                         if (q < s.cols_left) o[q] = done[r][q];
                 }
-                if (s.mirror != 0) {  // the same row into the neighbour slab's ghost plane (peer memory over NVLink)
+                if (s.mirror != 0 && s.hout >= s.mlo && s.hout < s.mhi) {  // the same row into the neighbour slab's ghost plane (NVLink)
                     double *om = o + s.mirror;
                     if (s.cols_left >= 4) {
                         if (s.vec4) {
@@ -175,6 +180,12 @@ __device__ __forceinline__ void plane_phase(int i, Sweep3D &s, double (&A)[3][4]
             }
         }
         s.optr += s.plane_pitch;
+        if (s.hout == s.early_plane) {  // CTA-uniform: the lo band is complete -- tell the neighbour now, not at the end
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) seg_arrive(*s.sg, s.seg);
+        }
+        s.hout++;
     }
 #pragma unroll
     for (int r = 0; r < 4; r++)
@@ -233,6 +244,13 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     s.row_pitch = g.row_pitch;
     s.plane_pitch = g.plane_pitch;
     s.mirror = g.sg.mirror[seg];
+    s.hout = h0;
+    s.mlo = (int)g.sg.mlo[seg];
+    s.mhi = (int)g.sg.mhi[seg];
+    const bool early = g.sg.flag[seg] != nullptr && g.sg.early[seg] != 0;
+    s.early_plane = early ? s.mhi - 1 : -1;
+    s.sg = &g.sg;
+    s.seg = seg;
     s.optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(r0 + 2) * g.row_pitch + 4 + c0;
 
     double A[3][4][4];
@@ -248,7 +266,7 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
         if (base + 1 < nin) plane_phase<FORM, 1>(base + 1, s, A, w);
         if (base + 2 < nin) plane_phase<FORM, 2>(base + 2, s, A, w);
     }
-    if (g.sg.flag[seg] != nullptr) {  // a band chunk: tell the neighbour once every CTA of the band has stored
+    if (g.sg.flag[seg] != nullptr && !early) {  // a band chunk: tell the neighbour once every CTA of the band has stored
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) seg_arrive(g.sg, seg);

@@ -35,7 +35,9 @@ CASES = [("1d2r", (1 << 20,), 47, 2), ("1d1r", (100000,), 4, 3), ("1d2r", (40000
          ("box2d3r", (300, 258), 5, 3), ("star2d3r", (300, 258), 5, 2), ("star2d1r", (256, 256), 25, 4),
          ("star2d3r", (2048, 1024), 31, 8), ("star2d1r", (90, 70), 7, 3), ("box3d1r", (64, 64, 128), 5, 2),
          ("star3d1r", (33, 40, 136), 4, 3), ("box3d1r", (96, 32, 64), 21, 8), ("star3d1r", (8, 20, 30), 6, 4),
-         ("box2d3r", (120, 71), 5, 3), ("star2d3r", (64, 129), 4, 2), ("box3d1r", (12, 9, 31), 4, 3)]  # odd columns
+         ("box2d3r", (120, 71), 5, 3), ("star2d3r", (64, 129), 4, 2), ("box3d1r", (12, 9, 31), 4, 3),  # odd columns
+         # enough planes per slab for several plane chunks: the bands are folded into the first / last chunk
+         ("box3d1r", (200, 64, 128), 5, 2), ("star3d1r", (150, 40, 136), 4, 3), ("box3d1r", (260, 32, 64), 7, 4)]
 
 
 @pytest.mark.parametrize("shape,dims,times,k", CASES, ids=lambda v: v if isinstance(v, str) else str(v).replace(" ", ""))
