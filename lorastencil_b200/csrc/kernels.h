@@ -170,7 +170,8 @@ struct Geom2D {
 constexpr int kTb2Max = 3;
 constexpr int kEdgeRows2Tb = 160;                          // longest edge-strip task (output rows)
 constexpr int kHalRows2Tb = kEdgeRows2Tb + 6 * kTb2Max;    // its input rows
-constexpr int kSmem2Tb = kSmem12 + kWarpsPerCta * kHalRows2Tb * 8 * 8;
+constexpr int kSmem2TbScratch = kSmem12 + kWarpsPerCta * kHalRows2Tb * 8 * 8;  // one scratch word per warp behind the staging area
+constexpr int kSmem2Tb = kSmem2TbScratch + 64;
 
 // temporally blocked 2-D sweep (stencil2d_tb.cu): TB (odd) launches fused; strips write 128 - 8 (TB - 1) columns
 struct Geom2DTB {

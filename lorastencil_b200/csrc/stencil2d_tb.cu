@@ -39,6 +39,7 @@ struct SweepTB {
     double *orow;           // output row pointer (this lane's first column), advances by pitch once rows retire
     const double *hsrc;     // caller's halo: padded buffer 0, pointing at (row 0, this lane's first column)
     const double *hal;      // shared memory: caller's halo columns of the task's rows, [nin][4 left + 4 right]
+    volatile int *scratch;  // shared memory: one word per warp (the guard store of the early refill)
     long long pitch, mirror;
     int nin, nst, boxcol, row0_padded, lane;
     int rho0;               // interior row of input row 0 of the chunk (= r0 - 3 TB)
@@ -106,13 +107,30 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
         x[2 * k] = v.x;
         x[2 * k + 1] = v.y;
     }
+    // Refilling a stage needs care: the TMA unit is NOT ordered behind the warp's LDS queue.  Issuing the refill right
+    // after the stage's last loads were *issued* (round 1) let a refill that hits in L2 land before a delayed LDS had
+    // read its row -- observed about once per 10^6 refills when several grids share the SMs (multi-GPU slabs on one
+    // device): the lanes then saw the row 16 rows further down.  Two safe orders:
+    //   * late: refill after the push -- the FP64 operations cannot issue before the LDS data is in the registers;
+    //   * early (cross form: +6.6 %, 450 -> 480 GStencil/s; the diamond form loses 11 % to extra spills): refill before
+    //     the push, but behind a shared-memory store of the XOR of every value of the row -- that store cannot issue
+    //     before the loads have completed, and the TMA is issued after it in program order.
+    constexpr bool kEarlyRefill = FORM == LORA_FORM_CROSS;
+    const bool refill_row = rr == kRowsPerStage - 1 || i == s.nin - 1;
+    if (kEarlyRefill && refill_row) {
+        int guard = 0;
+#pragma unroll
+        for (int k = 0; k < 12; k++) guard ^= __double2hiint(x[k]);
+        __syncwarp();  // every lane has its values of this stage
+        if (s.lane == 0 && st + kStages < s.nst) {
+            *s.scratch = guard;
+            mbar_arrive_expect_tx(&s.bars[slot], kStageElems * 8);
+            tma_load_2d(s.ring + slot * kStageElems, s.tmap, s.boxcol, s.row0_padded + (st + kStages) * kRowsPerStage,
+                        &s.bars[slot]);
+        }
+    }
     push_row<FORM, PH>(x, A[0], w, wd);
-    // Refill the stage only AFTER the push has consumed x[]: the FP64 operations cannot issue before the LDS data has
-    // arrived, so once every lane is past them (__syncwarp) no read of this stage is still in flight.  Issuing the TMA
-    // right after the loads were *issued* is not enough: the TMA unit is not ordered behind the warp's LDS queue, and
-    // with several grids sharing the SMs a refill that hits in L2 was observed (about once per 10^6 refills) to land
-    // before a delayed LDS of the stage's last row had read it -- the lanes then saw the row 16 rows further down.
-    if (rr == kRowsPerStage - 1 || i == s.nin - 1) {
+    if (!kEarlyRefill && refill_row) {
         __syncwarp();  // every lane has consumed this stage
         if (s.lane == 0 && st + kStages < s.nst) {
             mbar_arrive_expect_tx(&s.bars[slot], kStageElems * 8);
@@ -264,6 +282,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.hsrc = g.halo_src + 4 * g.pitch + 4 + s.c0;
     double *hal = reinterpret_cast<double *>(smem_raw + kSmem12) + warp * (kHalRows2Tb * 8);
     s.hal = hal;
+    s.scratch = reinterpret_cast<volatile int *>(smem_raw + kSmem2TbScratch) + 2 * warp;
     if (s.col_edge && s.hal_ok) {
         // stage the caller's halo columns (4 left of column 0, 4 right of column n-1) of the task's rows
         for (int idx = lane; idx < s.nin; idx += 32) {

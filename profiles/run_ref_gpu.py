@@ -2,7 +2,8 @@
 artifact recompile"), timed on the same B200 beside this library's operators -- same padded host arrays, same launch
 counts, each side's own timed region (the launch loop, as both print it in their banner).
 
-    python profiles/run_ref_gpu.py [--launches 21] > profiles/r1_ref_gpu_recompile.json
+    python profiles/run_ref_gpu.py [--launches 21] > profiles/r2_ref_gpu_recompile.json
+Both sides' outputs are compared as well (bit-identical while the integers stay exact, max relative error otherwise).
 Not part of bench.py: the reference binaries are test infrastructure (oracle/), this is a side-by-side report."""
 import argparse
 import json
@@ -54,15 +55,25 @@ for shape in args.shapes.split(","):
     a = rng.integers(0, 10, size=oracle.padded_shape(shape, dims)).astype(np.float64)
     p = oracle.reference_params(shape)
     out = np.zeros_like(a)
-    ref_txt = ""
+    ref_txt, ref_out = "", [None]
+
+    def run_ref():
+        ref_out[0] = oracle.ref_gpu_run(shape, a, p, args.launches)
     for _ in range(2):  # second call = warm
-        ref_txt = captured_stdout(lambda: oracle.ref_gpu_run(shape, a, p, args.launches))
+        ref_txt = captured_stdout(run_ref)
     our_txt = ""
     for _ in range(2):
         our_txt = captured_stdout(lambda: ops.BY_SHAPE[shape](a, out, p, args.launches, *dims))
+    # the two sides ran on the same input: compare what they returned (full padded output; 1-D leaves the last double)
+    got, want = (out[:-1], ref_out[0][:-1]) if len(dims) == 1 else (out, ref_out[0])
+    finite = np.isfinite(want)
+    scale = float(np.abs(want[finite]).max()) if finite.any() else 0.0
+    err = float(np.abs(got[finite] - want[finite]).max() / scale) if scale > 0 else 0.0
     r = {"shape": shape, "dims": list(dims), "launches": args.launches,
          "reference_sm100a_recompile_gstencils": banner_gstencils(ref_txt, shape),
-         "this_library_gstencils": banner_gstencils(our_txt, shape)}
+         "this_library_gstencils": banner_gstencils(our_txt, shape),
+         "outputs_bit_identical": bool(np.array_equal(got, want)), "max_rel_err_over_finite_cells": err,
+         "same_non_finite_cells": bool(np.array_equal(np.isfinite(got), finite))}
     if r["reference_sm100a_recompile_gstencils"] and r["this_library_gstencils"]:
         r["speedup"] = r["this_library_gstencils"] / r["reference_sm100a_recompile_gstencils"]
     rows.append(r)
