@@ -232,6 +232,16 @@ def time_cpu(shape, dims, min_seconds=15.0, max_launches=60, cores=None):
                       f"(of the job's launches), {el:.2f} s wall"}
 
 
+def cpu_baselines_in_a_clean_process(jobs):
+    """time_cpu for a list of (shape, dims, kwargs) in a child process that never touches CUDA or torch: inside the
+    GPU process (CUDA context, pinned allocations, staging / NVML threads) the same loop measured 2x slower."""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-jobs", json.dumps(jobs)], capture_output=True, text=True)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("[")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("cpu baseline child failed: " + r.stdout[-500:] + r.stderr[-500:])
+    return json.loads(lines[-1])
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -265,7 +275,7 @@ def device_fill(torch, shape_padded, mod, device, seed):
     return torch.randint(0, mod, shape_padded, generator=g, device=device).double()
 
 
-def measure_shape(torch, ls, ops, shape, dims, launches, hbm_gbs, device_index, reps=5, e2e=True, cpu=True):
+def measure_shape(torch, ls, ops, shape, dims, launches, hbm_gbs, device_index, reps=5, e2e=True, cpu=False):
     """One row of the per-shape table: device-resident GStencil/s (CUDA events, best and median of `reps`, NVML clocks
     sampled during the repetitions), e2e through the reference-facing operator (pinned and pageable host buffers),
     the reference's test_cpu on 1 core and on all host cores."""
@@ -439,7 +449,11 @@ def main():
     ap.add_argument("--shape", default=None, help="measure this shape instead of the headline 1d2r job")
     ap.add_argument("--dims", default=None, help="comma-separated interior sizes (per GPU if weak, global if strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-jobs", default=None, help=argparse.SUPPRESS)  # internal: cpu_baselines_in_a_clean_process
     args = ap.parse_args()
+    if args.cpu_jobs:
+        print(json.dumps([time_cpu(s_, tuple(d_), **kw) for s_, d_, kw in json.loads(args.cpu_jobs)]))
+        return
     if args.impl == "reference":
         return run_reference_arm(args)
     # libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout, so everything
@@ -689,9 +703,17 @@ def main():
     if extra is not None:
         line["scaling_extra"] = extra
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = time_cpu(shape, dims)
+        line["cpu_baseline"] = cpu_baselines_in_a_clean_process([(shape, list(dims), {})])[0]
     if world == 1 and not args.no_shapes:
         line["shapes"] = [measure_shape(torch, ls, ops, s, d, l, hbm_gbs, local) for s, d, l in SHAPE_TABLE]
+        if not args.no_cpu:  # the reference's test_cpu per shape: 1 core (as shipped) and all host cores
+            jobs = []
+            for s_, d_, _ in SHAPE_TABLE:
+                jobs.append((s_, list(d_), {"min_seconds": 1.0, "max_launches": 1, "cores": 1}))
+                jobs.append((s_, list(d_), {"min_seconds": 4.0, "max_launches": 8}))
+            res = cpu_baselines_in_a_clean_process(jobs)
+            for i, row in enumerate(line["shapes"]):
+                row["cpu_baseline"] = {"one_core": res[2 * i], "all_cores": res[2 * i + 1]}
         worst = min(line["shapes"], key=lambda r: r["roofline_frac"])
         line["worst_shape_frac"] = worst["roofline_frac"]
         line["worst_shape"] = worst["shape"]
