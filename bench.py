@@ -64,8 +64,8 @@ def headline_config():
 
 def measured_traffic(kernel_key):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    (profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         return json.load(open(path)).get(kernel_key)
     except (OSError, ValueError):
