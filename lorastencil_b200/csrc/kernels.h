@@ -62,6 +62,17 @@ constexpr int k3Smem = k3Stages * k3StageBytes + 2 * k3Stages * 8;
 constexpr int k3Warps = 8;
 constexpr int k3Threads = 32 * k3Warps;
 
+// ---- temporally blocked 3-D kernel (stencil3d_tb.cu): two launches per sweep ----
+// thread tile 24 rows x 128 columns (8 warps x 3 rows, lane = 4 columns); a CTA writes 22 x 120 cells of it
+constexpr int kT3Rm = 3;
+constexpr int kT3Rows = kT3Rm * k3Warps;
+constexpr int kT3OutRows = kT3Rows - 2;
+constexpr int kT3OutCols = k3TileCols - 8;
+constexpr int kT3BoxRows = kT3Rows + 2;
+constexpr int kT3StageBytes = ((kT3BoxRows * k3BoxCols * 8 + 127) / 128) * 128;
+constexpr int kT3EdgeBytes = 2 * k3Warps * 2 * k3TileCols * 8;  // first / last level-1 row of every warp, double-buffered
+constexpr int kT3Smem = k3Stages * kT3StageBytes + kT3EdgeBytes + 2 * k3Stages * 8;
+
 struct Weights1D {
     double w[9];
 };
@@ -258,6 +269,19 @@ cudaError_t launch_2d_tb(int form, int tb, const CUtensorMap &tmap, const Geom2D
                          const WeightsDirect49 &wd, cudaStream_t s);
 int strip_out_cols_2d_tb(int tb);
 cudaError_t launch_3d(int form, const CUtensorMap &tmap, const Geom3D &g, const Weights3D &w, cudaStream_t s);
+
+// fused 3-D sweep of two launches (stencil3d_tb.cu); tmap: boxes of k3BoxCols x kT3BoxRows x 1
+struct Geom3DTB {
+    double *out;
+    long long row_pitch, plane_pitch;
+    int h, m, n;
+    long long h_lo, h_hi;     // interior planes written by this launch
+    int planes_per_chunk;
+    int tiles_m, tiles_n;     // tiles of kT3OutRows x kT3OutCols
+    int vec4;
+};
+cudaError_t launch_3d_tb(int form, const CUtensorMap &tmap, const Geom3DTB &g, const Weights3D &w, cudaStream_t s);
+cudaError_t kernels_init_3d_tb();
 cudaError_t kernels_init();     // opt in to large dynamic shared memory once per process/device
 cudaError_t kernels_init_1d();
 cudaError_t kernels_init_1d_tb();

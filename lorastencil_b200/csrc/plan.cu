@@ -101,6 +101,7 @@ struct lora_plan {
         CUtensorMap map;
     };
     std::vector<Map1D> maps1d;  // 1-D line viewed as rows of 16 doubles starting at cell `off`, 128B swizzle
+    std::vector<std::pair<const void *, CUtensorMap>> maps3tb;  // 3-D, the fused kernel's box (kT3BoxRows rows)
     long long launches = 0;
     int sm_count = 148;
     int slots = 148 * 16;  // concurrently resident warp workers (1-D / 2-D) or CTAs (3-D)
@@ -112,6 +113,8 @@ struct lora_plan {
     WeightsDirect49 eff{}; // the effective direct taps (49, or 27 in 3-D) the chosen form equals
 };
 
+constexpr int kTb3 = 2;  // the 3-D temporal block (stencil3d_tb.cu)
+static bool tb3_form(int form) { return form == LORA_FORM_STAR7; }
 constexpr int kTb2 = 3;  // the 2-D temporal block (odd, so that time parity == buffer parity at every sweep)
 static bool tb2_form(int form) {
     return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID || form == LORA_FORM_PYRAMID_PRUNED;
@@ -241,6 +244,11 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
             p->tb_auto = false;
         }
     }
+    if (dim == 3 && tb3_form(p->form) && !p->odd_cols) {
+        // 3-D fusion (stencil3d_tb.cu): two launches per sweep for the 7-point form
+        p->max_tb = kTb3;
+        if (const char *e = getenv("LORA_TB3")) p->max_tb = (atoi(e) >= kTb3) ? kTb3 : 1;
+    }
     if (dim == 1) {
         p->max_tb = kDefaultTb1;
         if (const char *e = getenv("LORA_TB")) {
@@ -294,6 +302,31 @@ static int get_tmap(lora_plan *p, const double *src, const CUtensorMap **out) {
     return LORA_OK;
 }
 
+// 3-D fused sweeps: same tensor, boxes of k3BoxCols x kT3BoxRows x 1
+static int get_tmap3tb(lora_plan *p, const double *src, const CUtensorMap **out) {
+    for (auto &kv : p->maps3tb)
+        if (kv.first == src) {
+            *out = &kv.second;
+            return LORA_OK;
+        }
+    encode_tiled_fn enc = get_encode();
+    if (!enc) return fail(LORA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    if (reinterpret_cast<uintptr_t>(src) % 16) return fail(LORA_ERR_ARG, "source buffer must be 16-byte aligned");
+    CUtensorMap m;
+    cuuint64_t gdim[3] = {(cuuint64_t)p->padded[2], (cuuint64_t)p->padded[1], (cuuint64_t)p->padded[0]};
+    cuuint64_t gstr[2] = {(cuuint64_t)p->padded[2] * 8, (cuuint64_t)p->padded[2] * p->padded[1] * 8};
+    cuuint32_t box[3] = {(cuuint32_t)k3BoxCols, (cuuint32_t)kT3BoxRows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(src), gdim, gstr, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LORA_ERR_CUDA, "cuTensorMapEncodeTiled (fused 3-D box) failed with CUresult %d", (int)r);
+    if (p->maps3tb.size() >= 8) p->maps3tb.erase(p->maps3tb.begin());
+    p->maps3tb.emplace_back(src, m);
+    *out = &p->maps3tb.back().second;
+    return LORA_OK;
+}
+
 // 1-D temporal blocking: the padded line from cell `off` on as a (rows x 16) tensor, boxes of 32 rows = 512 cells
 // = one warp row, 128-byte swizzle (stencil1d_tb.cu).  Used for loads (off 0) and stores (off = -4 tb mod 16).
 static int get_tmap1d(lora_plan *p, const double *ptr, long long off, long long rows, CUtensorMap *out) {
@@ -339,14 +372,14 @@ static long long pick_len(long long total, long long lanes, long long slots, lon
 // waves x (L + 4) among chunks of at most max_len planes: 512^3 -> 9 chunks of 57 (3.9 waves); a slab of 126 planes x
 // 256 tiles (1024^3 on 8 GPUs) -> 4 chunks of 32 (6.9 waves) instead of 2 chunks of 63 (3.5 waves: a quarter of the
 // last wave idle for 65 plane times).
-static long long pick_chunk_3d(long long planes, long long tiles, long long slots, long long max_len) {
+static long long pick_chunk_3d(long long planes, long long tiles, long long slots, long long max_len, long long overhead = 4) {
     long long best_len = planes < max_len ? planes : max_len, best_cost = -1;
     for (long long c = 1; c <= planes; c++) {
         const long long L = (planes + c - 1) / c;
         if (L > max_len) continue;
         if (L < 8 && c > 1) break;
         const long long waves = (c * tiles + slots - 1) / slots;
-        const long long cost = waves * (L + 4);
+        const long long cost = waves * (L + overhead);
         if (best_cost < 0 || cost < best_cost) best_cost = cost, best_len = L;
     }
     return best_len;
@@ -587,7 +620,7 @@ extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
     else if (p->dim == 2)
         p->max_tb = (tb >= kTb2 && tb2_form(p->form) && !p->odd_cols) ? kTb2 : 1;  // 2-D fuses exactly 3 launches or none
     else
-        p->max_tb = 1;
+        p->max_tb = (tb >= kTb3 && tb3_form(p->form) && !p->odd_cols) ? kTb3 : 1;  // 3-D fuses exactly 2 launches or none
     return LORA_OK;
 }
 
@@ -861,6 +894,43 @@ static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStr
     return LORA_OK;
 }
 
+// 3-D fused launch of kTb3 = 2 time steps over interior planes [lo, hi): see stencil3d_tb.cu.  The source buffer's
+// halo ring must hold what an EVEN time calls for (the caller's halo): lora_plan_run arranges that.
+static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long lo, long long hi, void *stream) {
+    if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
+    if (p->dim != 3 || !tb3_form(p->form) || p->odd_cols)
+        return fail(LORA_ERR_UNSUPPORTED, "3-D temporal blocking fuses %d launches of the 7-point form (even column counts)", kTb3);
+    if (p->boundary == LORA_BOUNDARY_DIRICHLET)
+        return fail(LORA_ERR_UNSUPPORTED, "fused 3-D sweeps keep a zero halo at the intermediate level: not with a Dirichlet boundary");
+    if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
+    if (lo == hi) return LORA_OK;
+    if (int rc = check_device(p)) return rc;
+    const CUtensorMap *tm;
+    if (int rc = get_tmap3tb(p, src, &tm)) return rc;
+    Geom3DTB g{};
+    g.out = dst;
+    g.row_pitch = p->padded[2];
+    g.plane_pitch = p->padded[1] * p->padded[2];
+    g.h = (int)p->dims[0];
+    g.m = (int)p->dims[1];
+    g.n = (int)p->dims[2];
+    g.h_lo = lo;
+    g.h_hi = hi;
+    g.tiles_m = (g.m + kT3OutRows - 1) / kT3OutRows;
+    g.tiles_n = (g.n + kT3OutCols - 1) / kT3OutCols;
+    long long max_planes = 96;
+    if (const char *e = getenv("LORA_MAX_PLANES_3DTB")) {  // tuning knob
+        const long long v = atoll(e);
+        if (v >= 2 && v <= 4096) max_planes = v;
+    }
+    g.planes_per_chunk = (int)pick_chunk_3d(hi - lo, (long long)g.tiles_m * g.tiles_n, p->slots, max_planes, 6);
+    g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
+    cudaError_t e = launch_3d_tb(p->form, *tm, g, p->w3, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    p->launches++;
+    return LORA_OK;
+}
+
 // Fused or not?  The fused 2-D kernel runs at the edge of the register file (255 registers, 8 warps per SM), and
 // whether 3 launches per sweep beat 3 single launches has differed between boxes for the diamond form (387 vs 337
 // GStencil/s on one, 322 vs 330 on another).  So the first lora_plan_run of a large cross / diamond plan measures both
@@ -963,6 +1033,26 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
             if (rc) return rc;
             left -= tb;
         }
+        return LORA_OK;
+    }
+    if (p->dim == 3 && p->max_tb == kTb3 && times >= 2 * kTb3 && p->boundary != LORA_BOUNDARY_DIRICHLET) {
+        // Sweeps of 2 launches, an EVEN number of them, then the remaining 1..3 launches one by one.  A fused sweep
+        // starts at an even time and needs the caller's halo around its source: sweep k reads buf[k % 2], and buffer
+        // 1's ring holds zeros (S2) -- so the ring of buffer 0 is copied into buffer 1 before the first odd sweep and
+        // cleared again after the last one.  With an even number of sweeps the data is back in buffer 0, the single
+        // launches then see the rings they expect, and the result lands in buf[times % 2] (S3).
+        int a = times / kTb3;
+        a -= a % 2;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const bool zero_mode = p->boundary == LORA_BOUNDARY_ZERO;  // both rings are zero anyway
+        if (!zero_mode)
+            if (int rc = copy_ring(p, buf1, buf0, st)) return rc;
+        for (int k = 0; k < a; k++)
+            if (int rc = step_fused_3d(p, buf[k % 2], buf[(k + 1) % 2], 0, p->dims[0], stream)) return rc;
+        if (!zero_mode)
+            if (int rc = copy_ring(p, buf1, nullptr, st)) return rc;
+        for (int i = a * kTb3; i < times; i++)
+            if (int rc = lora_plan_step(p, buf[i % 2], buf[(i + 1) % 2], 0, p->dims[0], stream)) return rc;
         return LORA_OK;
     }
     for (int i = 0; i < times; i++) {

@@ -312,6 +312,7 @@ cudaError_t kernels_init() {
     if ((e = kernels_init_1d_tb()) != cudaSuccess) return e;
     if ((e = kernels_init_2d()) != cudaSuccess) return e;
     if ((e = kernels_init_2d_tb()) != cudaSuccess) return e;
+    if ((e = kernels_init_3d_tb()) != cudaSuccess) return e;
     return kernels_init_3d();
 }
 

@@ -457,3 +457,48 @@ def test_copy_overlapped_operator_equals_plain_sequence(shape, dims, times, monk
         ref = np.full_like(a, -7.0)
         oracle.run(shape, a, oracle.effective_params(shape, p), times, out=ref)
         assert np.array_equal(plain, ref)
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 64), (40, 50, 130), (7, 33, 132), (64, 64, 64), (30, 22, 120), (33, 23, 122), (5, 100, 400),
+                                  (3, 3, 4), (70, 40, 250)])
+def test_temporal_blocking_3d_equals_unfused_launches(dims):
+    """3-D sweeps of 2 fused launches (star3d1r; level 1 handed on in registers, by warp shuffles and through two
+    shared-memory rows per warp; overlapped 22 x 120 tiles; zero halo at the intermediate level, the caller's ring
+    copied into buffer 1 for the odd sweeps and cleared afterwards) give the same bits as one launch per step, match
+    the oracle, and leave both halo rings as the reference's ping-pong would."""
+    import torch
+    shape = "star3d1r"
+    a = oracle.fill_rand(shape, dims)
+    rng = np.random.default_rng(sum(dims))
+    af = rng.uniform(-1, 1, a.shape)
+    eff = oracle.effective_params(shape)
+    plan = ls.Plan(shape, dims)
+    assert plan.temporal_block == 2
+    inner = interior(shape, dims)
+    for data in (a, af):
+        for times in (4, 5, 6, 7, 8, 9, 12, 15):
+            results = []
+            for tb in (1, 2):
+                plan.temporal_block = tb
+                assert plan.temporal_block == tb
+                b0, b1 = torch.from_numpy(data).cuda(), plan.new_buffer()
+                n0 = plan.launches
+                res = plan.run(b0, b1, times)
+                torch.cuda.synchronize()
+                assert res is (b0 if times % 2 == 0 else b1)
+                fused_sweeps = (times // 2) - (times // 2) % 2
+                assert plan.launches - n0 == (times if tb == 1 else fused_sweeps + times - 2 * fused_sweeps)
+                results.append(res.cpu().numpy())
+                # the rings: buffer 0 still holds the caller's halo, buffer 1 zeros
+                h0, h1 = b0.cpu().numpy().copy(), b1.cpu().numpy().copy()
+                d_h = data.copy()
+                h0[inner] = 0.0
+                d_h[inner] = 0.0
+                h1[inner] = 0.0
+                assert np.array_equal(h0, d_h) and not h1.any()
+            assert np.array_equal(results[0], results[1]), (dims, times)  # same operation order => same bits
+            ref = oracle.run(shape, data, eff, times)
+            if data is a and times <= 15:
+                assert np.array_equal(results[1], ref), (dims, times)
+            else:
+                assert max_rel_err(results[1], ref) <= RTOL, (dims, times)
