@@ -114,7 +114,7 @@ struct lora_plan {
 };
 
 constexpr int kTb3 = 2;  // the 3-D temporal block (stencil3d_tb.cu)
-static bool tb3_form(int form) { return form == LORA_FORM_STAR7; }
+static bool tb3_form(int form) { return form == LORA_FORM_STAR7 || form == LORA_FORM_SEP3; }
 constexpr int kTb2 = 3;  // the 2-D temporal block (odd, so that time parity == buffer parity at every sweep)
 static bool tb2_form(int form) {
     return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID || form == LORA_FORM_PYRAMID_PRUNED;
@@ -899,7 +899,7 @@ static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStr
 static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long lo, long long hi, void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
     if (p->dim != 3 || !tb3_form(p->form) || p->odd_cols)
-        return fail(LORA_ERR_UNSUPPORTED, "3-D temporal blocking fuses %d launches of the 7-point form (even column counts)", kTb3);
+        return fail(LORA_ERR_UNSUPPORTED, "3-D temporal blocking fuses %d launches of the 7-point and separable forms (even column counts)", kTb3);
     if (p->boundary == LORA_BOUNDARY_DIRICHLET)
         return fail(LORA_ERR_UNSUPPORTED, "fused 3-D sweeps keep a zero halo at the intermediate level: not with a Dirichlet boundary");
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);

@@ -52,11 +52,46 @@ __device__ __forceinline__ double star_inplane(const Weights3D &w, double c, dou
     return v;
 }
 
+// separable 27-point operator a (x) b (x) c, one level, with the window delivered row by row (only one window row is
+// live at a time): s = c * row along n, t = b * s along m, then the two carried plane accumulators -- the operation
+// order of stencil3d.cu's SEP3 push.  rowfn(rr, row): window row rr (region row RM*warp - 1 + rr), row[j] = column
+// 4*lane - 2 + j; only row[1..6] are read.
+template <class RowFn>
+__device__ __forceinline__ void sep3_level(const Weights3D &w, RowFn rowfn, LevelState &L, double (&out)[RM][4]) {
+    double t[RM][4];
+#pragma unroll
+    for (int rr = 0; rr < RM + 2; rr++) {
+        double row[8];
+        rowfn(rr, row);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            double s = w.c[0] * row[q + 1];
+            s = fma(w.c[1], row[q + 2], s);
+            s = fma(w.c[2], row[q + 3], s);
+#pragma unroll
+            for (int r = 0; r < RM; r++) {
+                const int dr = rr - 1 - r;  // row rr is the dr neighbour of micro-tile row r
+                if (dr == -1) t[r][q] = w.b[0] * s;
+                else if (dr == 0) t[r][q] = fma(w.b[1], s, t[r][q]);
+                else if (dr == 1) t[r][q] = fma(w.b[2], s, t[r][q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RM; r++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            out[r][q] = fma(w.a[2], t[r][q], L.full[r][q]);      // this plane is h+1 of the plane that completes
+            L.full[r][q] = fma(w.a[1], t[r][q], L.next[r][q]);   // and h of the next one
+            L.next[r][q] = fma(w.a[0], t[r][q], 0.0);            // and h-1 of the one after
+        }
+}
+
 template <int FORM>
 __global__ void __launch_bounds__(k3Threads, 1)
 k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom3DTB g,
                const __grid_constant__ Weights3D w) {
-    static_assert(FORM == LORA_FORM_STAR7, "fused 3-D sweeps are built for the 7-point form");
+    static_assert(FORM == LORA_FORM_STAR7 || FORM == LORA_FORM_SEP3, "fused 3-D sweeps: 7-point and separable forms");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double *edge = reinterpret_cast<double *>(smem_raw + k3Stages * kT3StageBytes);  // [2][k3Warps][2][k3TileCols]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + k3Stages * kT3StageBytes + kT3EdgeBytes);
@@ -107,49 +142,71 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; q++) L1.full[r][q] = L1.next[r][q] = L2.full[r][q] = L2.next[r][q] = 0.0;
 
-    for (int i = 0; i < nin; i++) {
-        // ---- level 0 -> level 1: plane q = h0 - 2 + i arrives, level-1 plane q - 1 completes
-        const int slot = i % k3Stages;
-        mbar_wait(&full[slot], (i / k3Stages) & 1);
-        const double *tile = reinterpret_cast<const double *>(smem_raw + slot * kT3StageBytes);
-        double X[RM + 2][8];  // rows RM*warp-1 .. RM*warp+RM, columns 4*lane-2 .. 4*lane+5 (region coordinates)
-#pragma unroll
-        for (int rr = 0; rr < RM + 2; rr++) {
-            const double2 *rowp = reinterpret_cast<const double2 *>(tile + (RM * warp + rr) * k3BoxCols + 4 * lane);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if ((rr == 0 || rr == RM + 1) && (k == 0 || k == 3)) continue;  // corners are not part of a star
-                const double2 v = rowp[k];
-                X[rr][2 * k] = v.x;
-                X[rr][2 * k + 1] = v.y;
-            }
-        }
+    // consumer release + producer duty (as in stencil3d.cu): the stage's values are in registers
+    auto release_stage = [&](int i, int slot) {
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&empty[slot]);  // this warp no longer needs the stage
             const int nx = i - 1 + k3Stages;
-            if (warp == 0 && i >= 1 && nx < nin) {  // producer duty: refill the slot every warp released one plane ago
+            if (warp == 0 && i >= 1 && nx < nin) {  // refill the slot every warp released one plane ago
                 const int ps = (i - 1) % k3Stages;
                 mbar_wait(&empty[ps], ((i - 1) / k3Stages) & 1);
                 mbar_arrive_expect_tx(&full[ps], kT3BoxRows * k3BoxCols * 8);
                 tma_load_3d(smem_raw + ps * kT3StageBytes, &tmap, box_c, box_r, box_h + nx, &full[ps]);
             }
         }
+    };
+
+    for (int i = 0; i < nin; i++) {
+        // ---- level 0 -> level 1: plane q = h0 - 2 + i arrives, level-1 plane q - 1 completes
+        const int slot = i % k3Stages;
+        mbar_wait(&full[slot], (i / k3Stages) & 1);
+        const double *tile = reinterpret_cast<const double *>(smem_raw + slot * kT3StageBytes);
         const int j1 = h0 - 3 + i;  // the level-1 plane that completes now
         const bool plane1_in = j1 >= 0 && j1 < g.h;
         double V[RM][4];
+        if constexpr (FORM == LORA_FORM_STAR7) {
+            double X[RM + 2][8];  // rows RM*warp-1 .. RM*warp+RM, columns 4*lane-2 .. 4*lane+5 (region coordinates)
+#pragma unroll
+            for (int rr = 0; rr < RM + 2; rr++) {
+                const double2 *rowp = reinterpret_cast<const double2 *>(tile + (RM * warp + rr) * k3BoxCols + 4 * lane);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if ((rr == 0 || rr == RM + 1) && (k == 0 || k == 3)) continue;  // corners are not part of a star
+                    const double2 v = rowp[k];
+                    X[rr][2 * k] = v.x;
+                    X[rr][2 * k + 1] = v.y;
+                }
+            }
+            release_stage(i, slot);
+#pragma unroll
+            for (int r = 0; r < RM; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double xc = X[r + 1][q + 2];
+                    const double v = star_inplane(w, xc, X[r + 1][q + 1], X[r + 1][q + 3], X[r][q + 2], X[r + 2][q + 2]);
+                    V[r][q] = fma(w.star[6], xc, L1.full[r][q]);  // this plane is h+1 of level-1 plane q-1
+                    L1.full[r][q] = L1.next[r][q] + v;             // plane q: born one plane ago + its in-plane part
+                    L1.next[r][q] = fma(w.star[5], xc, 0.0);       // this plane is h-1 of level-1 plane q+1
+                }
+        } else {
+            sep3_level(w, [&](int rr, double (&row)[8]) {
+                const double2 *rowp = reinterpret_cast<const double2 *>(tile + (RM * warp + rr) * k3BoxCols + 4 * lane);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const double2 v = rowp[k];
+                    row[2 * k] = v.x;
+                    row[2 * k + 1] = v.y;
+                }
+            }, L1, V);
+            release_stage(i, slot);
+        }
+        // level 1 lives at an odd time: its halo is zero (S2) -- outside the interior nothing is computed
 #pragma unroll
         for (int r = 0; r < RM; r++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const double xc = X[r + 1][q + 2];
-                const double v = star_inplane(w, xc, X[r + 1][q + 1], X[r + 1][q + 3], X[r][q + 2], X[r + 2][q + 2]);
-                const double done = fma(w.star[6], xc, L1.full[r][q]);  // this plane is h+1 of level-1 plane q-1
-                L1.full[r][q] = L1.next[r][q] + v;                       // plane q: born one plane ago + its in-plane part
-                L1.next[r][q] = fma(w.star[5], xc, 0.0);                 // this plane is h-1 of level-1 plane q+1
-                // level 1 lives at an odd time: its halo is zero (S2) -- outside the interior nothing is computed
-                V[r][q] = (plane1_in && rowin[r] && colin[q]) ? done : 0.0;
-            }
+            for (int q = 0; q < 4; q++)
+                if (!(plane1_in && rowin[r] && colin[q])) V[r][q] = 0.0;
         if (i < 2) continue;  // CTA-uniform: level-1 planes before h0 - 1 are not needed
 
         // ---- level 1 -> level 2: rows above / below through shared memory, columns left / right by shuffle
@@ -163,48 +220,76 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             bot[1] = make_double2(V[RM - 1][2], V[RM - 1][3]);
         }
         __syncthreads();  // one barrier per plane: the other buffer is not touched before everybody has passed this one again
-        double up[4], dn[4], lf[RM], rt[RM];
-        {
-            // warp 0 has nobody above and warp 7 nobody below: their outer rows are never stored, any value will do
-            const int wa = warp > 0 ? warp - 1 : 0, wb = warp < k3Warps - 1 ? warp + 1 : k3Warps - 1;
-            const double2 *a = reinterpret_cast<const double2 *>(eb + (wa * 2 + 1) * k3TileCols + 4 * lane);
-            const double2 *b = reinterpret_cast<const double2 *>(eb + (wb * 2 + 0) * k3TileCols + 4 * lane);
-            const double2 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
-            up[0] = a0.x, up[1] = a0.y, up[2] = a1.x, up[3] = a1.y;
-            dn[0] = b0.x, dn[1] = b0.y, dn[2] = b1.x, dn[3] = b1.y;
-        }
+        double lf[RM], rt[RM];
 #pragma unroll
         for (int r = 0; r < RM; r++) {
             lf[r] = __shfl_up_sync(kFull, V[r][3], 1);    // lane 0 gets its own value back: its columns are never stored
             rt[r] = __shfl_down_sync(kFull, V[r][0], 1);  // likewise lane 31
         }
+        // warp 0 has nobody above and warp 7 nobody below: their outer rows are never stored, any value will do
+        const int wa = warp > 0 ? warp - 1 : 0, wb = warp < k3Warps - 1 ? warp + 1 : k3Warps - 1;
         const bool emit = i >= 4;  // level-2 plane h0 + i - 4 completes
+        double O[RM][4];
+        if constexpr (FORM == LORA_FORM_STAR7) {
+            double up[4], dn[4];
+            {
+                const double2 *a = reinterpret_cast<const double2 *>(eb + (wa * 2 + 1) * k3TileCols + 4 * lane);
+                const double2 *b = reinterpret_cast<const double2 *>(eb + (wb * 2 + 0) * k3TileCols + 4 * lane);
+                const double2 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+                up[0] = a0.x, up[1] = a0.y, up[2] = a1.x, up[3] = a1.y;
+                dn[0] = b0.x, dn[1] = b0.y, dn[2] = b1.x, dn[3] = b1.y;
+            }
+#pragma unroll
+            for (int r = 0; r < RM; r++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double xc = V[r][q];
+                    const double v = star_inplane(w, xc, q > 0 ? V[r][q - 1] : lf[r], q < 3 ? V[r][q + 1] : rt[r],
+                                                  r > 0 ? V[r - 1][q] : up[q], r < RM - 1 ? V[r + 1][q] : dn[q]);
+                    O[r][q] = fma(w.star[6], xc, L2.full[r][q]);
+                    L2.full[r][q] = L2.next[r][q] + v;
+                    L2.next[r][q] = fma(w.star[5], xc, 0.0);
+                }
+        } else {
+            // window rows of level 1: the neighbour warps' edge rows (8 columns from 4*lane - 2; lanes 0 and 31 read a
+            // shifted window -- their columns are never stored), own rows from registers + the shuffled columns
+            const int cbase = min(max(4 * lane - 2, 0), k3TileCols - 8);
+            sep3_level(w, [&](int rr, double (&row)[8]) {
+                if (rr == 0 || rr == RM + 1) {
+                    const double2 *e = reinterpret_cast<const double2 *>(
+                        eb + ((rr == 0 ? wa * 2 + 1 : wb * 2 + 0)) * k3TileCols + cbase);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const double2 v = e[k];
+                        row[2 * k] = v.x;
+                        row[2 * k + 1] = v.y;
+                    }
+                } else {
+                    row[0] = 0.0;
+                    row[1] = lf[rr - 1];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) row[2 + q] = V[rr - 1][q];
+                    row[6] = rt[rr - 1];
+                    row[7] = 0.0;
+                }
+            }, L2, O);
+        }
 #pragma unroll
         for (int r = 0; r < RM; r++) {
-            double o[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const double xc = V[r][q];
-                const double v = star_inplane(w, xc, q > 0 ? V[r][q - 1] : lf[r], q < 3 ? V[r][q + 1] : rt[r],
-                                              r > 0 ? V[r - 1][q] : up[q], r < RM - 1 ? V[r + 1][q] : dn[q]);
-                o[q] = fma(w.star[6], xc, L2.full[r][q]);
-                L2.full[r][q] = L2.next[r][q] + v;
-                L2.next[r][q] = fma(w.star[5], xc, 0.0);
-            }
             const int rr = RM * warp + r;  // region row
             if (emit && lane_stores && rr >= 1 && rr <= kT3Rows - 2 && gr0 + r < g.m) {
                 double *op = optr + r * g.row_pitch;
                 if (cols_left >= 4) {
                     if (g.vec4) {
-                        st_global_v4(op, o[0], o[1], o[2], o[3]);
+                        st_global_v4(op, O[r][0], O[r][1], O[r][2], O[r][3]);
                     } else {
-                        st_global_v2(op, o[0], o[1]);
-                        st_global_v2(op + 2, o[2], o[3]);
+                        st_global_v2(op, O[r][0], O[r][1]);
+                        st_global_v2(op + 2, O[r][2], O[r][3]);
                     }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; q++)
-                        if (q < cols_left) op[q] = o[q];
+                        if (q < cols_left) op[q] = O[r][q];
                 }
             }
         }
@@ -215,16 +300,21 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 }  // namespace
 
 cudaError_t kernels_init_3d_tb() {
-    return cudaFuncSetAttribute(k_stencil3d_tb<LORA_FORM_STAR7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3Smem);
+    cudaError_t e = cudaFuncSetAttribute(k_stencil3d_tb<LORA_FORM_STAR7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3Smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_stencil3d_tb<LORA_FORM_SEP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3Smem);
 }
 
 cudaError_t launch_3d_tb(int form, const CUtensorMap &tmap, const Geom3DTB &g, const Weights3D &w, cudaStream_t s) {
-    if (form != LORA_FORM_STAR7) return cudaErrorInvalidValue;
+    if (form != LORA_FORM_STAR7 && form != LORA_FORM_SEP3) return cudaErrorInvalidValue;
     const long long planes = g.h_hi - g.h_lo;
     if (planes <= 0) return cudaSuccess;
     const int chunks = (int)((planes + g.planes_per_chunk - 1) / g.planes_per_chunk);
     dim3 grid(g.tiles_m * g.tiles_n, chunks);
-    k_stencil3d_tb<LORA_FORM_STAR7><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
+    if (form == LORA_FORM_STAR7)
+        k_stencil3d_tb<LORA_FORM_STAR7><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
+    else
+        k_stencil3d_tb<LORA_FORM_SEP3><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
     return cudaGetLastError();
 }
 

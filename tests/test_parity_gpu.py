@@ -461,13 +461,13 @@ def test_copy_overlapped_operator_equals_plain_sequence(shape, dims, times, monk
 
 @pytest.mark.parametrize("dims", [(16, 16, 64), (40, 50, 130), (7, 33, 132), (64, 64, 64), (30, 22, 120), (33, 23, 122), (5, 100, 400),
                                   (3, 3, 4), (70, 40, 250)])
-def test_temporal_blocking_3d_equals_unfused_launches(dims):
-    """3-D sweeps of 2 fused launches (star3d1r; level 1 handed on in registers, by warp shuffles and through two
+@pytest.mark.parametrize("shape", ["star3d1r", "box3d1r"])
+def test_temporal_blocking_3d_equals_unfused_launches(shape, dims):
+    """3-D sweeps of 2 fused launches (level 1 handed on in registers, by warp shuffles and through two
     shared-memory rows per warp; overlapped 22 x 120 tiles; zero halo at the intermediate level, the caller's ring
     copied into buffer 1 for the odd sweeps and cleared afterwards) give the same bits as one launch per step, match
     the oracle, and leave both halo rings as the reference's ping-pong would."""
     import torch
-    shape = "star3d1r"
     a = oracle.fill_rand(shape, dims)
     rng = np.random.default_rng(sum(dims))
     af = rng.uniform(-1, 1, a.shape)
@@ -498,7 +498,7 @@ def test_temporal_blocking_3d_equals_unfused_launches(dims):
                 assert np.array_equal(h0, d_h) and not h1.any()
             assert np.array_equal(results[0], results[1]), (dims, times)  # same operation order => same bits
             ref = oracle.run(shape, data, eff, times)
-            if data is a and times <= 15:
-                assert np.array_equal(results[1], ref), (dims, times)
+            if data is a and times <= (15 if shape == "star3d1r" else 8):
+                assert np.array_equal(results[1], ref), (shape, dims, times)
             else:
-                assert max_rel_err(results[1], ref) <= RTOL, (dims, times)
+                assert max_rel_err(results[1], ref) <= RTOL, (shape, dims, times)
