@@ -245,8 +245,9 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         }
     }
     if (dim == 3 && tb3_form(p->form) && !p->odd_cols) {
-        // 3-D fusion (stencil3d_tb.cu): two launches per sweep for the 7-point form
-        p->max_tb = kTb3;
+        // 3-D fusion (stencil3d_tb.cu): two launches per sweep.  On by default for the 7-point form (433 vs 377
+        // GStencil/s at 512^3); the separable form is built and bit-identical but slower fused (354 vs 384): off
+        p->max_tb = p->form == LORA_FORM_STAR7 ? kTb3 : 1;
         if (const char *e = getenv("LORA_TB3")) p->max_tb = (atoi(e) >= kTb3) ? kTb3 : 1;
     }
     if (dim == 1) {
