@@ -906,6 +906,7 @@ static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if (lo == hi) return LORA_OK;
     if (int rc = check_device(p)) return rc;
+    if (reinterpret_cast<uintptr_t>(dst) % 16) return fail(LORA_ERR_ARG, "destination buffer must be 16-byte aligned");
     const CUtensorMap *tm;
     if (int rc = get_tmap3tb(p, src, &tm)) return rc;
     Geom3DTB g{};

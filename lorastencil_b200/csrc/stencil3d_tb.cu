@@ -52,39 +52,93 @@ __device__ __forceinline__ double star_inplane(const Weights3D &w, double c, dou
     return v;
 }
 
-// separable 27-point operator a (x) b (x) c, one level, with the window delivered row by row (only one window row is
-// live at a time): s = c * row along n, t = b * s along m, then the two carried plane accumulators -- the operation
-// order of stencil3d.cu's SEP3 push.  rowfn(rr, row): window row rr (region row RM*warp - 1 + rr), row[j] = column
-// 4*lane - 2 + j; only row[1..6] are read.
-template <class RowFn>
-__device__ __forceinline__ void sep3_level(const Weights3D &w, RowFn rowfn, LevelState &L, double (&out)[RM][4]) {
-    double t[RM][4];
+// Column ownership: lane l owns region columns {2l, 2l+1} (pair A) and {64+2l, 64+2l+1} (pair B) of every row.  A
+// 128-bit shared-memory access then has a lane stride of 16 bytes -- conflict-free -- where 4 consecutive columns per
+// lane (stride 32 bytes, stencil3d.cu) cost two wavefronts per quarter-warp; the columns left / right of a pair come
+// from the neighbour lanes by CIRCULAR warp shuffle: lane 31's pair A ends at column 63, whose right neighbour is lane
+// 0's pair B, and vice versa; only column -1 (lane 0) and column 128 (lane 31) are not owned by anybody in the warp.
+// A window row is {LA, A0, A1, RA, LB, B0, B1, RB}.
+__device__ __forceinline__ void window_row(double a0, double a1, double b0, double b1, int lane, double edge_l, double edge_r,
+                                           double (&row)[8]) {
+    const int prev = (lane + 31) & 31, next = (lane + 1) & 31;
+    const double la = __shfl_sync(kFull, a1, prev), lb = __shfl_sync(kFull, b1, prev);
+    const double ra = __shfl_sync(kFull, a0, next), rb = __shfl_sync(kFull, b0, next);
+    row[0] = lane == 0 ? edge_l : la;
+    row[1] = a0;
+    row[2] = a1;
+    row[3] = lane == 31 ? rb : ra;
+    row[4] = lane == 0 ? la : lb;
+    row[5] = b0;
+    row[6] = b1;
+    row[7] = lane == 31 ? edge_r : rb;
+}
+// own cell q (0, 1: pair A; 2, 3: pair B) sits at row[kCell[q]]
+#define LORA_CELL(q) ((q) < 2 ? 1 + (q) : 3 + (q))
+
+// One level of the operator over the lane's RM x 4 cells, the window delivered row by row (only one window row is
+// live at a time).  rowfn(rr, row): window row rr = region row RM*warp - 1 + rr; `full_row` false: only the own cells
+// of that row are needed (rows above / below of a star).  Operation order = stencil3d.cu's pushes, so fused and unfused
+// launches give the same bits.
+template <int FORM, class RowFn>
+__device__ __forceinline__ void level(const Weights3D &w, RowFn rowfn, LevelState &L, double (&out)[RM][4]) {
+    if constexpr (FORM == LORA_FORM_SEP3) {
+        // s = c * row along n, t = b * s along m, then the two carried plane accumulators (a along h)
+        double t[RM][4];
 #pragma unroll
-    for (int rr = 0; rr < RM + 2; rr++) {
-        double row[8];
-        rowfn(rr, row);
+        for (int rr = 0; rr < RM + 2; rr++) {
+            double row[8];
+            rowfn(rr, row, true);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            double s = w.c[0] * row[q + 1];
-            s = fma(w.c[1], row[q + 2], s);
-            s = fma(w.c[2], row[q + 3], s);
+            for (int q = 0; q < 4; q++) {
+                double s = w.c[0] * row[LORA_CELL(q) - 1];
+                s = fma(w.c[1], row[LORA_CELL(q)], s);
+                s = fma(w.c[2], row[LORA_CELL(q) + 1], s);
 #pragma unroll
-            for (int r = 0; r < RM; r++) {
-                const int dr = rr - 1 - r;  // row rr is the dr neighbour of micro-tile row r
-                if (dr == -1) t[r][q] = w.b[0] * s;
-                else if (dr == 0) t[r][q] = fma(w.b[1], s, t[r][q]);
-                else if (dr == 1) t[r][q] = fma(w.b[2], s, t[r][q]);
+                for (int r = 0; r < RM; r++) {
+                    const int dr = rr - 1 - r;  // row rr is the dr neighbour of micro-tile row r
+                    if (dr == -1) t[r][q] = w.b[0] * s;
+                    else if (dr == 0) t[r][q] = fma(w.b[1], s, t[r][q]);
+                    else if (dr == 1) t[r][q] = fma(w.b[2], s, t[r][q]);
+                }
             }
         }
-    }
 #pragma unroll
-    for (int r = 0; r < RM; r++)
+        for (int r = 0; r < RM; r++)
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            out[r][q] = fma(w.a[2], t[r][q], L.full[r][q]);      // this plane is h+1 of the plane that completes
-            L.full[r][q] = fma(w.a[1], t[r][q], L.next[r][q]);   // and h of the next one
-            L.next[r][q] = fma(w.a[0], t[r][q], 0.0);            // and h-1 of the one after
+            for (int q = 0; q < 4; q++) {
+                out[r][q] = fma(w.a[2], t[r][q], L.full[r][q]);      // this plane is h+1 of the plane that completes
+                L.full[r][q] = fma(w.a[1], t[r][q], L.next[r][q]);   // and h of the next one
+                L.next[r][q] = fma(w.a[0], t[r][q], 0.0);            // and h-1 of the one after
+            }
+    } else {
+        // 7-point star: centre, n-1, n+1, m-1, m+1 in-plane; the plane taps through the carried accumulators
+        double v[RM][4], up[4], cur[8], nxt[8];
+        rowfn(0, cur, false);
+#pragma unroll
+        for (int q = 0; q < 4; q++) up[q] = cur[LORA_CELL(q)];
+        rowfn(1, cur, true);
+#pragma unroll
+        for (int r = 0; r < RM; r++) {
+            rowfn(r + 2, nxt, r + 2 <= RM);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double xc = cur[LORA_CELL(q)];
+                double a = w.star[0] * xc;
+                a = fma(w.star[1], cur[LORA_CELL(q) - 1], a);
+                a = fma(w.star[2], cur[LORA_CELL(q) + 1], a);
+                a = fma(w.star[3], up[q], a);
+                a = fma(w.star[4], nxt[LORA_CELL(q)], a);
+                v[r][q] = a;
+                out[r][q] = fma(w.star[6], xc, L.full[r][q]);  // this plane is h+1 of the plane that completes
+                L.full[r][q] = L.next[r][q] + a;                // plane q: born one plane ago + its in-plane part
+                L.next[r][q] = fma(w.star[5], xc, 0.0);         // this plane is h-1 of the plane after
+                up[q] = xc;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) cur[k] = nxt[k];
         }
+        (void)v;
+    }
 }
 
 template <int FORM>
@@ -123,39 +177,26 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
     __syncthreads();
 
-    // this lane's cells: region rows RM*warp .. +RM-1, region columns 4*lane .. +3
-    const int gr0 = R0 + RM * warp - 1;  // interior row of the lane's first row
-    const int gc0 = C0 + 4 * lane - 4;   // interior column of its first column
+    // this lane's cells: region rows RM*warp .. +RM-1; region columns 2*lane, 2*lane+1 (A) and 64+2*lane, +1 (B)
+    const int gr0 = R0 + RM * warp - 1;         // interior row of the lane's first row
+    const int gcA = C0 + 2 * lane - 4;          // interior column of A0
+    const int gcB = gcA + 64;                   // interior column of B0
     bool rowin[RM], colin[4];
 #pragma unroll
     for (int r = 0; r < RM; r++) rowin[r] = gr0 + r >= 0 && gr0 + r < g.m;
-#pragma unroll
-    for (int q = 0; q < 4; q++) colin[q] = gc0 + q >= 0 && gc0 + q < g.n;
-    // what this lane stores: region rows 1 .. kT3Rows-2, lanes 1 .. 30, inside the grid
-    const bool lane_stores = lane >= 1 && lane <= 30 && gc0 < g.n;
-    const int cols_left = g.n - gc0;
-    double *optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(gr0 + 2) * g.row_pitch + 4 + gc0;
+    colin[0] = gcA >= 0 && gcA < g.n;
+    colin[1] = gcA + 1 >= 0 && gcA + 1 < g.n;
+    colin[2] = gcB >= 0 && gcB < g.n;
+    colin[3] = gcB + 1 >= 0 && gcB + 1 < g.n;
+    // what this lane stores: region columns 4 .. 123 (pair A of lanes >= 2, pair B of lanes <= 29), inside the grid
+    const bool storeA = lane >= 2 && gcA < g.n, storeB = lane <= 29 && gcB < g.n;
+    double *optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(gr0 + 2) * g.row_pitch + 4 + gcA;
 
     LevelState L1, L2;
 #pragma unroll
     for (int r = 0; r < RM; r++)
 #pragma unroll
         for (int q = 0; q < 4; q++) L1.full[r][q] = L1.next[r][q] = L2.full[r][q] = L2.next[r][q] = 0.0;
-
-    // consumer release + producer duty (as in stencil3d.cu): the stage's values are in registers
-    auto release_stage = [&](int i, int slot) {
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&empty[slot]);  // this warp no longer needs the stage
-            const int nx = i - 1 + k3Stages;
-            if (warp == 0 && i >= 1 && nx < nin) {  // refill the slot every warp released one plane ago
-                const int ps = (i - 1) % k3Stages;
-                mbar_wait(&empty[ps], ((i - 1) / k3Stages) & 1);
-                mbar_arrive_expect_tx(&full[ps], kT3BoxRows * k3BoxCols * 8);
-                tma_load_3d(smem_raw + ps * kT3StageBytes, &tmap, box_c, box_r, box_h + nx, &full[ps]);
-            }
-        }
-    };
 
     for (int i = 0; i < nin; i++) {
         // ---- level 0 -> level 1: plane q = h0 - 2 + i arrives, level-1 plane q - 1 completes
@@ -165,41 +206,31 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const int j1 = h0 - 3 + i;  // the level-1 plane that completes now
         const bool plane1_in = j1 >= 0 && j1 < g.h;
         double V[RM][4];
-        if constexpr (FORM == LORA_FORM_STAR7) {
-            double X[RM + 2][8];  // rows RM*warp-1 .. RM*warp+RM, columns 4*lane-2 .. 4*lane+5 (region coordinates)
-#pragma unroll
-            for (int rr = 0; rr < RM + 2; rr++) {
-                const double2 *rowp = reinterpret_cast<const double2 *>(tile + (RM * warp + rr) * k3BoxCols + 4 * lane);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if ((rr == 0 || rr == RM + 1) && (k == 0 || k == 3)) continue;  // corners are not part of a star
-                    const double2 v = rowp[k];
-                    X[rr][2 * k] = v.x;
-                    X[rr][2 * k + 1] = v.y;
-                }
+        level<FORM>(w, [&](int rr, double (&row)[8], bool full_row) {
+            // box row RM*warp + rr; box column = region column + 2
+            const double *rowp = tile + (RM * warp + rr) * k3BoxCols + 2;
+            const double2 a = *reinterpret_cast<const double2 *>(rowp + 2 * lane);
+            const double2 b = *reinterpret_cast<const double2 *>(rowp + 64 + 2 * lane);
+            if (full_row) {
+                double e = 0.0;
+                if (lane == 0) e = rowp[-1];       // region column -1
+                if (lane == 31) e = rowp[128];     // region column 128
+                window_row(a.x, a.y, b.x, b.y, lane, e, e, row);
+            } else {
+                row[1] = a.x, row[2] = a.y, row[5] = b.x, row[6] = b.y;
             }
-            release_stage(i, slot);
-#pragma unroll
-            for (int r = 0; r < RM; r++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const double xc = X[r + 1][q + 2];
-                    const double v = star_inplane(w, xc, X[r + 1][q + 1], X[r + 1][q + 3], X[r][q + 2], X[r + 2][q + 2]);
-                    V[r][q] = fma(w.star[6], xc, L1.full[r][q]);  // this plane is h+1 of level-1 plane q-1
-                    L1.full[r][q] = L1.next[r][q] + v;             // plane q: born one plane ago + its in-plane part
-                    L1.next[r][q] = fma(w.star[5], xc, 0.0);       // this plane is h-1 of level-1 plane q+1
-                }
-        } else {
-            sep3_level(w, [&](int rr, double (&row)[8]) {
-                const double2 *rowp = reinterpret_cast<const double2 *>(tile + (RM * warp + rr) * k3BoxCols + 4 * lane);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const double2 v = rowp[k];
-                    row[2 * k] = v.x;
-                    row[2 * k + 1] = v.y;
-                }
-            }, L1, V);
-            release_stage(i, slot);
+        }, L1, V);
+        // the stage's values are in registers (consumed by the level): release it, refill the one released a plane ago
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[slot]);
+            const int nx = i - 1 + k3Stages;
+            if (warp == 0 && i >= 1 && nx < nin) {
+                const int ps = (i - 1) % k3Stages;
+                mbar_wait(&empty[ps], ((i - 1) / k3Stages) & 1);
+                mbar_arrive_expect_tx(&full[ps], kT3BoxRows * k3BoxCols * 8);
+                tma_load_3d(smem_raw + ps * kT3StageBytes, &tmap, box_c, box_r, box_h + nx, &full[ps]);
+            }
         }
         // level 1 lives at an odd time: its halo is zero (S2) -- outside the interior nothing is computed
 #pragma unroll
@@ -209,93 +240,57 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 if (!(plane1_in && rowin[r] && colin[q])) V[r][q] = 0.0;
         if (i < 2) continue;  // CTA-uniform: level-1 planes before h0 - 1 are not needed
 
-        // ---- level 1 -> level 2: rows above / below through shared memory, columns left / right by shuffle
+        // ---- level 1 -> level 2: the rows above / below come through shared memory (first / last row of every warp),
+        // everything else from the lane's own registers and its neighbours' by shuffle
         double *eb = edge + (size_t)(i & 1) * (k3Warps * 2 * k3TileCols);
         {
-            double2 *top = reinterpret_cast<double2 *>(eb + (warp * 2 + 0) * k3TileCols + 4 * lane);
-            double2 *bot = reinterpret_cast<double2 *>(eb + (warp * 2 + 1) * k3TileCols + 4 * lane);
-            top[0] = make_double2(V[0][0], V[0][1]);
-            top[1] = make_double2(V[0][2], V[0][3]);
-            bot[0] = make_double2(V[RM - 1][0], V[RM - 1][1]);
-            bot[1] = make_double2(V[RM - 1][2], V[RM - 1][3]);
+            double *top = eb + (warp * 2 + 0) * k3TileCols, *bot = eb + (warp * 2 + 1) * k3TileCols;
+            *reinterpret_cast<double2 *>(top + 2 * lane) = make_double2(V[0][0], V[0][1]);
+            *reinterpret_cast<double2 *>(top + 64 + 2 * lane) = make_double2(V[0][2], V[0][3]);
+            *reinterpret_cast<double2 *>(bot + 2 * lane) = make_double2(V[RM - 1][0], V[RM - 1][1]);
+            *reinterpret_cast<double2 *>(bot + 64 + 2 * lane) = make_double2(V[RM - 1][2], V[RM - 1][3]);
         }
         __syncthreads();  // one barrier per plane: the other buffer is not touched before everybody has passed this one again
-        double lf[RM], rt[RM];
-#pragma unroll
-        for (int r = 0; r < RM; r++) {
-            lf[r] = __shfl_up_sync(kFull, V[r][3], 1);    // lane 0 gets its own value back: its columns are never stored
-            rt[r] = __shfl_down_sync(kFull, V[r][0], 1);  // likewise lane 31
-        }
         // warp 0 has nobody above and warp 7 nobody below: their outer rows are never stored, any value will do
         const int wa = warp > 0 ? warp - 1 : 0, wb = warp < k3Warps - 1 ? warp + 1 : k3Warps - 1;
-        const bool emit = i >= 4;  // level-2 plane h0 + i - 4 completes
         double O[RM][4];
-        if constexpr (FORM == LORA_FORM_STAR7) {
-            double up[4], dn[4];
-            {
-                const double2 *a = reinterpret_cast<const double2 *>(eb + (wa * 2 + 1) * k3TileCols + 4 * lane);
-                const double2 *b = reinterpret_cast<const double2 *>(eb + (wb * 2 + 0) * k3TileCols + 4 * lane);
-                const double2 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
-                up[0] = a0.x, up[1] = a0.y, up[2] = a1.x, up[3] = a1.y;
-                dn[0] = b0.x, dn[1] = b0.y, dn[2] = b1.x, dn[3] = b1.y;
+        level<FORM>(w, [&](int rr, double (&row)[8], bool full_row) {
+            double a0, a1, b0, b1;
+            if (rr == 0 || rr == RM + 1) {
+                const double *e = eb + (rr == 0 ? wa * 2 + 1 : wb * 2 + 0) * k3TileCols;
+                const double2 a = *reinterpret_cast<const double2 *>(e + 2 * lane);
+                const double2 b = *reinterpret_cast<const double2 *>(e + 64 + 2 * lane);
+                a0 = a.x, a1 = a.y, b0 = b.x, b1 = b.y;
+            } else {
+                a0 = V[rr - 1][0], a1 = V[rr - 1][1], b0 = V[rr - 1][2], b1 = V[rr - 1][3];
             }
+            if (full_row) {
+                window_row(a0, a1, b0, b1, lane, 0.0, 0.0, row);  // columns -1 and 128 only feed cells that are never stored
+            } else {
+                row[1] = a0, row[2] = a1, row[5] = b0, row[6] = b1;
+            }
+        }, L2, O);
+        if (i >= 4) {  // level-2 plane h0 + i - 4 is complete
 #pragma unroll
-            for (int r = 0; r < RM; r++)
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const double xc = V[r][q];
-                    const double v = star_inplane(w, xc, q > 0 ? V[r][q - 1] : lf[r], q < 3 ? V[r][q + 1] : rt[r],
-                                                  r > 0 ? V[r - 1][q] : up[q], r < RM - 1 ? V[r + 1][q] : dn[q]);
-                    O[r][q] = fma(w.star[6], xc, L2.full[r][q]);
-                    L2.full[r][q] = L2.next[r][q] + v;
-                    L2.next[r][q] = fma(w.star[5], xc, 0.0);
-                }
-        } else {
-            // window rows of level 1: the neighbour warps' edge rows (8 columns from 4*lane - 2; lanes 0 and 31 read a
-            // shifted window -- their columns are never stored), own rows from registers + the shuffled columns
-            const int cbase = min(max(4 * lane - 2, 0), k3TileCols - 8);
-            sep3_level(w, [&](int rr, double (&row)[8]) {
-                if (rr == 0 || rr == RM + 1) {
-                    const double2 *e = reinterpret_cast<const double2 *>(
-                        eb + ((rr == 0 ? wa * 2 + 1 : wb * 2 + 0)) * k3TileCols + cbase);
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const double2 v = e[k];
-                        row[2 * k] = v.x;
-                        row[2 * k + 1] = v.y;
+            for (int r = 0; r < RM; r++) {
+                const int rr = RM * warp + r;  // region row
+                if (rr >= 1 && rr <= kT3Rows - 2 && gr0 + r < g.m) {
+                    double *op = optr + r * g.row_pitch;
+                    if (storeA) {
+                        if (gcA + 1 < g.n) st_global_v2(op, O[r][0], O[r][1]);
+                        else op[0] = O[r][0];
                     }
-                } else {
-                    row[0] = 0.0;
-                    row[1] = lf[rr - 1];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) row[2 + q] = V[rr - 1][q];
-                    row[6] = rt[rr - 1];
-                    row[7] = 0.0;
-                }
-            }, L2, O);
-        }
-#pragma unroll
-        for (int r = 0; r < RM; r++) {
-            const int rr = RM * warp + r;  // region row
-            if (emit && lane_stores && rr >= 1 && rr <= kT3Rows - 2 && gr0 + r < g.m) {
-                double *op = optr + r * g.row_pitch;
-                if (cols_left >= 4) {
-                    if (g.vec4) {
-                        st_global_v4(op, O[r][0], O[r][1], O[r][2], O[r][3]);
-                    } else {
-                        st_global_v2(op, O[r][0], O[r][1]);
-                        st_global_v2(op + 2, O[r][2], O[r][3]);
+                    if (storeB) {
+                        if (gcB + 1 < g.n) st_global_v2(op + 64, O[r][2], O[r][3]);
+                        else op[64] = O[r][2];
                     }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        if (q < cols_left) op[q] = O[r][q];
                 }
             }
+            optr += g.plane_pitch;
         }
-        if (emit) optr += g.plane_pitch;
     }
 }
+#undef LORA_CELL
 
 }  // namespace
 
