@@ -67,10 +67,11 @@ constexpr int k3Threads = 32 * k3Warps;
 constexpr int kT3Rm = 3;
 constexpr int kT3Rows = kT3Rm * k3Warps;
 constexpr int kT3OutRows = kT3Rows - 2;
-constexpr int kT3OutCols = k3TileCols - 8;
+constexpr int kT3OutCols = k3TileCols;      // the level-1 columns just outside a tile are extra cells (stencil3d_tb.cu)
 constexpr int kT3BoxRows = kT3Rows + 2;
 constexpr int kT3StageBytes = ((kT3BoxRows * k3BoxCols * 8 + 127) / 128) * 128;
-constexpr int kT3EdgeBytes = 2 * k3Warps * 2 * k3TileCols * 8;  // first / last level-1 row of every warp, double-buffered
+constexpr int kT3EdgePitch = k3TileCols + 4;  // columns -2 .. 129 of a level-1 edge row
+constexpr int kT3EdgeBytes = 2 * k3Warps * 2 * kT3EdgePitch * 8;  // first / last level-1 row of every warp, double-buffered
 constexpr int kT3Smem = k3Stages * kT3StageBytes + kT3EdgeBytes + 2 * k3Stages * 8;
 
 struct Weights1D {

@@ -15,10 +15,12 @@
 //   * level 1 reaches level 2 without a tile round trip: a lane's own 3 x 4 values stay in registers, the columns
 //     left / right come from the neighbour lanes by warp shuffle, and only the first / last row of every warp goes
 //     through shared memory (2 x 128 doubles per warp and plane, double-buffered, ONE __syncthreads per plane);
-//   * overlapped tiling: every level is computed on the full 24 x 128 thread tile, the valid region shrinks by one
-//     cell per level and side; a CTA writes 22 rows x 120 columns (lanes 0 and 31 and the outer rows only feed their
-//     neighbours), i.e. it reads a 26 x 132 box per 22 x 120 outputs: 18.4 B of DRAM traffic per cell per TWO launches
-//     against 2 x 16.8 unfused.
+//   * overlapped tiling along the rows only: every level is computed on the full 24 x 128 thread tile and the outer
+//     rows only feed their neighbours (a CTA writes 22 rows); along the columns a tile writes ALL 128 columns it owns
+//     (512 columns = 4 tiles, not 5 of 120): the two level-1 columns just outside the tile, which level 2 needs, are
+//     computed as ONE extra cell per lane (lanes 0 .. 2 RM - 1: RM rows x {left, right}) from the level-0 box, which
+//     covers them anyway, and handed to lanes 0 / 31 by shuffle.  A CTA reads a 26 x 132 box per 22 x 128 outputs:
+//     17.2 B of DRAM traffic per cell per TWO launches against 2 x 16.8 unfused.
 //
 // Reference semantics (S2) under fusion: a fused sweep starts at an even time -- level 0 sees the caller's halo, which
 // is physically in the source buffer's ring (the host copies the ring of buffer 0 into buffer 1 before the first sweep
@@ -42,14 +44,41 @@ struct LevelState {
     double next[RM][4];
 };
 
-// 7-point star, in-plane part: centre, n-1, n+1, m-1, m+1 -- the operation order of stencil3d.cu's STAR7 push
-__device__ __forceinline__ double star_inplane(const Weights3D &w, double c, double l, double r, double u, double d) {
-    double v = w.star[0] * c;
-    v = fma(w.star[1], l, v);
-    v = fma(w.star[2], r, v);
-    v = fma(w.star[3], u, v);
-    v = fma(w.star[4], d, v);
-    return v;
+// the extra level-1 cell of a lane (region column -1 or 128): same operator, same operation order, operands straight
+// from the level-0 box.  c points at the cell's centre in the box, `pitch` doubles per box row.
+struct EdgeState {
+    double full, next;
+};
+template <int FORM>
+__device__ __forceinline__ double edge_cell(const Weights3D &w, const double *c, int pitch, EdgeState &E) {
+    double out;
+    if constexpr (FORM == LORA_FORM_SEP3) {
+        double s[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const double *r = c + (k - 1) * pitch;
+            s[k] = w.c[0] * r[-1];
+            s[k] = fma(w.c[1], r[0], s[k]);
+            s[k] = fma(w.c[2], r[1], s[k]);
+        }
+        double t = w.b[0] * s[0];
+        t = fma(w.b[1], s[1], t);
+        t = fma(w.b[2], s[2], t);
+        out = fma(w.a[2], t, E.full);
+        E.full = fma(w.a[1], t, E.next);
+        E.next = fma(w.a[0], t, 0.0);
+    } else {
+        const double xc = c[0];
+        double a = w.star[0] * xc;
+        a = fma(w.star[1], c[-1], a);
+        a = fma(w.star[2], c[1], a);
+        a = fma(w.star[3], c[-pitch], a);
+        a = fma(w.star[4], c[pitch], a);
+        out = fma(w.star[6], xc, E.full);
+        E.full = E.next + a;
+        E.next = fma(w.star[5], xc, 0.0);
+    }
+    return out;
 }
 
 // Column ownership: lane l owns region columns {2l, 2l+1} (pair A) and {64+2l, 64+2l+1} (pair B) of every row.  A
@@ -158,8 +187,8 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int nin = H + 4;                       // level-0 planes h0-2 .. h0+H+1
     const int R0 = tile_m * kT3OutRows, C0 = tile_n * kT3OutCols;  // first output row / column of the tile
     // TMA box origin in padded coordinates: region row -1 = interior row R0 - 2 = padded row R0; region column -2 =
-    // interior column C0 - 6 = padded column C0 - 2 (out-of-bounds coordinates are zero-filled)
-    const int box_c = C0 - 2, box_r = R0, box_h = h0 - 1;
+    // interior column C0 - 2 = padded column C0 + 2 (out-of-bounds coordinates are zero-filled)
+    const int box_c = C0 + 2, box_r = R0, box_h = h0 - 1;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -179,20 +208,26 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
     // this lane's cells: region rows RM*warp .. +RM-1; region columns 2*lane, 2*lane+1 (A) and 64+2*lane, +1 (B)
     const int gr0 = R0 + RM * warp - 1;         // interior row of the lane's first row
-    const int gcA = C0 + 2 * lane - 4;          // interior column of A0
+    const int gcA = C0 + 2 * lane;              // interior column of A0
     const int gcB = gcA + 64;                   // interior column of B0
     bool rowin[RM], colin[4];
 #pragma unroll
     for (int r = 0; r < RM; r++) rowin[r] = gr0 + r >= 0 && gr0 + r < g.m;
-    colin[0] = gcA >= 0 && gcA < g.n;
-    colin[1] = gcA + 1 >= 0 && gcA + 1 < g.n;
-    colin[2] = gcB >= 0 && gcB < g.n;
-    colin[3] = gcB + 1 >= 0 && gcB + 1 < g.n;
-    // what this lane stores: region columns 4 .. 123 (pair A of lanes >= 2, pair B of lanes <= 29), inside the grid
-    const bool storeA = lane >= 2 && gcA < g.n, storeB = lane <= 29 && gcB < g.n;
+    colin[0] = gcA < g.n;
+    colin[1] = gcA + 1 < g.n;
+    colin[2] = gcB < g.n;
+    colin[3] = gcB + 1 < g.n;
+    // level-1 cells outside the interior are zero (S2); only tiles that touch the rim of the grid have any
+    const bool rim = R0 == 0 || R0 + kT3Rows - 1 > g.m || C0 + k3TileCols > g.n;
+    // the lane's extra level-1 cell: lane e < 2 RM owns row e % RM of region column -1 (e < RM) or 128
+    const int er = lane % RM, eside = (lane / RM) & 1;
+    const int ebox = ((RM * warp + er + 1) * k3BoxCols) + (eside ? k3TileCols + 2 : 1);  // its centre in the box
+    const int egc = eside ? C0 + k3TileCols : C0 - 1;
+    const bool ein = gr0 + er >= 0 && gr0 + er < g.m && egc >= 0 && egc < g.n;
     double *optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(gr0 + 2) * g.row_pitch + 4 + gcA;
 
     LevelState L1, L2;
+    EdgeState E1{0.0, 0.0};
 #pragma unroll
     for (int r = 0; r < RM; r++)
 #pragma unroll
@@ -220,6 +255,7 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 row[1] = a.x, row[2] = a.y, row[5] = b.x, row[6] = b.y;
             }
         }, L1, V);
+        double EV = edge_cell<FORM>(w, tile + ebox, k3BoxCols, E1);
         // the stage's values are in registers (consumed by the level): release it, refill the one released a plane ago
         __syncwarp();
         if (lane == 0) {
@@ -233,39 +269,54 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             }
         }
         // level 1 lives at an odd time: its halo is zero (S2) -- outside the interior nothing is computed
+        if (rim || !plane1_in) {  // CTA-uniform
 #pragma unroll
-        for (int r = 0; r < RM; r++)
+            for (int r = 0; r < RM; r++)
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (!(plane1_in && rowin[r] && colin[q])) V[r][q] = 0.0;
+                for (int q = 0; q < 4; q++)
+                    if (!(plane1_in && rowin[r] && colin[q])) V[r][q] = 0.0;
+        }
+        if (!(plane1_in && ein)) EV = 0.0;
         if (i < 2) continue;  // CTA-uniform: level-1 planes before h0 - 1 are not needed
 
         // ---- level 1 -> level 2: the rows above / below come through shared memory (first / last row of every warp),
         // everything else from the lane's own registers and its neighbours' by shuffle
-        double *eb = edge + (size_t)(i & 1) * (k3Warps * 2 * k3TileCols);
+        double *eb = edge + (size_t)(i & 1) * (k3Warps * 2 * kT3EdgePitch) + 2;  // column c of an edge row at [c]
         {
-            double *top = eb + (warp * 2 + 0) * k3TileCols, *bot = eb + (warp * 2 + 1) * k3TileCols;
+            double *top = eb + (warp * 2 + 0) * kT3EdgePitch, *bot = eb + (warp * 2 + 1) * kT3EdgePitch;
             *reinterpret_cast<double2 *>(top + 2 * lane) = make_double2(V[0][0], V[0][1]);
             *reinterpret_cast<double2 *>(top + 64 + 2 * lane) = make_double2(V[0][2], V[0][3]);
             *reinterpret_cast<double2 *>(bot + 2 * lane) = make_double2(V[RM - 1][0], V[RM - 1][1]);
             *reinterpret_cast<double2 *>(bot + 64 + 2 * lane) = make_double2(V[RM - 1][2], V[RM - 1][3]);
+            if constexpr (FORM == LORA_FORM_SEP3) {  // the window rows above / below are full rows: columns -1, 128 too
+                if (lane < 2 * RM && (er == 0 || er == RM - 1))
+                    (er == 0 ? top : bot)[eside ? k3TileCols : -1] = EV;
+            }
         }
         __syncthreads();  // one barrier per plane: the other buffer is not touched before everybody has passed this one again
         // warp 0 has nobody above and warp 7 nobody below: their outer rows are never stored, any value will do
         const int wa = warp > 0 ? warp - 1 : 0, wb = warp < k3Warps - 1 ? warp + 1 : k3Warps - 1;
         double O[RM][4];
         level<FORM>(w, [&](int rr, double (&row)[8], bool full_row) {
-            double a0, a1, b0, b1;
+            double a0, a1, b0, b1, el = 0.0, er_ = 0.0;
             if (rr == 0 || rr == RM + 1) {
-                const double *e = eb + (rr == 0 ? wa * 2 + 1 : wb * 2 + 0) * k3TileCols;
+                const double *e = eb + (rr == 0 ? wa * 2 + 1 : wb * 2 + 0) * kT3EdgePitch;
                 const double2 a = *reinterpret_cast<const double2 *>(e + 2 * lane);
                 const double2 b = *reinterpret_cast<const double2 *>(e + 64 + 2 * lane);
                 a0 = a.x, a1 = a.y, b0 = b.x, b1 = b.y;
+                if (full_row) {
+                    if (lane == 0) el = e[-1];
+                    if (lane == 31) er_ = e[k3TileCols];
+                }
             } else {
                 a0 = V[rr - 1][0], a1 = V[rr - 1][1], b0 = V[rr - 1][2], b1 = V[rr - 1][3];
+                if (full_row) {  // the lanes that own this row's extra cells hand them over
+                    el = __shfl_sync(kFull, EV, rr - 1);
+                    er_ = __shfl_sync(kFull, EV, RM + rr - 1);
+                }
             }
             if (full_row) {
-                window_row(a0, a1, b0, b1, lane, 0.0, 0.0, row);  // columns -1 and 128 only feed cells that are never stored
+                window_row(a0, a1, b0, b1, lane, el, er_, row);
             } else {
                 row[1] = a0, row[2] = a1, row[5] = b0, row[6] = b1;
             }
@@ -276,11 +327,11 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 const int rr = RM * warp + r;  // region row
                 if (rr >= 1 && rr <= kT3Rows - 2 && gr0 + r < g.m) {
                     double *op = optr + r * g.row_pitch;
-                    if (storeA) {
+                    if (colin[0]) {
                         if (gcA + 1 < g.n) st_global_v2(op, O[r][0], O[r][1]);
                         else op[0] = O[r][0];
                     }
-                    if (storeB) {
+                    if (colin[2]) {
                         if (gcB + 1 < g.n) st_global_v2(op + 64, O[r][2], O[r][3]);
                         else op[64] = O[r][2];
                     }

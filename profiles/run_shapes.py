@@ -19,9 +19,10 @@ ap.add_argument("--launches", type=int, default=4)
 ap.add_argument("--shapes", default=",".join(SIZES))
 ap.add_argument("--tb", type=int, default=0, help="temporal block to request (0 = the plan's default)")
 ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--dims", default="", help="override the size, e.g. 1024x1024x1024 (applies to every shape listed)")
 args = ap.parse_args()
 for shape in args.shapes.split(","):
-    dims = SIZES[shape]
+    dims = tuple(int(x) for x in args.dims.split("x")) if args.dims else SIZES[shape]
     plan = ls.Plan(shape, dims)
     if args.tb:
         plan.temporal_block = args.tb
