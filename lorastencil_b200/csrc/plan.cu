@@ -119,6 +119,8 @@ constexpr int kTb2 = 3;  // the 2-D temporal block (odd, so that time parity == 
 static bool tb2_form(int form) {
     return form == LORA_FORM_CROSS || form == LORA_FORM_DIAMOND || form == LORA_FORM_PYRAMID || form == LORA_FORM_PYRAMID_PRUNED;
 }
+// ... and sweeps of TWO launches (no register spills where three spill): every form but the cross, which is cheap at three
+static bool tb2_pair_form(int form) { return tb2_form(form) && form != LORA_FORM_CROSS; }
 static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
                          int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
                          const double *mirror_base, void *stream);
@@ -240,14 +242,15 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         // ... and where fusion is on by default, a large grid settles it by measurement on first use (probe_tb2)
         p->tb_auto = p->max_tb == kTb2 && p->elems >= (1LL << 22) && p->dims[0] >= 512;
         if (const char *e = getenv("LORA_TB2")) {
-            p->max_tb = (atoi(e) >= kTb2) ? kTb2 : 1;
+            const int v = atoi(e);
+            p->max_tb = v >= kTb2 ? kTb2 : ((v == 2 && tb2_pair_form(p->form)) ? 2 : 1);
             p->tb_auto = false;
         }
     }
     if (dim == 3 && tb3_form(p->form) && !p->odd_cols) {
-        // 3-D fusion (stencil3d_tb.cu): two launches per sweep.  On by default for the 7-point form (433 vs 377
-        // GStencil/s at 512^3); the separable form is built and bit-identical but slower fused (354 vs 384): off
-        p->max_tb = p->form == LORA_FORM_STAR7 ? kTb3 : 1;
+        // 3-D fusion (stencil3d_tb.cu): two launches per sweep, on by default for both forms (512^3: 7-point 581 vs
+        // 380 GStencil/s, separable 452 vs 389; 1024^3: 601 vs 388, 469 vs 389); LORA_TB3=1 turns it off
+        p->max_tb = kTb3;
         if (const char *e = getenv("LORA_TB3")) p->max_tb = (atoi(e) >= kTb3) ? kTb3 : 1;
     }
     if (dim == 1) {
@@ -619,7 +622,8 @@ extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
     if (p->dim == 1)
         p->max_tb = tb < kMaxTb1 ? tb : kMaxTb1;
     else if (p->dim == 2)
-        p->max_tb = (tb >= kTb2 && tb2_form(p->form) && !p->odd_cols) ? kTb2 : 1;  // 2-D fuses exactly 3 launches or none
+        p->max_tb = (tb >= kTb2 && tb2_form(p->form) && !p->odd_cols) ? kTb2
+                    : (tb == 2 && tb2_pair_form(p->form) && !p->odd_cols) ? 2 : 1;  // 2-D fuses 3 or 2 launches, or none
     else
         p->max_tb = (tb >= kTb3 && tb3_form(p->form) && !p->odd_cols) ? kTb3 : 1;  // 3-D fuses exactly 2 launches or none
     return LORA_OK;
@@ -679,8 +683,8 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
                          const double *mirror_base, void *stream) {
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if (tb == 1) return step_unfused(p, src, dst, lo, hi, ex, mirror_base, stream);
-    if (tb != kTb2 || !tb2_form(p->form) || p->odd_cols)
-        return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses exactly %d launches (forms: cross, diamond, pyramid; even column counts)", kTb2);
+    if (!((tb == kTb2 && tb2_form(p->form)) || (tb == 2 && tb2_pair_form(p->form))) || p->odd_cols)
+        return fail(LORA_ERR_UNSUPPORTED, "2-D temporal blocking fuses %d launches (forms: cross, diamond, pyramid) or 2 (diamond, pyramid); even column counts", kTb2);
     if (!halo_src) return fail(LORA_ERR_ARG, "fused 2-D launches need halo_src (the buffer holding the caller's halo)");
     if (lo == hi) return LORA_OK;
     if (int rc = check_device(p)) return rc;
@@ -1035,6 +1039,25 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
             if (rc) return rc;
             left -= tb;
         }
+        return LORA_OK;
+    }
+    if (p->dim == 2 && p->max_tb == 2 && times >= 4) {
+        // Sweeps of 2 launches, an EVEN number of them (so that the data is back in buffer 0 and the remaining 0..3
+        // single launches see the rings they expect, S3).  Every sweep starts at an even time, so its level 0 needs
+        // the caller's halo around its source: the ring of buffer 0 is copied into buffer 1 for the duration and
+        // cleared again afterwards (as for the fused 3-D sweeps below); the intermediate level's halo is virtual.
+        int a = times / 2;
+        a -= a % 2;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const bool ref_mode = p->boundary == LORA_BOUNDARY_REFERENCE;  // otherwise both rings are the same already
+        if (ref_mode)
+            if (int rc = copy_ring(p, buf1, buf0, st)) return rc;
+        for (int k = 0; k < a; k++)
+            if (int rc = step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, 0, p->dims[0], 2, 2 * k, 1, 1, nullptr, nullptr, stream)) return rc;
+        if (ref_mode)
+            if (int rc = copy_ring(p, buf1, nullptr, st)) return rc;
+        for (int i = 2 * a; i < times; i++)
+            if (int rc = lora_plan_step(p, buf[i % 2], buf[(i + 1) % 2], 0, p->dims[0], stream)) return rc;
         return LORA_OK;
     }
     if (p->dim == 3 && p->max_tb == kTb3 && times >= 2 * kTb3 && p->boundary != LORA_BOUNDARY_DIRICHLET) {

@@ -188,6 +188,7 @@ extern "C" int lora_slab_create(lora_slab_t **out, int shape, int mode, const do
         }
         if (temporal_block > 0) lora_plan_set_temporal_block(probe, temporal_block);
         s->max_tb = dim == 3 ? 1 : lora_plan_temporal_block(probe);  // 3-D slabs advance one launch per sweep
+        if (dim == 2 && s->max_tb == 2) s->max_tb = 1;  // ... and 2-D slabs fuse three launches or none
         lora_plan_destroy(probe);
     }
     s->ghost = (s->max_tb > 1 && dim < 3) ? (long long)kRadius0[dim] * s->max_tb : kHalo0[dim];

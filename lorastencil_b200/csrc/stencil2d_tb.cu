@@ -341,6 +341,9 @@ cudaError_t kernels_init_2d_tb() {
     if ((e = opt_in<LORA_FORM_PYRAMID_PRUNED, 3>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_CROSS, 3>()) != cudaSuccess) return e;
     if ((e = opt_in<LORA_FORM_DIAMOND, 3>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_PYRAMID, 2>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_PYRAMID_PRUNED, 2>()) != cudaSuccess) return e;
+    if ((e = opt_in<LORA_FORM_DIAMOND, 2>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -348,6 +351,14 @@ int strip_out_cols_2d_tb(int tb) { return kWarpCols - 8 * (tb - 1); }
 
 cudaError_t launch_2d_tb(int form, int tb, const CUtensorMap &tmap, const Geom2DTB &g, const Weights2D &w,
                          const WeightsDirect49 &wd, cudaStream_t s) {
+    if (tb == 2) {  // two launches per sweep: no spills for the forms that are heavy at three (stencil2d_tb.cu header)
+        switch (form) {
+            case LORA_FORM_PYRAMID: return launch_form<LORA_FORM_PYRAMID, 2>(tmap, g, w, wd, s);
+            case LORA_FORM_PYRAMID_PRUNED: return launch_form<LORA_FORM_PYRAMID_PRUNED, 2>(tmap, g, w, wd, s);
+            case LORA_FORM_DIAMOND: return launch_form<LORA_FORM_DIAMOND, 2>(tmap, g, w, wd, s);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     if (tb != 3) return cudaErrorInvalidValue;
     switch (form) {
         case LORA_FORM_PYRAMID: return launch_form<LORA_FORM_PYRAMID, 3>(tmap, g, w, wd, s);

@@ -344,6 +344,49 @@ def test_temporal_blocking_2d_equals_unfused_launches(shape, dims):
                 assert max_rel_err(results[1], ref) <= RTOL, (shape, dims, times)
 
 
+@pytest.mark.parametrize("shape", ["star2d1r", "box2d1r"])
+@pytest.mark.parametrize("dims", [(40, 130), (64, 64), (300, 258), (257, 1000), (1000, 130), (9, 8), (2, 2), (400, 230)])
+def test_temporal_blocking_2d_pairs_equal_unfused_launches(shape, dims):
+    """2-D sweeps of TWO fused launches (the diamond and pyramid forms: no register spills where three launches spill):
+    an even number of sweeps, the caller's ring copied into buffer 1 for their duration and cleared afterwards, the
+    remaining launches one by one -- same bits as one launch per step, the oracle's values, and both halo rings left
+    as the reference's ping-pong leaves them."""
+    import torch
+    a = oracle.fill_rand(shape, dims)
+    rng = np.random.default_rng(dims[0] * 5 + dims[1])
+    af = rng.uniform(-1, 1, a.shape)
+    eff = oracle.effective_params(shape)
+    plan = ls.Plan(shape, dims)
+    inner = interior(shape, dims)
+    exact_upto = {"box2d1r": 5, "star2d1r": 6}[shape]
+    for data in (a, af):
+        for times in (4, 5, 6, 7, 8, 9, 11, 12):
+            results = []
+            for tb in (1, 2):
+                plan.temporal_block = tb
+                assert plan.temporal_block == tb
+                b0, b1 = torch.from_numpy(data).cuda(), plan.new_buffer()
+                n0 = plan.launches
+                res = plan.run(b0, b1, times)
+                torch.cuda.synchronize()
+                assert res is (b0 if times % 2 == 0 else b1)
+                sweeps = (times // 2) - (times // 2) % 2
+                assert plan.launches - n0 == (times if tb == 1 else sweeps + times - 2 * sweeps)
+                results.append(res.cpu().numpy())
+                h0, h1 = b0.cpu().numpy().copy(), b1.cpu().numpy().copy()
+                d_h = data.copy()
+                h0[inner] = 0.0
+                d_h[inner] = 0.0
+                h1[inner] = 0.0
+                assert np.array_equal(h0, d_h) and not h1.any()
+            assert np.array_equal(results[0], results[1]), (shape, dims, times)
+            ref = oracle.run(shape, data, eff, times)
+            if data is a and times <= exact_upto:
+                assert np.array_equal(results[1], ref), (shape, dims, times)
+            else:
+                assert max_rel_err(results[1], ref) <= RTOL, (shape, dims, times)
+
+
 @pytest.mark.parametrize("shape,dims,times", [("1d1r", (5000,), 31), ("1d2r", (100003,), 16), ("star2d1r", (70, 250), 7),
                                               ("box2d1r", (64, 130), 4), ("star2d3r", (300, 370), 10), ("box3d1r", (9, 34, 130), 4),
                                               ("star3d1r", (12, 8, 64), 5), ("star2d3r", (9, 8), 4)])
@@ -473,7 +516,7 @@ def test_temporal_blocking_3d_equals_unfused_launches(shape, dims):
     af = rng.uniform(-1, 1, a.shape)
     eff = oracle.effective_params(shape)
     plan = ls.Plan(shape, dims)
-    assert plan.temporal_block == (2 if shape == "star3d1r" else 1)  # the separable form is not fused by default
+    assert plan.temporal_block == 2  # both forms are fused by default
     inner = interior(shape, dims)
     for data in (a, af):
         for times in (4, 5, 6, 7, 8, 9, 12, 15):
