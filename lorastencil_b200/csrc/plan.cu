@@ -236,10 +236,11 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     }
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
     if (dim == 2 && tb2_form(p->form) && !p->odd_cols) {
-        // 2-D fusion (stencil2d_tb.cu): on for the cheap forms (cross 560 vs 335 GStencil/s unfused, diamond 387 vs
-        // 327); the pyramid form is FP64-bound already and loses (223 vs 339), so it stays at one launch per step
-        p->max_tb = (p->form == LORA_FORM_CROSS || p->form == LORA_FORM_DIAMOND) ? kTb2 : 1;
-        // ... and where fusion is on by default, a large grid settles it by measurement on first use (probe_tb2)
+        // 2-D fusion (stencil2d_tb.cu), 10240^2 on B200: the cross form runs sweeps of three launches (480 vs 335
+        // GStencil/s unfused); the diamond form sweeps of two (445 vs 370; three spill: 363); the pyramid form is
+        // FP64-bound already and loses either way (345 / 260 vs 375), so it stays at one launch per step
+        p->max_tb = p->form == LORA_FORM_CROSS ? kTb2 : (p->form == LORA_FORM_DIAMOND ? 2 : 1);
+        // ... and for the cross form a large grid settles it by measurement on first use (probe_tb2)
         p->tb_auto = p->max_tb == kTb2 && p->elems >= (1LL << 22) && p->dims[0] >= 512;
         if (const char *e = getenv("LORA_TB2")) {
             const int v = atoi(e);
@@ -868,11 +869,15 @@ extern "C" int lora_plan_set_boundary(lora_plan_t *p, int mode) {
 }
 extern "C" int lora_plan_boundary(const lora_plan_t *p) { return p ? p->boundary : -1; }
 
-// halo ring of dst <- halo ring of src (src == nullptr: zeros), everything outside the interior, nothing inside
-static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStream_t st) {
+// halo ring of dst <- halo ring of src (src == nullptr: zeros), everything outside the interior, nothing inside;
+// restricted to padded indices [r0, r1) of the outermost axis (the bands of run_host_pipelined)
+static int copy_ring_rows(const lora_plan *p, double *dst, const double *src, long long r0, long long r1, cudaStream_t st) {
     static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
     const int dim = p->dim;
     const long long P0 = p->padded[0], rest = p->elems / P0, h0 = halo[dim][0];
+    r0 = std::max(r0, 0LL);
+    r1 = std::min(r1, P0);
+    if (r0 >= r1) return LORA_OK;
     auto flat = [&](long long off, long long cnt) -> cudaError_t {
         if (cnt <= 0) return cudaSuccess;
         return src ? cudaMemcpyAsync(dst + off, src + off, (size_t)cnt * 8, cudaMemcpyDeviceToDevice, st)
@@ -884,19 +889,24 @@ static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStr
                                        cudaMemcpyDeviceToDevice, st)
                    : cudaMemset2DAsync(dst + off, (size_t)pitch * 8, 0, (size_t)width * 8, (size_t)height, st);
     };
-    CU_TRY(flat(0, h0 * rest));                  // leading halo rows / planes (1-D: cells)
-    CU_TRY(flat((P0 - h0) * rest, h0 * rest));   // trailing ones
+    // leading / trailing halo rows / planes (1-D: cells) inside the range
+    CU_TRY(flat(r0 * rest, (std::min(r1, h0) - r0) * rest));
+    CU_TRY(flat(std::max(r0, P0 - h0) * rest, (r1 - std::max(r0, P0 - h0)) * rest));
+    const long long base = r0 * rest, cnt = r1 - r0;
     if (dim == 2) {
-        CU_TRY(strided(0, 4, P0, p->padded[1]));                  // left halo columns of every row
-        CU_TRY(strided(p->padded[1] - 4, 4, P0, p->padded[1]));   // right halo columns
+        CU_TRY(strided(base, 4, cnt, p->padded[1]));                      // left halo columns of every row
+        CU_TRY(strided(base + p->padded[1] - 4, 4, cnt, p->padded[1]));   // right halo columns
     } else if (dim == 3) {
         const long long pitch = p->padded[2], plane = p->padded[1] * pitch;
-        CU_TRY(strided(0, 2 * pitch, P0, plane));                       // 2 leading halo rows of every plane
-        CU_TRY(strided(plane - 2 * pitch, 2 * pitch, P0, plane));       // 2 trailing halo rows
-        CU_TRY(strided(0, 4, P0 * p->padded[1], pitch));                // left halo columns of every row of every plane
-        CU_TRY(strided(pitch - 4, 4, P0 * p->padded[1], pitch));        // right halo columns
+        CU_TRY(strided(base, 2 * pitch, cnt, plane));                          // 2 leading halo rows of every plane
+        CU_TRY(strided(base + plane - 2 * pitch, 2 * pitch, cnt, plane));      // 2 trailing halo rows
+        CU_TRY(strided(base, 4, cnt * p->padded[1], pitch));                   // left halo columns of every row of every plane
+        CU_TRY(strided(base + pitch - 4, 4, cnt * p->padded[1], pitch));       // right halo columns
     }
     return LORA_OK;
+}
+static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStream_t st) {
+    return copy_ring_rows(p, dst, src, 0, p->padded[0], st);
 }
 
 // 3-D fused launch of kTb3 = 2 time steps over interior planes [lo, hi): see stencil3d_tb.cu.  The source buffer's
@@ -1408,6 +1418,12 @@ static bool run_host_1d_chunked(int shape, int mode, const double *in, double *o
     return true;
 }
 
+// sweeps of TWO launches (2-D diamond / pyramid on request, 3-D): every sweep starts at an even time, so the ring of
+// BOTH ping-pong buffers has to hold the caller's halo while they run (lora_plan_run, run_host_pipelined)
+static bool pair_sweeps(const lora_plan *p) {
+    return p->boundary == LORA_BOUNDARY_REFERENCE && ((p->dim == 2 && p->max_tb == 2) || (p->dim == 3 && p->max_tb == kTb3));
+}
+
 // the sweeps lora_plan_run would issue for `times` launches (temporal blocks; their count has the parity of `times`)
 static std::vector<int> plan_schedule(const lora_plan *p, int times) {
     if (p->dim == 1 && p->max_tb > 1 && times > 1) return temporal_schedule(times, p->max_tb);
@@ -1418,6 +1434,14 @@ static std::vector<int> plan_schedule(const lora_plan *p, int times) {
             tbs.push_back(tb);
             left -= tb;
         }
+        return tbs;
+    }
+    if (pair_sweeps(p) && times >= 4) {
+        // sweeps of two launches, an even number of them, then the remaining 0..3 launches one by one (lora_plan_run)
+        int a = times / 2;
+        a -= a % 2;
+        tbs.assign(a, 2);
+        tbs.insert(tbs.end(), times - 2 * a, 1);
         return tbs;
     }
     tbs.assign(times, 1);
@@ -1431,6 +1455,7 @@ static int sweep_range(lora_plan *p, double *buf0, double *buf1, int k, int tb, 
     if (p->dim == 1 && (tb > 1 || p->max_tb > 1))
         return lora_plan_step_fused(p, buf[k % 2], buf[(k + 1) % 2], buf0, lo, hi, tb, done, 1, 1, stream);
     if (p->dim == 2 && tb > 1) return step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, lo, hi, tb, done, 1, 1, nullptr, nullptr, stream);
+    if (p->dim == 3 && tb > 1) return step_fused_3d(p, buf[k % 2], buf[(k + 1) % 2], lo, hi, stream);
     return lora_plan_step(p, buf[k % 2], buf[(k + 1) % 2], lo, hi, stream);
 }
 
@@ -1455,6 +1480,9 @@ static void run_host_pipelined(lora_plan *p, const double *in, double *out, int 
     if (p->tb_auto && times >= kTb2) probe_tb2(p);
     const std::vector<int> tbs = plan_schedule(p, times);
     const int S = (int)tbs.size();
+    int npairs = 0;  // leading sweeps of two launches (pair_sweeps): they need the caller's ring in buffer 1 too
+    if (pair_sweeps(p))
+        for (int tb : tbs) npairs += tb == 2;
     long long rmax = 0;
     for (int tb : tbs) rmax = std::max(rmax, (long long)radius0[p->dim] * tb);
     // few, large bands: every band is swept launch by launch, and launches over a few hundred rows fill the GPU badly
@@ -1509,8 +1537,20 @@ static void run_host_pipelined(lora_plan *p, const double *in, double *out, int 
                                        // the staging memcpy; band k-1's launches are still queued on the GPU meanwhile)
         CU_DIE(cudaStreamWaitEvent(s_comp, in_done[k], 0));
         CU_DIE(cudaEventRecord(t0[k], s_comp));
+        if (npairs > 0) {  // the rows just uploaded: their ring into buffer 1 as well
+            const long long u0 = k == 0 ? 0 : std::min(rows, B[k] + h0), u1 = k == K - 1 ? rows : std::min(rows, B[k + 1] + h0);
+            if (copy_ring_rows(p, b1, b0, u0, u1, s_comp) != LORA_OK) die_plan("ring copy");
+        }
         int launched = 0;
         for (int s = 1; s <= S; s++) {
+            if (npairs > 0 && s == npairs + 1) {
+                // Buffer 1's ring back to zeros before a single launch reads it (and for the download, S3), in the rows
+                // no later band's pair sweeps read from buffer 1 any more: band k+1's last pair sweep reads from interior
+                // row B[k+1] - (npairs + 1) rmax on, this band's single launches stay strictly below that
+                const long long c0 = k == 0 ? 0 : B[k] - (npairs + 1) * rmax + h0;
+                const long long c1 = k == K - 1 ? rows : B[k + 1] - (npairs + 1) * rmax + h0;
+                if (copy_ring_rows(p, b1, nullptr, c0, c1, s_comp) != LORA_OK) die_plan("ring reset");
+            }
             if (sweep_range(p, b0, b1, s - 1, tbs[s - 1], launched, lo_of(k, s), hi_of(k, s), s_comp) != LORA_OK) die_plan("launch");
             launched += tbs[s - 1];
         }

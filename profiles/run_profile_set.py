@@ -17,7 +17,8 @@ import lorastencil_b200 as ls  # noqa: E402
 SET = [("1d2r", (1 << 28,), 15, 15), ("1d1r", (1 << 28,), 15, 15), ("star2d3r", (10240, 10240), 3, 3),
        ("star2d1r", (10240, 10240), 3, 3), ("star2d1r", (10240, 10240), 1, 1), ("box2d3r", (10240, 10240), 1, 1),
        ("box3d1r", (512, 512, 512), 1, 1), ("star3d1r", (512, 512, 512), 1, 1),
-       ("star3d1r", (512, 512, 512), 2, 4), ("box3d1r", (512, 512, 512), 2, 4)]
+       ("star3d1r", (512, 512, 512), 2, 4), ("box3d1r", (512, 512, 512), 2, 4),
+       ("box2d3r", (10240, 10240), 2, 4), ("star2d1r", (10240, 10240), 2, 4)]
 only = sys.argv[1].split(",") if len(sys.argv) > 1 else None  # e.g. star3d1r:2,box3d1r:2 or 1d2r
 for shape, dims, tb, launches in SET:
     if only and shape not in only and f"{shape}:{tb}" not in only:

@@ -177,9 +177,9 @@ def test_plan_api_partial_ranges_and_device_buffers():
             assert np.array_equal(got[:-1], full[:-1])
         else:
             assert np.array_equal(got, full)
-        # 1-D and the 2-D star forms fuse the 3 launches of `run` into one temporally blocked sweep; the FP64-bound
-        # 2-D box form and 3-D launch once per step
-        fused = oracle.dim_of(shape) == 1 or shape in ("star2d1r", "star2d3r")
+        # 1-D and the 2-D cross form fuse the 3 launches of `run` into one temporally blocked sweep; the 2-D diamond form
+        # and 3-D fuse pairs (from 4 launches on), the FP64-bound 2-D box form launches once per step
+        fused = oracle.dim_of(shape) == 1 or shape == "star2d3r"
         assert plan.launches == len(cuts) - 1 + (1 if fused else 3)
 
 
@@ -321,7 +321,8 @@ def test_temporal_blocking_2d_equals_unfused_launches(shape, dims):
     af = rng.uniform(-1, 1, a.shape)
     eff = oracle.effective_params(shape)
     plan = ls.Plan(shape, dims)
-    assert plan.temporal_block == (1 if shape == "box2d1r" else 3)  # the FP64-bound pyramid form is not fused by default
+    # defaults: the FP64-bound pyramid form is not fused, the diamond form fuses two launches, the cross form three
+    assert plan.temporal_block == {"box2d1r": 1, "star2d1r": 2, "star2d3r": 3}[shape]
     exact_upto = {"box2d1r": 5, "star2d1r": 6, "star2d3r": 9}[shape]
     for data in (a, af):
         for times in (3, 4, 5, 6, 7, 9, 10):
@@ -469,12 +470,15 @@ def test_fused_2d_inner_strip_crossing_the_right_edge(shape):
 
 @pytest.mark.parametrize("shape,dims,times", [("box2d3r", (3000, 3072), 4), ("star2d3r", (2500, 4100), 7), ("star2d1r", (4096, 2048), 1),
                                               ("box3d1r", (200, 256, 256), 5), ("star3d1r", (130, 200, 264), 2), ("1d2r", (3000000,), 9),
-                                              ("box2d1r", (4000, 2050), 0)])
+                                              ("box2d1r", (4000, 2050), 0), ("star3d1r", (130, 200, 264), 9), ("star3d1r", (96, 130, 136), 7),
+                                              ("star2d1r", (4096, 2048), 6), ("star2d1r", (3000, 1030), 8), ("box3d1r", (150, 64, 256), 4),
+                                              ("star2d1r", (2000, 1500), 5)])
 def test_copy_overlapped_operator_equals_plain_sequence(shape, dims, times, monkeypatch):
     """The 2-D / 3-D drop-in operators upload band by band under the first sweep and download band by band behind
     the last one (run_host_pipelined); pageable buffers go through pinned staging slots filled by worker threads
     (hostmove.cu).  LORA_BANDS=1 is the plain copy -> launch loop -> copy sequence: same bits, for pageable (numpy) and
-    pinned (torch) caller buffers, halo rows included; and the oracle agrees."""
+    pinned (torch) caller buffers, halo rows included; and the oracle agrees -- also where the bands run sweeps of two
+    launches (3-D, 2-D diamond), which borrow buffer 1's ring for the caller's halo and hand it back zeroed."""
     import torch
     rng = np.random.default_rng(5)
     a = rng.integers(0, 100, size=oracle.padded_shape(shape, dims)).astype(np.float64)
@@ -496,10 +500,16 @@ def test_copy_overlapped_operator_equals_plain_sequence(shape, dims, times, monk
         outs.append(hout.numpy().copy())
     for o in outs:
         assert np.array_equal(o, plain), (shape, dims, times)
+    ref = np.full_like(a, -7.0)
+    oracle.run(shape, a, oracle.effective_params(shape, p), times, out=ref)
     if times in (1, 2):
-        ref = np.full_like(a, -7.0)
-        oracle.run(shape, a, oracle.effective_params(shape, p), times, out=ref)
         assert np.array_equal(plain, ref)
+    else:  # sweeps of two or three launches inside the bands (ring of buffer 1 borrowed and given back): the oracle's values
+        assert max_rel_err(plain, ref) <= RTOL
+        halo = np.ones(a.shape, dtype=bool)
+        halo[interior(shape, dims)] = False
+        if oracle.dim_of(shape) > 1:
+            assert np.array_equal(plain[halo], ref[halo])  # the ring: the caller's or zeros, exactly (S3)
 
 
 @pytest.mark.parametrize("dims", [(16, 16, 64), (40, 50, 130), (7, 33, 132), (64, 64, 64), (30, 22, 120), (33, 23, 122), (5, 100, 400),
