@@ -22,7 +22,7 @@ constexpr int kStageLoad1 = kStageRows1 * kRowElems + 8;   // doubles fetched pe
 __global__ void __launch_bounds__(32 * kWarpsPerCta, 4)
 k_stencil1d(const __grid_constant__ Geom1D g, const __grid_constant__ Weights1D w) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (task >= g.ntasks) return;
 

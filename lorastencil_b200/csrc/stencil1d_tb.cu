@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, kTbCtasPerSm)
 k_stencil1d_tb(const __grid_constant__ CUtensorMap imap, const __grid_constant__ CUtensorMap omap,
                const __grid_constant__ Geom1DTB g, const __grid_constant__ Weights1D w) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const long long task = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (task >= g.ntasks) return;  // warps never synchronise with each other
     const int TB = g.tb;

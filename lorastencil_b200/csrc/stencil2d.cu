@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta,
 k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2D g,
             const __grid_constant__ Weights2D w, const __grid_constant__ WeightsDirect49 wd) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int task = blockIdx.x * kWarpsPerCta + warp;
     if (task >= g.ntasks) return;  // warps never synchronise with each other
 

@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta, 2)
 k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2DTB g,
                const __grid_constant__ Weights2D w, const __grid_constant__ WeightsDirect49 wd) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
     const int task = blockIdx.x * kWarpsPerCta + warp;
     if (task >= g.ntasks) return;  // warps never synchronise with each other
 
@@ -311,7 +311,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     __syncwarp();
 
     sweep_rows<FORM, TB>(s, w, wd);
-    const int seg_done = seg_of(g.sg, blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5));  // recomputed: not kept live
+    const int seg_done = seg_of(g.sg, blockIdx.x * kWarpsPerCta + uniform_warp_id());  // recomputed: not kept live
     if (g.sg.flag[seg_done] != nullptr) {  // a band task: tell the neighbour once every task of the band has stored
         __threadfence_system();
         __syncwarp();

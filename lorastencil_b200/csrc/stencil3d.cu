@@ -200,7 +200,7 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + k3Stages * k3StageBytes);
     uint64_t *empty = full + k3Stages;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
     const int tile_n = blockIdx.x % g.tiles_n, tile_m = blockIdx.x / g.tiles_n;
     const int seg = seg_of(g.sg, blockIdx.y);  // band segments come first in blockIdx.y, i.e. in dispatch order

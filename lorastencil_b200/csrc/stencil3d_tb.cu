@@ -179,7 +179,7 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     double *edge = reinterpret_cast<double *>(smem_raw + k3Stages * kT3StageBytes);  // [2][k3Warps][2][k3TileCols]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + k3Stages * kT3StageBytes + kT3EdgeBytes);
     uint64_t *empty = full + k3Stages;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
 
     const int tile_n = blockIdx.x % g.tiles_n, tile_m = blockIdx.x / g.tiles_n;
     const int h0 = (int)(g.h_lo + (long long)blockIdx.y * g.planes_per_chunk);  // first output plane of the chunk
@@ -233,14 +233,14 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; q++) L1.full[r][q] = L1.next[r][q] = L2.full[r][q] = L2.next[r][q] = 0.0;
 
-    for (int i = 0; i < nin; i++) {
-        // ---- level 0 -> level 1: plane q = h0 - 2 + i arrives, level-1 plane q - 1 completes
+    // ---- level 0 -> level 1: plane q = h0 - 2 + i arrives, level-1 plane q - 1 completes (V: the lane's cells, EV: its
+    // extra cell)
+    auto level1 = [&](int i, double (&V)[RM][4], double &EV) {
         const int slot = i % k3Stages;
         mbar_wait(&full[slot], (i / k3Stages) & 1);
         const double *tile = reinterpret_cast<const double *>(smem_raw + slot * kT3StageBytes);
         const int j1 = h0 - 3 + i;  // the level-1 plane that completes now
         const bool plane1_in = j1 >= 0 && j1 < g.h;
-        double V[RM][4];
         level<FORM>(w, [&](int rr, double (&row)[8], bool full_row) {
             // box row RM*warp + rr; box column = region column + 2
             const double *rowp = tile + (RM * warp + rr) * k3BoxCols + 2;
@@ -255,7 +255,7 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 row[1] = a.x, row[2] = a.y, row[5] = b.x, row[6] = b.y;
             }
         }, L1, V);
-        double EV = edge_cell<FORM>(w, tile + ebox, k3BoxCols, E1);
+        EV = edge_cell<FORM>(w, tile + ebox, k3BoxCols, E1);
         // the stage's values are in registers (consumed by the level): release it, refill the one released a plane ago
         __syncwarp();
         if (lane == 0) {
@@ -277,7 +277,19 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                     if (!(plane1_in && rowin[r] && colin[q])) V[r][q] = 0.0;
         }
         if (!(plane1_in && ein)) EV = 0.0;
-        if (i < 2) continue;  // CTA-uniform: level-1 planes before h0 - 1 are not needed
+    };
+
+    // The first two planes only warm level 1 up (level-1 planes before h0 - 1 are not needed).  Peeled, not skipped with
+    // a `continue`: with the early exit in the loop ptxas treats the loop as divergent and keeps the weights in vector
+    // registers; peeled, the weights are uniform-register operands and the kernel needs ~30 registers less.
+    {
+        double V[RM][4], EV;
+        level1(0, V, EV);
+        level1(1, V, EV);
+    }
+    for (int i = 2; i < nin; i++) {
+        double V[RM][4], EV;
+        level1(i, V, EV);
 
         // ---- level 1 -> level 2: the rows above / below come through shared memory (first / last row of every warp),
         // everything else from the lane's own registers and its neighbours' by shuffle
