@@ -26,3 +26,6 @@ int lora_plan_step_exchange(lora_plan_t *p, const double *src, double *dst, cons
 
 // error text for the calling thread (lora_last_error), settable from slab.cu / peer.cu
 int lora_fail(int code, const char *fmt, ...);
+// halo ring of dst <- halo ring of src (src == nullptr: zeros): side halo of every local row / plane, leading / trailing
+// halo rows only if `lead` / `trail` (sweeps of two launches borrow buffer 1's ring for the caller's halo)
+int lora_plan_copy_ring(lora_plan_t *p, double *dst, const double *src, int lead, int trail, void *stream);

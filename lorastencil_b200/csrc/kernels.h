@@ -58,7 +58,8 @@ constexpr int k3BoxRows = k3TileRows + 2;
 constexpr int k3BoxCols = k3TileCols + 4;  // 2 halo columns each side keeps the box origin 16-byte aligned
 constexpr int k3Stages = 4;
 constexpr int k3StageBytes = ((k3BoxRows * k3BoxCols * 8 + 127) / 128) * 128;
-constexpr int k3Smem = k3Stages * k3StageBytes + 2 * k3Stages * 8;
+constexpr int k3GuardBytes = 128;  // one guard word per warp (stage release, see stencil3d.cu: plane_phase)
+constexpr int k3Smem = k3Stages * k3StageBytes + 2 * k3Stages * 8 + k3GuardBytes;
 constexpr int k3Warps = 8;
 constexpr int k3Threads = 32 * k3Warps;
 
@@ -72,7 +73,7 @@ constexpr int kT3BoxRows = kT3Rows + 2;
 constexpr int kT3StageBytes = ((kT3BoxRows * k3BoxCols * 8 + 127) / 128) * 128;
 constexpr int kT3EdgePitch = k3TileCols + 4;  // columns -2 .. 129 of a level-1 edge row
 constexpr int kT3EdgeBytes = 2 * k3Warps * 2 * kT3EdgePitch * 8;  // first / last level-1 row of every warp, double-buffered
-constexpr int kT3Smem = k3Stages * kT3StageBytes + kT3EdgeBytes + 2 * k3Stages * 8;
+constexpr int kT3Smem = k3Stages * kT3StageBytes + kT3EdgeBytes + 2 * k3Stages * 8 + k3GuardBytes;
 
 struct Weights1D {
     double w[9];

@@ -236,10 +236,9 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     }
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
     if (dim == 2 && tb2_form(p->form) && !p->odd_cols) {
-        // 2-D fusion (stencil2d_tb.cu), 10240^2 on B200: the cross form runs sweeps of three launches (480 vs 335
-        // GStencil/s unfused); the diamond form sweeps of two (445 vs 370; three spill: 363); the pyramid form is
-        // FP64-bound already and loses either way (345 / 260 vs 375), so it stays at one launch per step
-        p->max_tb = p->form == LORA_FORM_CROSS ? kTb2 : (p->form == LORA_FORM_DIAMOND ? 2 : 1);
+        // 2-D fusion (stencil2d_tb.cu), 10240^2 on B200, GStencil/s: the cross form runs sweeps of three launches (627 vs
+        // 369 unfused); the diamond and pyramid forms sweeps of two (538 vs 370, three: 515; 418 vs 372, three: 318)
+        p->max_tb = p->form == LORA_FORM_CROSS ? kTb2 : 2;
         // ... and for the cross form a large grid settles it by measurement on first use (probe_tb2)
         p->tb_auto = p->max_tb == kTb2 && p->elems >= (1LL << 22) && p->dims[0] >= 512;
         if (const char *e = getenv("LORA_TB2")) {
@@ -871,7 +870,8 @@ extern "C" int lora_plan_boundary(const lora_plan_t *p) { return p ? p->boundary
 
 // halo ring of dst <- halo ring of src (src == nullptr: zeros), everything outside the interior, nothing inside;
 // restricted to padded indices [r0, r1) of the outermost axis (the bands of run_host_pipelined)
-static int copy_ring_rows(const lora_plan *p, double *dst, const double *src, long long r0, long long r1, cudaStream_t st) {
+static int copy_ring_rows(const lora_plan *p, double *dst, const double *src, long long r0, long long r1, cudaStream_t st,
+                          bool lead = true, bool trail = true) {
     static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
     const int dim = p->dim;
     const long long P0 = p->padded[0], rest = p->elems / P0, h0 = halo[dim][0];
@@ -889,9 +889,10 @@ static int copy_ring_rows(const lora_plan *p, double *dst, const double *src, lo
                                        cudaMemcpyDeviceToDevice, st)
                    : cudaMemset2DAsync(dst + off, (size_t)pitch * 8, 0, (size_t)width * 8, (size_t)height, st);
     };
-    // leading / trailing halo rows / planes (1-D: cells) inside the range
-    CU_TRY(flat(r0 * rest, (std::min(r1, h0) - r0) * rest));
-    CU_TRY(flat(std::max(r0, P0 - h0) * rest, (r1 - std::max(r0, P0 - h0)) * rest));
+    // leading / trailing halo rows / planes (1-D: cells) inside the range (a slab that faces a neighbour keeps ghost
+    // rows there instead: not part of the ring)
+    if (lead) CU_TRY(flat(r0 * rest, (std::min(r1, h0) - r0) * rest));
+    if (trail) CU_TRY(flat(std::max(r0, P0 - h0) * rest, (r1 - std::max(r0, P0 - h0)) * rest));
     const long long base = r0 * rest, cnt = r1 - r0;
     if (dim == 2) {
         CU_TRY(strided(base, 4, cnt, p->padded[1]));                      // left halo columns of every row
@@ -907,6 +908,13 @@ static int copy_ring_rows(const lora_plan *p, double *dst, const double *src, lo
 }
 static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStream_t st) {
     return copy_ring_rows(p, dst, src, 0, p->padded[0], st);
+}
+// for the slab driver (exchange.h): the ring of a slab's local array -- the side halo of every local row / plane, and the
+// leading / trailing halo rows only where the slab ends the grid
+int lora_plan_copy_ring(lora_plan_t *p, double *dst, const double *src, int lead, int trail, void *stream) {
+    if (!p || !dst) return fail(LORA_ERR_ARG, "null argument");
+    if (int rc = check_device(p)) return rc;
+    return copy_ring_rows(p, dst, src, 0, p->padded[0], static_cast<cudaStream_t>(stream), lead != 0, trail != 0);
 }
 
 // 3-D fused launch of kTb3 = 2 time steps over interior planes [lo, hi): see stencil3d_tb.cu.  The source buffer's

@@ -109,6 +109,13 @@ std::vector<int> schedule_for(int dim, int times, int max_tb) {
     } else if (dim == 2 && max_tb >= 3) {
         for (int i = 0; i < times / 3; i++) tbs.push_back(3);
         for (int i = 0; i < times % 3; i++) tbs.push_back(1);
+    } else if (dim == 2 && max_tb == 2 && times >= 4) {
+        // sweeps of two launches, an even number of them (the data is back in buffer 0), the rest one by one; the ring
+        // of buffer 1 holds the caller's halo while they run (pair_ring below; same rule as lora_plan_run)
+        int a = times / 2;
+        a -= a % 2;
+        tbs.assign(a, 2);
+        tbs.insert(tbs.end(), times - 2 * a, 1);
     } else {
         tbs.assign(times, 1);
     }
@@ -136,6 +143,20 @@ struct lora_slab {
     unsigned long long seq = 0;              // sweeps issued: the flags only ever grow
     long long launch = 0, time = 0;          // result sits in buf[launch % 2]
 };
+
+// Sweeps of two launches start at even times: level 0 must see the caller's halo around BOTH buffers while they run.
+// before != 0: ring of buffer 1 <- ring of buffer 0; else: ring of buffer 1 <- zeros (S2 again for the single launches
+// that follow and for the result).  Only ring cells are touched -- the neighbours' mirror stores write interior
+// columns of the ghost rows only -- so this needs no ordering against the neighbours.
+static int pair_ring(lora_slab *s, int before, void *stream) {
+    return lora_plan_copy_ring(s->plan, s->buf[1], before ? s->buf[0] : nullptr, !s->g.has_prev, !s->g.has_next, stream);
+}
+static int count_pairs(const std::vector<int> &tbs, int dim, int max_tb) {
+    int a = 0;
+    if (dim == 2 && max_tb == 2)
+        for (int tb : tbs) a += tb == 2;
+    return a;
+}
 
 extern "C" int lora_slab_geometry(int dim, const long long *global_dims, int world, int rank, long long ghost,
                                   long long *out8) {
@@ -188,7 +209,6 @@ extern "C" int lora_slab_create(lora_slab_t **out, int shape, int mode, const do
         }
         if (temporal_block > 0) lora_plan_set_temporal_block(probe, temporal_block);
         s->max_tb = dim == 3 ? 1 : lora_plan_temporal_block(probe);  // 3-D slabs advance one launch per sweep
-        if (dim == 2 && s->max_tb == 2) s->max_tb = 1;  // ... and 2-D slabs fuse three launches or none
         lora_plan_destroy(probe);
     }
     s->ghost = (s->max_tb > 1 && dim < 3) ? (long long)kRadius0[dim] * s->max_tb : kHalo0[dim];
@@ -357,10 +377,18 @@ extern "C" int lora_slab_run(lora_slab_t *s, int times, void *stream) {
     }
     if (s->max_tb > 1 && s->launch % 2 != s->time % 2)
         return lora_fail(LORA_ERR_ARG, "fused runs must start from a parity-consistent state");
-    for (int tb : schedule_for(s->g.dim, times, s->max_tb)) {
-        int rc = lora_slab_sweep(s, tb, stream);
+    const std::vector<int> tbs = schedule_for(s->g.dim, times, s->max_tb);
+    const int pairs = count_pairs(tbs, s->g.dim, s->max_tb);
+    if (pairs > 0)
+        if (int rc = pair_ring(s, 1, stream)) return rc;
+    for (size_t k = 0; k < tbs.size(); k++) {
+        if (pairs > 0 && (int)k == pairs)
+            if (int rc = pair_ring(s, 0, stream)) return rc;
+        int rc = lora_slab_sweep(s, tbs[k], stream);
         if (rc) return rc;
     }
+    if (pairs > 0 && (int)tbs.size() == pairs)
+        if (int rc = pair_ring(s, 0, stream)) return rc;
     return LORA_OK;
 }
 
@@ -478,11 +506,22 @@ extern "C" int lora_slabset_run(lora_slabset_t *set, int times) {
         if (s0->max_tb > 1 && s0->launch % 2 != s0->time % 2)
             rc = lora_fail(LORA_ERR_ARG, "fused runs must start from a parity-consistent state");
         const std::vector<int> tbs = schedule_for(set->dim, times, s0->max_tb);
-        for (size_t k = 0; k < tbs.size() && !rc; k++)
+        const int pairs = count_pairs(tbs, set->dim, s0->max_tb);
+        auto ring_all = [&](int before) {
+            for (int r = 0; r < set->ndev && !rc; r++) {
+                cudaSetDevice(set->devices[r]);
+                rc = pair_ring(set->slabs[r], before, set->streams[r]);
+            }
+        };
+        if (pairs > 0) ring_all(1);
+        for (size_t k = 0; k < tbs.size() && !rc; k++) {
+            if (pairs > 0 && (int)k == pairs) ring_all(0);
             for (int r = 0; r < set->ndev && !rc; r++) {
                 cudaSetDevice(set->devices[r]);
                 rc = lora_slab_sweep(set->slabs[r], tbs[k], set->streams[r]);
             }
+        }
+        if (pairs > 0 && (int)tbs.size() == pairs) ring_all(0);
     }
     if (cur >= 0) cudaSetDevice(cur);
     return rc;

@@ -98,6 +98,7 @@ struct Sweep3D {
     double *optr;        // output plane pointer for this lane's micro-tile origin (advances by plane_pitch)
     long long row_pitch, plane_pitch, mirror;
     int nin, warp, lane;
+    volatile int *guard;       // shared memory: one word per warp (the guard store of the stage release)
     int rows_left, cols_left;  // how many of the 4 micro-tile rows / columns exist
     bool vec4;
     int hout;                  // interior plane index of the next plane to be stored
@@ -128,14 +129,30 @@ __device__ __forceinline__ void plane_phase(int i, Sweep3D &s, double (&A)[3][4]
             X[rr][2 * k + 1] = v.y;
         }
     }
+    // Release the stage -- but only once its values have ARRIVED in the registers, not merely once the loads have been
+    // issued: the mbarrier arrive does not queue behind the warp's shared-memory loads, and with eight warps' loads
+    // backed up in the load / store unit the refill (which needs nothing but the eight arrivals and an L2 hit) was seen
+    // landing on rows a delayed LDS had yet to read -- a handful of wrong rows per 10^5 planes, run-to-run differences
+    // in profiles/debug/tb3_stress.py.  A shared-memory store of a word computed from every loaded value cannot issue
+    // before the loads have completed, and the arrive follows it in program order.
+    {
+        int gw = 0;
+#pragma unroll
+        for (int rr = 0; rr < 6; rr++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) gw ^= __double2hiint(X[rr][2 * k]);
+        *s.guard = gw;
+    }
     __syncwarp();
-    if (s.lane == 0) {
-        mbar_arrive(&s.empty[slot]);  // this warp no longer needs the stage
-        // producer duty: refill the slot every warp released one plane ago with plane i - 1 + k3Stages
-        const int nx = i - 1 + k3Stages;
-        if (s.warp == 0 && i >= 1 && nx < s.nin) {
-            const int ps = (i - 1) % k3Stages;
-            mbar_wait(&s.empty[ps], ((i - 1) / k3Stages) & 1);
+    if (s.lane == 0) mbar_arrive(&s.empty[slot]);  // this warp no longer needs the stage
+    // producer duty: refill the slot every warp released one plane ago with plane i - 1 + k3Stages.  All of warp 0 waits
+    // (a warp-uniform branch): a spin loop under `lane == 0` makes ptxas treat the plane loop as divergent, and the
+    // weights then sit in vector registers instead of uniform ones
+    const int nx = i - 1 + k3Stages;
+    if (s.warp == 0 && i >= 1 && nx < s.nin) {
+        const int ps = (i - 1) % k3Stages;
+        mbar_wait(&s.empty[ps], ((i - 1) / k3Stages) & 1);
+        if (s.lane == 0) {
             mbar_arrive_expect_tx(&s.full[ps], k3BoxRows * k3BoxCols * 8);
             tma_load_3d(const_cast<unsigned char *>(s.ring) + ps * k3StageBytes, s.tmap, s.box_c, s.box_r,
                         s.box_h + nx, &s.full[ps]);
@@ -234,6 +251,7 @@ k_stencil3d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     s.box_h = h0;
     s.full = full;
     s.empty = empty;
+    s.guard = reinterpret_cast<volatile int *>(empty + k3Stages) + warp;
     s.nin = nin;
     s.warp = warp;
     s.lane = lane;

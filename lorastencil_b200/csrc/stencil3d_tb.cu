@@ -180,6 +180,7 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + k3Stages * kT3StageBytes + kT3EdgeBytes);
     uint64_t *empty = full + k3Stages;
     const int warp = uniform_warp_id(), lane = threadIdx.x & 31;
+    volatile int *guard = reinterpret_cast<volatile int *>(empty + k3Stages) + warp;  // stage release, see level1
 
     const int tile_n = blockIdx.x % g.tiles_n, tile_m = blockIdx.x / g.tiles_n;
     const int h0 = (int)(g.h_lo + (long long)blockIdx.y * g.planes_per_chunk);  // first output plane of the chunk
@@ -241,29 +242,37 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const double *tile = reinterpret_cast<const double *>(smem_raw + slot * kT3StageBytes);
         const int j1 = h0 - 3 + i;  // the level-1 plane that completes now
         const bool plane1_in = j1 >= 0 && j1 < g.h;
+        int gw = 0;  // a word computed from every value loaded from the stage (the guard store below)
         level<FORM>(w, [&](int rr, double (&row)[8], bool full_row) {
             // box row RM*warp + rr; box column = region column + 2
             const double *rowp = tile + (RM * warp + rr) * k3BoxCols + 2;
             const double2 a = *reinterpret_cast<const double2 *>(rowp + 2 * lane);
             const double2 b = *reinterpret_cast<const double2 *>(rowp + 64 + 2 * lane);
+            gw ^= __double2hiint(a.x) ^ __double2hiint(b.x);
             if (full_row) {
                 double e = 0.0;
                 if (lane == 0) e = rowp[-1];       // region column -1
                 if (lane == 31) e = rowp[128];     // region column 128
+                gw ^= __double2hiint(e);
                 window_row(a.x, a.y, b.x, b.y, lane, e, e, row);
             } else {
                 row[1] = a.x, row[2] = a.y, row[5] = b.x, row[6] = b.y;
             }
         }, L1, V);
         EV = edge_cell<FORM>(w, tile + ebox, k3BoxCols, E1);
-        // the stage's values are in registers (consumed by the level): release it, refill the one released a plane ago
+        // Release the stage and refill the one released a plane ago -- once the stage's values have ARRIVED in registers
+        // (stencil3d.cu, plane_phase): the store of a word computed from all of them cannot issue before the loads have
+        // completed, and the arrive follows it in program order
+        *guard = gw ^ __double2hiint(EV);
+        // (the producer's wait is done by all of warp 0, a warp-uniform branch: a spin loop under `lane == 0` makes
+        // ptxas treat the whole plane loop as divergent, and the weights then live in vector registers)
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&empty[slot]);
-            const int nx = i - 1 + k3Stages;
-            if (warp == 0 && i >= 1 && nx < nin) {
-                const int ps = (i - 1) % k3Stages;
-                mbar_wait(&empty[ps], ((i - 1) / k3Stages) & 1);
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        const int nx = i - 1 + k3Stages;
+        if (warp == 0 && i >= 1 && nx < nin) {
+            const int ps = (i - 1) % k3Stages;
+            mbar_wait(&empty[ps], ((i - 1) / k3Stages) & 1);
+            if (lane == 0) {
                 mbar_arrive_expect_tx(&full[ps], kT3BoxRows * k3BoxCols * 8);
                 tma_load_3d(smem_raw + ps * kT3StageBytes, &tmap, box_c, box_r, box_h + nx, &full[ps]);
             }

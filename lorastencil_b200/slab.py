@@ -61,12 +61,18 @@ def temporal_schedule(times: int, max_tb: int):
 
 
 def temporal_schedule_2d(times: int, max_tb: int):
-    """2-D fuses exactly 3 launches or none: sweeps of 3, then the remainder one by one.  Every sweep advances an odd
-    number of steps, so sweep k reads buf[k % 2] at a time of parity k % 2 (the source buffer's own halo ring is the
-    right one for level 0) and the result lands in buf[times % 2] (S3)."""
-    if max_tb < 3:
-        return [1] * times
-    return [3] * (times // 3) + [1] * (times % 3)
+    """2-D fuses 3 launches (cross form), 2 (diamond / pyramid) or none.  Sweeps of 3, then the remainder one by one:
+    every sweep advances an odd number of steps, so sweep k reads buf[k % 2] at a time of parity k % 2 (the source
+    buffer's own halo ring is the right one for level 0) and the result lands in buf[times % 2] (S3)."""
+    if max_tb >= 3:
+        return [3] * (times // 3) + [1] * (times % 3)
+    if max_tb == 2 and times >= 4:
+        # sweeps of two launches (diamond / pyramid forms, native slab driver only): an even number of them, so that the
+        # data is back in buffer 0 when the remaining launches run one by one (csrc/slab.cu: schedule_for)
+        a = times // 2
+        a -= a % 2
+        return [2] * a + [1] * (times - 2 * a)
+    return [1] * times
 
 
 class SlabGeometry:
@@ -206,7 +212,9 @@ class SlabRunner:
         if dim == 1:
             self.max_tb = max(1, min(MAX_TB_1D, temporal_block))
         elif dim == 2:
-            self.max_tb = 3 if temporal_block >= 3 else 1  # 2-D fuses exactly 3 launches or none
+            # 2-D fuses 3 launches, or 2 (which borrow buffer 1's halo ring: the native peer-memory driver only), or none
+            pairs_ok = self.cuda and not injected and os.environ.get("LORA_HALO", "p2p") == "p2p"
+            self.max_tb = 3 if temporal_block >= 3 else (2 if temporal_block == 2 and pairs_ok else 1)
         else:
             self.max_tb = 1
         if injected and fused_fn is None:
@@ -258,6 +266,8 @@ class SlabRunner:
                 if self.rank == 0:
                     print(f"lorastencil_b200.slab: peer-memory halo exchange unavailable ({err}); using NCCL", flush=True)
         if self.halo_mode != "p2p":
+            if dim == 2 and self.max_tb == 2:
+                self.max_tb = 1  # pairs need the native driver; the ghost rows stay as wide as they are
             if not injected:
                 from .plan import Plan
                 self.plan = Plan(shape, g.local_dims, params=params, mode=mode)
