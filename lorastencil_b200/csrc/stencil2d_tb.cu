@@ -111,16 +111,19 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
     // after the stage's last loads were *issued* (round 1) let a refill that hits in L2 land before a delayed LDS had
     // read its row -- observed about once per 10^6 refills when several grids share the SMs (multi-GPU slabs on one
     // device): the lanes then saw the row 16 rows further down.  Two safe orders:
-    //   * late: refill after the push -- the FP64 operations cannot issue before the LDS data is in the registers;
+    //   * late: refill after the push, behind the same guard store (arithmetic is free to move across the refill's asm,
+    //     so "after the push" alone orders nothing);
     //   * early (cross form: +6.6 %, 450 -> 480 GStencil/s; the diamond form loses 11 % to extra spills): refill before
     //     the push, but behind a shared-memory store of the XOR of every value of the row -- that store cannot issue
     //     before the loads have completed, and the TMA is issued after it in program order.
     constexpr bool kEarlyRefill = FORM == LORA_FORM_CROSS;
     const bool refill_row = rr == kRowsPerStage - 1 || i == s.nin - 1;
-    if (kEarlyRefill && refill_row) {
-        int guard = 0;
+    int guard = 0;
+    if (refill_row) {
 #pragma unroll
         for (int k = 0; k < 12; k++) guard ^= __double2hiint(x[k]);
+    }
+    if (kEarlyRefill && refill_row) {
         __syncwarp();  // every lane has its values of this stage
         if (s.lane == 0 && st + kStages < s.nst) {
             *s.scratch = guard;
@@ -133,6 +136,7 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
     if (!kEarlyRefill && refill_row) {
         __syncwarp();  // every lane has consumed this stage
         if (s.lane == 0 && st + kStages < s.nst) {
+            *s.scratch = guard;  // behind the push in program order is not enough for ptxas: the same guard store
             mbar_arrive_expect_tx(&s.bars[slot], kStageElems * 8);
             tma_load_2d(s.ring + slot * kStageElems, s.tmap, s.boxcol, s.row0_padded + (st + kStages) * kRowsPerStage,
                         &s.bars[slot]);
