@@ -707,7 +707,7 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
         if (i == sc.n - 1) {  // the main segment (the only one of a plain launch): the planner of plan_tasks_2dtb
             g.row_lo = (int)sc.lo[i];
             g.row_hi = (int)sc.hi[i];
-            plan_tasks_2dtb(g, rows, (long long)p->sm_count * 2 * kWarpsPerCta);
+            plan_tasks_2dtb(g, rows, (long long)p->sm_count * (tb == 2 ? 3 : 2) * kWarpsPerCta);  // resident warps: stencil2d_tb.cu
             chunk[i] = g.rows_per_chunk;
             tasks[i] = g.ntasks;
         } else {  // a band: short tasks, every strip

@@ -40,8 +40,8 @@ struct Sweep2D {
 
 // one input row: wait for its stage if it opens one, read the window, push, retire the oldest
 // accumulator, refill the ring if the row closes a stage
-template <int FORM, int PH>
-__device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4], const Weights2D &w,
+template <int FORM>
+__device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[kAcc][4], const Weights2D &w,
                                           const WeightsDirect49 &wd) {
     const int st = i / kRowsPerStage, rr = i % kRowsPerStage, slot = st % kStages;
     if (rr == 0) mbar_wait(&s.bars[slot], (st / kStages) & 1);
@@ -53,9 +53,8 @@ __device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4
         x[2 * k] = v.x;
         x[2 * k + 1] = v.y;
     }
-    push_row<FORM, PH>(x, A, w, wd);
-
-    double(&done)[4] = A[PH % NACC];  // logical accumulator 0: output row i - 6 of the chunk
+    double done[4];  // output row i - 6 of the chunk
+    push_row<FORM>(x, A, done, w, wd);
     if (i >= 6) {
         if (s.ncols_left >= 4) {
             if (s.vec4) {
@@ -86,7 +85,6 @@ __device__ __forceinline__ void row_phase(int i, Sweep2D &s, double (&A)[NACC][4
         }
         s.orow += s.pitch;
     }
-    // `done` is reborn as logical accumulator 6 by the next row's dr = -3 term (an assignment): no zeroing
 
     if (rr == kRowsPerStage - 1 || i == s.nin - 1) {
         __syncwarp();  // every lane has consumed this stage
@@ -144,21 +142,13 @@ k_stencil2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Ge
     }
     __syncwarp();
 
-    double A[NACC][4];
+    double A[kAcc][4];
 #pragma unroll
-    for (int j = 0; j < NACC; j++)
+    for (int j = 0; j < kAcc; j++)
 #pragma unroll
         for (int q = 0; q < 4; q++) A[j][q] = 0.0;
 
-    for (int base = 0; base < s.nin; base += NACC) {
-        if (base + 0 < s.nin) row_phase<FORM, 0>(base + 0, s, A, w, wd);
-        if (base + 1 < s.nin) row_phase<FORM, 1>(base + 1, s, A, w, wd);
-        if (base + 2 < s.nin) row_phase<FORM, 2>(base + 2, s, A, w, wd);
-        if (base + 3 < s.nin) row_phase<FORM, 3>(base + 3, s, A, w, wd);
-        if (base + 4 < s.nin) row_phase<FORM, 4>(base + 4, s, A, w, wd);
-        if (base + 5 < s.nin) row_phase<FORM, 5>(base + 5, s, A, w, wd);
-        if (base + 6 < s.nin) row_phase<FORM, 6>(base + 6, s, A, w, wd);
-    }
+    for (int i = 0; i < s.nin; i++) row_phase<FORM>(i, s, A, w, wd);
     const int seg_done = seg_of(g.sg, task);  // recomputed: not kept live across the sweep
     if (g.sg.flag[seg_done] != nullptr) {  // a band task: tell the neighbour once every task of the band has stored
         __threadfence_system();

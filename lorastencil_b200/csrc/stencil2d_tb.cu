@@ -94,8 +94,8 @@ __device__ __forceinline__ void patch_row(double (&v)[4], int i_row, int rho, in
     }
 }
 
-template <int FORM, int TB, bool EDGE, int PH>
-__device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NACC][4], const Weights2D &w,
+template <int FORM, int TB, bool EDGE>
+__device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][kAcc][4], const Weights2D &w,
                                           const WeightsDirect49 &wd) {
     const int st = i / kRowsPerStage, rr = i % kRowsPerStage, slot = st % kStages;
     if (rr == 0) mbar_wait(&s.bars[slot], (st / kStages) & 1);
@@ -132,7 +132,8 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
                         &s.bars[slot]);
         }
     }
-    push_row<FORM, PH>(x, A[0], w, wd);
+    double v[4];  // the row level 1 completes: rho0 + i - 3
+    push_row<FORM>(x, A[0], v, w, wd);
     if (!kEarlyRefill && refill_row) {
         __syncwarp();  // every lane has consumed this stage
         if (s.lane == 0 && st + kStages < s.nst) {
@@ -143,14 +144,9 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
         }
     }
 
-    double v[4];
 #pragma unroll
-    for (int lv = 1; lv <= TB; lv++) {
-        // retire logical accumulator 0 of level lv: its row is  rho0 + i - 3 lv
-        double(&done)[4] = A[lv - 1][PH % NACC];
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = done[q];  // reborn by the next row's dr = -3 term (an assignment)
-        if (lv == TB) break;
+    for (int lv = 1; lv < TB; lv++) {
+        // v = the row level lv has just completed: rho0 + i - 3 lv
         if (EDGE) patch_row(v, i - 3 * lv, s.rho0 + i - 3 * lv, lv, s);
         // window of level lv: own 4 columns + 3 from either neighbour lane
         x[4] = v[0];
@@ -165,7 +161,7 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
         x[10] = __shfl_down_sync(kFull, v[2], 1);
         x[0] = 0.0;
         x[11] = 0.0;
-        push_row<FORM, PH>(x, A[lv], w, wd);
+        push_row<FORM>(x, A[lv], v, w, wd);
     }
 
     // v = level TB, row rho0 + i - 3 TB
@@ -205,45 +201,60 @@ __device__ __forceinline__ void row_phase(int i, SweepTB &s, double (&A)[TB][NAC
     }
 }
 
-// The row loop.  Groups of 7 rows (one turn of the accumulator rings) whose retired rows can meet the halo ring run
-// the phases WITH the patch code, all others the lean phases: a task at the top or bottom of the grid pays for
-// the patch code during its first / last few groups only; tasks of the first / last strip pay for it throughout.
+// rows per trip of the row loop: the light cross form wants a few rows in flight for the scheduler to interleave, the
+// FP64-heavy forms want the smallest loop body (instruction cache)
+#ifndef LORA_ROWS_UNROLL
+#define LORA_ROWS_UNROLL 0
+#endif
+template <int FORM>
+constexpr int kRowsUnroll = LORA_ROWS_UNROLL ? LORA_ROWS_UNROLL : 1;
+
+// The row loop.  Rows whose retired rows can meet the halo ring run the phase WITH the patch code, all others the lean
+// one (a warp-uniform branch per row): a task at the top or bottom of the grid pays for the patch code during its first /
+// last few rows only; tasks of the first / last strip pay for it throughout.
 template <int FORM, int TB>
 __device__ __forceinline__ void sweep_rows(SweepTB &s, const Weights2D &w, const WeightsDirect49 &wd) {
-    double A[TB][NACC][4];
+    double A[TB][kAcc][4];
 #pragma unroll
     for (int lv = 0; lv < TB; lv++)
 #pragma unroll
-        for (int j = 0; j < NACC; j++)
+        for (int j = 0; j < kAcc; j++)
 #pragma unroll
             for (int q = 0; q < 4; q++) A[lv][j][q] = 0.0;
 
-    for (int base = 0; base < s.nin; base += NACC) {
-        // rows retired by levels 1 .. TB-1 during this group: [rho0 + base - 3 (TB - 1), rho0 + base + 3]
+    constexpr int U = kRowsUnroll<FORM>;
+    for (int base = 0; base < s.nin; base += U) {
+        // rows retired by levels 1 .. TB-1 during these input rows: rho0 + base - 3 (TB - 1) .. rho0 + base + U - 1 - 3
         const bool edge = s.col_edge || (s.virt_top && s.rho0 + base - 3 * (TB - 1) < 0) ||
-                          (s.virt_bot && s.rho0 + base + 3 >= s.m);
+                          (s.virt_bot && s.rho0 + base + U - 4 >= s.m);
         if (edge) {
-            if (base + 0 < s.nin) row_phase<FORM, TB, true, 0>(base + 0, s, A, w, wd);
-            if (base + 1 < s.nin) row_phase<FORM, TB, true, 1>(base + 1, s, A, w, wd);
-            if (base + 2 < s.nin) row_phase<FORM, TB, true, 2>(base + 2, s, A, w, wd);
-            if (base + 3 < s.nin) row_phase<FORM, TB, true, 3>(base + 3, s, A, w, wd);
-            if (base + 4 < s.nin) row_phase<FORM, TB, true, 4>(base + 4, s, A, w, wd);
-            if (base + 5 < s.nin) row_phase<FORM, TB, true, 5>(base + 5, s, A, w, wd);
-            if (base + 6 < s.nin) row_phase<FORM, TB, true, 6>(base + 6, s, A, w, wd);
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                if (base + k < s.nin) row_phase<FORM, TB, true>(base + k, s, A, w, wd);
         } else {
-            if (base + 0 < s.nin) row_phase<FORM, TB, false, 0>(base + 0, s, A, w, wd);
-            if (base + 1 < s.nin) row_phase<FORM, TB, false, 1>(base + 1, s, A, w, wd);
-            if (base + 2 < s.nin) row_phase<FORM, TB, false, 2>(base + 2, s, A, w, wd);
-            if (base + 3 < s.nin) row_phase<FORM, TB, false, 3>(base + 3, s, A, w, wd);
-            if (base + 4 < s.nin) row_phase<FORM, TB, false, 4>(base + 4, s, A, w, wd);
-            if (base + 5 < s.nin) row_phase<FORM, TB, false, 5>(base + 5, s, A, w, wd);
-            if (base + 6 < s.nin) row_phase<FORM, TB, false, 6>(base + 6, s, A, w, wd);
+#pragma unroll
+            for (int k = 0; k < U; k++)
+                if (base + k < s.nin) row_phase<FORM, TB, false>(base + k, s, A, w, wd);
         }
     }
 }
 
+// Sweeps of two launches never need the caller's halo at their one intermediate level under the reference's
+// alternating halo (level 1 sits at an odd time: zeros), so they run without the halo staging area: 70 KB instead of
+// 115 KB of shared memory per CTA, i.e. THREE CTAs (12 warps) per SM where their register count allows it -- these
+// kernels are latency-bound at two warps per scheduler (profiles/r2_ncu_kernels.md).  (A Dirichlet boundary reads its
+// few halo cells from global memory instead.)
+template <int TB>
+struct Smem2DTB {
+    static constexpr int scratch = TB == 2 ? kSmem12 : kSmem2TbScratch;  // one guard word per warp
+    static constexpr int bytes = scratch + 64;
+};
+
 template <int FORM, int TB>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 2)
+#ifndef LORA_TB2_CTAS
+#define LORA_TB2_CTAS 3
+#endif
+__global__ void __launch_bounds__(32 * kWarpsPerCta, TB == 2 ? LORA_TB2_CTAS : 2)
 k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom2DTB g,
                const __grid_constant__ Weights2D w, const __grid_constant__ WeightsDirect49 wd) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -274,7 +285,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.out_hi = r0 + R;
     s.store_lane = lane >= TB - 1 && lane <= 32 - TB && s.c0 < g.n && s.c0 < cs + kStripOut;
     s.col_edge = cw < 0 || cw + kWarpCols > g.n;
-    s.hal_ok = R + 6 * TB <= kHalRows2Tb;
+    s.hal_ok = TB != 2 && R + 6 * TB <= kHalRows2Tb;
     s.virt_top = g.virt_top != 0;
     s.virt_bot = g.virt_bot != 0;
     s.par0 = g.par0 & 1;
@@ -286,7 +297,7 @@ k_stencil2d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     s.hsrc = g.halo_src + 4 * g.pitch + 4 + s.c0;
     double *hal = reinterpret_cast<double *>(smem_raw + kSmem12) + warp * (kHalRows2Tb * 8);
     s.hal = hal;
-    s.scratch = reinterpret_cast<volatile int *>(smem_raw + kSmem2TbScratch) + 2 * warp;
+    s.scratch = reinterpret_cast<volatile int *>(smem_raw + Smem2DTB<TB>::scratch) + 2 * warp;
     if (s.col_edge && s.hal_ok) {
         // stage the caller's halo columns (4 left of column 0, 4 right of column n-1) of the task's rows
         for (int idx = lane; idx < s.nin; idx += 32) {
@@ -328,13 +339,13 @@ cudaError_t launch_form(const CUtensorMap &tmap, const Geom2DTB &g, const Weight
                         cudaStream_t st) {
     if (g.ntasks <= 0) return cudaSuccess;
     const int ctas = (g.ntasks + kWarpsPerCta - 1) / kWarpsPerCta;
-    k_stencil2d_tb<FORM, TB><<<ctas, 32 * kWarpsPerCta, kSmem2Tb, st>>>(tmap, g, w, wd);
+    k_stencil2d_tb<FORM, TB><<<ctas, 32 * kWarpsPerCta, Smem2DTB<TB>::bytes, st>>>(tmap, g, w, wd);
     return cudaGetLastError();
 }
 
 template <int FORM, int TB>
 cudaError_t opt_in() {
-    return cudaFuncSetAttribute(k_stencil2d_tb<FORM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2Tb);
+    return cudaFuncSetAttribute(k_stencil2d_tb<FORM, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2DTB<TB>::bytes);
 }
 
 }  // namespace

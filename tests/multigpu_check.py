@@ -20,7 +20,9 @@ from lorastencil_b200.slab import SlabRunner  # noqa: E402
 
 CASES = [("1d2r", (1 << 20,), 7), ("1d2r", (1 << 22,), 47), ("1d1r", (100000,), 4), ("box2d1r", (512, 640), 6),
          ("star2d3r", (300, 258), 5), ("star2d1r", (256, 256), 25), ("star2d3r", (2048, 1024), 31), ("box3d1r", (64, 64, 128), 5),
-         ("star3d1r", (33, 40, 136), 4), ("box3d1r", (96, 32, 64), 21)]
+         ("star3d1r", (33, 40, 136), 4), ("box3d1r", (96, 32, 64), 21),
+         # sweeps of two launches (pyramid / diamond forms) in the slabs: ring of buffer 1 borrowed, ghost rows of 6
+         ("box2d1r", (1024, 640), 9), ("star2d1r", (600, 516), 8), ("box2d3r", (700, 258), 4)]
 
 
 def main():
