@@ -277,8 +277,8 @@ struct Geom3DTB {
     double *out;
     long long row_pitch, plane_pitch;
     int h, m, n;
-    long long h_lo, h_hi;     // interior planes written by this launch
-    int planes_per_chunk;
+    Segs sg;  // segments = interior plane ranges; first[] counts plane chunks (blockIdx.y), a CTA = (tile, chunk); a slab's
+              // bands are folded into its last / first chunk like Geom3D's (planes [mlo, mhi) mirrored, early flag)
     int tiles_m, tiles_n;     // tiles of kT3OutRows x kT3OutCols
     int vec4;
 };

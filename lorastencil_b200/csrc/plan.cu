@@ -121,6 +121,8 @@ static bool tb2_form(int form) {
 }
 // ... and sweeps of TWO launches (no register spills where three spill): every form but the cross, which is cheap at three
 static bool tb2_pair_form(int form) { return tb2_form(form) && form != LORA_FORM_CROSS; }
+static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long lo, long long hi, void *stream,
+                         const lora_exchange *ex);
 static int step_fused_2d(lora_plan *p, const double *src, double *dst, const double *halo_src, long long lo, long long hi,
                          int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
                          const double *mirror_base, void *stream);
@@ -750,7 +752,8 @@ int lora_plan_step_exchange(lora_plan_t *p, const double *src, double *dst, cons
                             long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
                             void *stream) {
     if (p && p->dim == 3) {
-        if (tb != 1) return fail(LORA_ERR_UNSUPPORTED, "3-D launches advance one time step");
+        if (tb == kTb3) return step_fused_3d(p, src, dst, lo, hi, stream, ex);
+        if (tb != 1) return fail(LORA_ERR_UNSUPPORTED, "3-D launches advance one time step, fused sweeps two");
         return step_unfused(p, src, dst, lo, hi, ex, nullptr, stream);
     }
     return step_fused_impl(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, ex, nullptr, stream);
@@ -919,7 +922,8 @@ int lora_plan_copy_ring(lora_plan_t *p, double *dst, const double *src, int lead
 
 // 3-D fused launch of kTb3 = 2 time steps over interior planes [lo, hi): see stencil3d_tb.cu.  The source buffer's
 // halo ring must hold what an EVEN time calls for (the caller's halo): lora_plan_run arranges that.
-static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long lo, long long hi, void *stream) {
+static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long lo, long long hi, void *stream,
+                         const lora_exchange *ex) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
     if (p->dim != 3 || !tb3_form(p->form) || p->odd_cols)
         return fail(LORA_ERR_UNSUPPORTED, "3-D temporal blocking fuses %d launches of the 7-point and separable forms (even column counts)", kTb3);
@@ -938,8 +942,6 @@ static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long
     g.h = (int)p->dims[0];
     g.m = (int)p->dims[1];
     g.n = (int)p->dims[2];
-    g.h_lo = lo;
-    g.h_hi = hi;
     g.tiles_m = (g.m + kT3OutRows - 1) / kT3OutRows;
     g.tiles_n = (g.n + kT3OutCols - 1) / kT3OutCols;
     long long max_planes = 96;
@@ -947,7 +949,45 @@ static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long
         const long long v = atoll(e);
         if (v >= 2 && v <= 4096) max_planes = v;
     }
-    g.planes_per_chunk = (int)pick_chunk_3d(hi - lo, (long long)g.tiles_m * g.tiles_n, p->slots, max_planes, 6);
+    const long long tiles = (long long)g.tiles_m * g.tiles_n;
+    const long long bl = ex && ex->band_lo > 0 ? ex->band_lo : 0, bh = ex && ex->band_hi > 0 ? ex->band_hi : 0;
+    long long L = pick_chunk_3d(hi - lo, tiles, p->slots, max_planes, 6);
+    long long nchunks = (hi - lo + L - 1) / L;
+    if ((bl || bh) && nchunks <= 2) {  // a slab with bands needs a first and a last chunk
+        L = (hi - lo + 1) / 2;
+        nchunks = 2;
+    }
+    long long last_lo = lo + (nchunks - 1) * L;
+    if ((bl || bh) && nchunks >= 3 && hi - last_lo < bh) {  // a short tail: the last chunk absorbs it (its own chunk length)
+        nchunks--;
+        last_lo = lo + (nchunks - 1) * L;
+    }
+    SegCut sc;
+    long long chunk[kMaxSegs], tasks[kMaxSegs];
+    if (bl || bh) {
+        // A slab that faces neighbours: its bands (2 planes = radius x 2 launches) are FOLDED into the ordinary plane
+        // chunks as in the unfused launch (step_unfused): the last chunk goes first in dispatch order -- its last
+        // planes are the hi band, mirrored as they are stored, flag raised when its CTAs finish -- the first chunk next
+        // -- its first planes are the lo band, flag raised right after they are stored -- then the chunks in between
+        if ((bl && !ex->mirror_lo) || (bh && !ex->mirror_hi)) return fail(LORA_ERR_ARG, "exchange band without a mirror address");
+        if (bl > L || bh > hi - last_lo)
+            return fail(LORA_ERR_UNSUPPORTED, "fused 3-D slab of %lld planes is too thin for its bands: use fewer GPUs", hi - lo);
+        sc.seq = ex->seq;
+        sc.add(last_lo, hi, bh ? (long long)(ex->mirror_hi - dst) : 0, false, bh ? ex->flag_hi : nullptr,
+               bh ? ex->count_hi : nullptr, bh ? ex->arrived_hi : nullptr);
+        sc.mlo[0] = hi - bh, sc.mhi[0] = hi;
+        sc.add(lo, lo + L, bl ? (long long)(ex->mirror_lo - dst) : 0, false, bl ? ex->flag_lo : nullptr,
+               bl ? ex->count_lo : nullptr, bl ? ex->arrived_lo : nullptr);
+        sc.mlo[1] = lo, sc.mhi[1] = lo + bl, sc.early[1] = 1;
+        if (nchunks > 2) sc.add(lo + L, last_lo, 0, false, nullptr, nullptr, nullptr);
+    } else {
+        sc.add(lo, hi, 0, false, nullptr, nullptr, nullptr);
+    }
+    for (int i = 0; i < sc.n; i++) {
+        chunk[i] = (bl || bh) && i == 0 ? hi - last_lo : L;  // the hi-band chunk is one task, whatever its length
+        tasks[i] = (sc.hi[i] - sc.lo[i] + chunk[i] - 1) / chunk[i];
+    }
+    fill_segs(g.sg, sc, chunk, tasks, tiles);
     g.vec4 = (g.n % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
     cudaError_t e = launch_3d_tb(p->form, *tm, g, p->w3, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(LORA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -1091,7 +1131,7 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
         if (!zero_mode)
             if (int rc = copy_ring(p, buf1, buf0, st)) return rc;
         for (int k = 0; k < a; k++)
-            if (int rc = step_fused_3d(p, buf[k % 2], buf[(k + 1) % 2], 0, p->dims[0], stream)) return rc;
+            if (int rc = step_fused_3d(p, buf[k % 2], buf[(k + 1) % 2], 0, p->dims[0], stream, nullptr)) return rc;
         if (!zero_mode)
             if (int rc = copy_ring(p, buf1, nullptr, st)) return rc;
         for (int i = a * kTb3; i < times; i++)
@@ -1463,7 +1503,7 @@ static int sweep_range(lora_plan *p, double *buf0, double *buf1, int k, int tb, 
     if (p->dim == 1 && (tb > 1 || p->max_tb > 1))
         return lora_plan_step_fused(p, buf[k % 2], buf[(k + 1) % 2], buf0, lo, hi, tb, done, 1, 1, stream);
     if (p->dim == 2 && tb > 1) return step_fused_2d(p, buf[k % 2], buf[(k + 1) % 2], buf0, lo, hi, tb, done, 1, 1, nullptr, nullptr, stream);
-    if (p->dim == 3 && tb > 1) return step_fused_3d(p, buf[k % 2], buf[(k + 1) % 2], lo, hi, stream);
+    if (p->dim == 3 && tb > 1) return step_fused_3d(p, buf[k % 2], buf[(k + 1) % 2], lo, hi, stream, nullptr);
     return lora_plan_step(p, buf[k % 2], buf[(k + 1) % 2], lo, hi, stream);
 }
 

@@ -109,7 +109,7 @@ std::vector<int> schedule_for(int dim, int times, int max_tb) {
     } else if (dim == 2 && max_tb >= 3) {
         for (int i = 0; i < times / 3; i++) tbs.push_back(3);
         for (int i = 0; i < times % 3; i++) tbs.push_back(1);
-    } else if (dim == 2 && max_tb == 2 && times >= 4) {
+    } else if ((dim == 2 || dim == 3) && max_tb == 2 && times >= 4) {
         // sweeps of two launches, an even number of them (the data is back in buffer 0), the rest one by one; the ring
         // of buffer 1 holds the caller's halo while they run (pair_ring below; same rule as lora_plan_run)
         int a = times / 2;
@@ -153,7 +153,7 @@ static int pair_ring(lora_slab *s, int before, void *stream) {
 }
 static int count_pairs(const std::vector<int> &tbs, int dim, int max_tb) {
     int a = 0;
-    if (dim == 2 && max_tb == 2)
+    if ((dim == 2 || dim == 3) && max_tb == 2)
         for (int tb : tbs) a += tb == 2;
     return a;
 }
@@ -208,10 +208,16 @@ extern "C" int lora_slab_create(lora_slab_t **out, int shape, int mode, const do
             return rc;
         }
         if (temporal_block > 0) lora_plan_set_temporal_block(probe, temporal_block);
-        s->max_tb = dim == 3 ? 1 : lora_plan_temporal_block(probe);  // 3-D slabs advance one launch per sweep
+        s->max_tb = lora_plan_temporal_block(probe);  // 1-D: up to 15, 2-D: 3 / 2 / 1, 3-D: 2 / 1
         lora_plan_destroy(probe);
     }
-    s->ghost = (s->max_tb > 1 && dim < 3) ? (long long)kRadius0[dim] * s->max_tb : kHalo0[dim];
+    if (dim >= 2 && s->max_tb == 2 && world > 1) {
+        // sweeps of two launches want room for both bands in every slab (3-D: a first and a last plane chunk that hold
+        // one band each); thinner slabs advance one launch per sweep (same rule in lorastencil_b200/slab.py)
+        const long long min_slab = global_dims[0] / world, need = 2 * (long long)kRadius0[dim] * 2;
+        if (min_slab < need) s->max_tb = 1;
+    }
+    s->ghost = s->max_tb > 1 ? (long long)kRadius0[dim] * s->max_tb : kHalo0[dim];
     int rc = make_geo(s->g, dim, global_dims, world, rank, s->ghost);
     if (!rc && rank > 0) rc = make_geo(s->gprev, dim, global_dims, world, rank - 1, s->ghost);
     if (!rc && rank < world - 1) rc = make_geo(s->gnext, dim, global_dims, world, rank + 1, s->ghost);

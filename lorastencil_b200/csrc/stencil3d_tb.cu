@@ -183,8 +183,9 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     volatile int *guard = reinterpret_cast<volatile int *>(empty + k3Stages) + warp;  // stage release, see level1
 
     const int tile_n = blockIdx.x % g.tiles_n, tile_m = blockIdx.x / g.tiles_n;
-    const int h0 = (int)(g.h_lo + (long long)blockIdx.y * g.planes_per_chunk);  // first output plane of the chunk
-    const int H = (int)min((long long)g.planes_per_chunk, g.h_hi - h0);
+    const int seg = seg_of(g.sg, blockIdx.y);  // a slab's hi-band chunk comes first in blockIdx.y, i.e. in dispatch order
+    const int h0 = (int)(g.sg.lo[seg] + (blockIdx.y - g.sg.first[seg]) * g.sg.chunk[seg]);  // first output plane of the chunk
+    const int H = (int)min(g.sg.chunk[seg], g.sg.hi[seg] - h0);
     const int nin = H + 4;                       // level-0 planes h0-2 .. h0+H+1
     const int R0 = tile_m * kT3OutRows, C0 = tile_n * kT3OutCols;  // first output row / column of the tile
     // TMA box origin in padded coordinates: region row -1 = interior row R0 - 2 = padded row R0; region column -2 =
@@ -226,6 +227,12 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int egc = eside ? C0 + k3TileCols : C0 - 1;
     const bool ein = gr0 + er >= 0 && gr0 + er < g.m && egc >= 0 && egc < g.n;
     double *optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(gr0 + 2) * g.row_pitch + 4 + gcA;
+    // multi-GPU slabs: planes [mlo, mhi) of this chunk are stored a second time at + mirror (the neighbour slab's ghost
+    // planes, peer memory over NVLink); `early_plane`: the lo band is complete once that plane is stored
+    const long long mirror = g.sg.mirror[seg];
+    const int mlo = (int)g.sg.mlo[seg], mhi = (int)g.sg.mhi[seg];
+    const bool early = g.sg.flag[seg] != nullptr && g.sg.early[seg] != 0;
+    const int early_plane = early ? mhi - 1 : -1;
 
     LevelState L1, L2;
     EdgeState E1{0.0, 0.0};
@@ -343,6 +350,8 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             }
         }, L2, O);
         if (i >= 4) {  // level-2 plane h0 + i - 4 is complete
+            const int hout = h0 + i - 4;
+            const bool mirrored = mirror != 0 && hout >= mlo && hout < mhi;  // CTA-uniform
 #pragma unroll
             for (int r = 0; r < RM; r++) {
                 const int rr = RM * warp + r;  // region row
@@ -356,10 +365,31 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                         if (gcB + 1 < g.n) st_global_v2(op + 64, O[r][2], O[r][3]);
                         else op[64] = O[r][2];
                     }
+                    if (mirrored) {
+                        double *om = op + mirror;
+                        if (colin[0]) {
+                            if (gcA + 1 < g.n) st_global_v2(om, O[r][0], O[r][1]);
+                            else om[0] = O[r][0];
+                        }
+                        if (colin[2]) {
+                            if (gcB + 1 < g.n) st_global_v2(om + 64, O[r][2], O[r][3]);
+                            else om[64] = O[r][2];
+                        }
+                    }
                 }
             }
             optr += g.plane_pitch;
+            if (hout == early_plane) {  // CTA-uniform: the lo band is complete -- tell the neighbour now, not at the end
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x == 0) seg_arrive(g.sg, seg);
+            }
         }
+    }
+    if (g.sg.flag[seg] != nullptr && !early) {  // the hi-band chunk: tell the neighbour once all its CTAs have stored
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) seg_arrive(g.sg, seg);
     }
 }
 #undef LORA_CELL
@@ -374,9 +404,8 @@ cudaError_t kernels_init_3d_tb() {
 
 cudaError_t launch_3d_tb(int form, const CUtensorMap &tmap, const Geom3DTB &g, const Weights3D &w, cudaStream_t s) {
     if (form != LORA_FORM_STAR7 && form != LORA_FORM_SEP3) return cudaErrorInvalidValue;
-    const long long planes = g.h_hi - g.h_lo;
-    if (planes <= 0) return cudaSuccess;
-    const int chunks = (int)((planes + g.planes_per_chunk - 1) / g.planes_per_chunk);
+    const int chunks = (int)g.sg.first[g.sg.nseg];
+    if (chunks <= 0) return cudaSuccess;
     dim3 grid(g.tiles_m * g.tiles_n, chunks);
     if (form == LORA_FORM_STAR7)
         k_stencil3d_tb<LORA_FORM_STAR7><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);

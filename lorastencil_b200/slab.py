@@ -203,10 +203,12 @@ class SlabRunner:
         if temporal_block is None:
             if dim == 1 and (not injected or fused_fn):
                 temporal_block = int(os.environ.get("LORA_TB", str(DEFAULT_TB_1D)))
-            elif dim == 2 and not injected:
+            elif dim >= 2 and not injected:
                 from .plan import Plan
-                # 3 for the star forms -- unless the column count is odd (no tensor map: direct-tap kernel, no fusion)
-                temporal_block = Plan(shape, (16, int(global_dims[1])), params=params, mode=mode).temporal_block
+                # 2-D: 3 for the cross form, 2 for diamond / pyramid; 3-D: 2 -- unless the column count is odd (no
+                # tensor map: direct-tap kernel, no fusion)
+                probe_dims = (16,) + tuple(int(x) for x in global_dims[1:])
+                temporal_block = Plan(shape, probe_dims, params=params, mode=mode).temporal_block
             else:
                 temporal_block = 1
         if dim == 1:
@@ -215,8 +217,11 @@ class SlabRunner:
             # 2-D fuses 3 launches, or 2 (which borrow buffer 1's halo ring: the native peer-memory driver only), or none
             pairs_ok = self.cuda and not injected and os.environ.get("LORA_HALO", "p2p") == "p2p"
             self.max_tb = 3 if temporal_block >= 3 else (2 if temporal_block == 2 and pairs_ok else 1)
-        else:
-            self.max_tb = 1
+        else:  # 3-D fuses 2 launches (native peer-memory driver only) or none
+            pairs_ok = self.cuda and not injected and os.environ.get("LORA_HALO", "p2p") == "p2p"
+            self.max_tb = 2 if temporal_block >= 2 and pairs_ok else 1
+        if dim >= 2 and self.max_tb == 2 and self.world > 1 and int(global_dims[0]) // self.world < 4 * (3 if dim == 2 else 1):
+            self.max_tb = 1  # slabs too thin for the bands of a two-launch sweep (same rule in csrc/slab.cu)
         if injected and fused_fn is None:
             self.max_tb = 1
         # ghost zone towards a neighbour: radius x deepest temporal block (1-D: 4 x tb cells, 2-D: 3 x 3 rows), never
@@ -226,6 +231,8 @@ class SlabRunner:
             ghost = 4 * self.max_tb
         elif dim == 2 and self.max_tb > 1:
             ghost = 3 * self.max_tb
+        elif dim == 3 and self.max_tb > 1:
+            ghost = self.max_tb
         self.ghost, self.align = ghost, (16 if dim == 1 else 1)
         self.geo = SlabGeometry(global_dims, self.world, self.rank, align=self.align, ghost=ghost)
         g = self.geo
@@ -266,8 +273,8 @@ class SlabRunner:
                 if self.rank == 0:
                     print(f"lorastencil_b200.slab: peer-memory halo exchange unavailable ({err}); using NCCL", flush=True)
         if self.halo_mode != "p2p":
-            if dim == 2 and self.max_tb == 2:
-                self.max_tb = 1  # pairs need the native driver; the ghost rows stay as wide as they are
+            if dim >= 2 and self.max_tb == 2:
+                self.max_tb = 1  # pairs need the native driver; the ghost rows / planes stay as wide as they are
             if not injected:
                 from .plan import Plan
                 self.plan = Plan(shape, g.local_dims, params=params, mode=mode)
