@@ -170,7 +170,9 @@ __device__ __forceinline__ void level(const Weights3D &w, RowFn rowfn, LevelStat
     }
 }
 
-template <int FORM>
+// SLAB: the launch serves neighbouring slabs (mirror stores, flags); the plain instantiation carries none of that code
+// (3-4 % on a single GPU: 502 vs 481 GStencil/s for the separable form at 512^3)
+template <int FORM, bool SLAB>
 __global__ void __launch_bounds__(k3Threads, 1)
 k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Geom3DTB g,
                const __grid_constant__ Weights3D w) {
@@ -229,9 +231,9 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     double *optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(gr0 + 2) * g.row_pitch + 4 + gcA;
     // multi-GPU slabs: planes [mlo, mhi) of this chunk are stored a second time at + mirror (the neighbour slab's ghost
     // planes, peer memory over NVLink); `early_plane`: the lo band is complete once that plane is stored
-    const long long mirror = g.sg.mirror[seg];
-    const int mlo = (int)g.sg.mlo[seg], mhi = (int)g.sg.mhi[seg];
-    const bool early = g.sg.flag[seg] != nullptr && g.sg.early[seg] != 0;
+    const long long mirror = SLAB ? g.sg.mirror[seg] : 0;
+    const int mlo = SLAB ? (int)g.sg.mlo[seg] : 0, mhi = SLAB ? (int)g.sg.mhi[seg] : 0;
+    const bool early = SLAB && g.sg.flag[seg] != nullptr && g.sg.early[seg] != 0;
     const int early_plane = early ? mhi - 1 : -1;
 
     LevelState L1, L2;
@@ -351,7 +353,7 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }, L2, O);
         if (i >= 4) {  // level-2 plane h0 + i - 4 is complete
             const int hout = h0 + i - 4;
-            const bool mirrored = mirror != 0 && hout >= mlo && hout < mhi;  // CTA-uniform
+            const bool mirrored = SLAB && mirror != 0 && hout >= mlo && hout < mhi;  // CTA-uniform
 #pragma unroll
             for (int r = 0; r < RM; r++) {
                 const int rr = RM * warp + r;  // region row
@@ -379,14 +381,14 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 }
             }
             optr += g.plane_pitch;
-            if (hout == early_plane) {  // CTA-uniform: the lo band is complete -- tell the neighbour now, not at the end
+            if (SLAB && hout == early_plane) {  // CTA-uniform: the lo band is complete -- tell the neighbour now, not at the end
                 __threadfence_system();
                 __syncthreads();
                 if (threadIdx.x == 0) seg_arrive(g.sg, seg);
             }
         }
     }
-    if (g.sg.flag[seg] != nullptr && !early) {  // the hi-band chunk: tell the neighbour once all its CTAs have stored
+    if (SLAB && g.sg.flag[seg] != nullptr && !early) {  // the hi-band chunk: tell the neighbour once all its CTAs have stored
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) seg_arrive(g.sg, seg);
@@ -394,12 +396,19 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 }
 #undef LORA_CELL
 
+template <int FORM, bool SLAB>
+cudaError_t opt_in_3d_tb() {
+    return cudaFuncSetAttribute(k_stencil3d_tb<FORM, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3Smem);
+}
+
 }  // namespace
 
 cudaError_t kernels_init_3d_tb() {
-    cudaError_t e = cudaFuncSetAttribute(k_stencil3d_tb<LORA_FORM_STAR7>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3Smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_stencil3d_tb<LORA_FORM_SEP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT3Smem);
+    cudaError_t e;
+    if ((e = opt_in_3d_tb<LORA_FORM_STAR7, false>()) != cudaSuccess) return e;
+    if ((e = opt_in_3d_tb<LORA_FORM_STAR7, true>()) != cudaSuccess) return e;
+    if ((e = opt_in_3d_tb<LORA_FORM_SEP3, false>()) != cudaSuccess) return e;
+    return opt_in_3d_tb<LORA_FORM_SEP3, true>();
 }
 
 cudaError_t launch_3d_tb(int form, const CUtensorMap &tmap, const Geom3DTB &g, const Weights3D &w, cudaStream_t s) {
@@ -407,10 +416,15 @@ cudaError_t launch_3d_tb(int form, const CUtensorMap &tmap, const Geom3DTB &g, c
     const int chunks = (int)g.sg.first[g.sg.nseg];
     if (chunks <= 0) return cudaSuccess;
     dim3 grid(g.tiles_m * g.tiles_n, chunks);
-    if (form == LORA_FORM_STAR7)
-        k_stencil3d_tb<LORA_FORM_STAR7><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
-    else
-        k_stencil3d_tb<LORA_FORM_SEP3><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
+    bool slab = false;  // any segment with a mirror or a flag
+    for (int i = 0; i < g.sg.nseg; i++) slab = slab || g.sg.mirror[i] != 0 || g.sg.flag[i] != nullptr;
+    if (form == LORA_FORM_STAR7) {
+        if (slab) k_stencil3d_tb<LORA_FORM_STAR7, true><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
+        else k_stencil3d_tb<LORA_FORM_STAR7, false><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
+    } else {
+        if (slab) k_stencil3d_tb<LORA_FORM_SEP3, true><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
+        else k_stencil3d_tb<LORA_FORM_SEP3, false><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
+    }
     return cudaGetLastError();
 }
 
