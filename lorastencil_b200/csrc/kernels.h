@@ -64,8 +64,8 @@ constexpr int k3Warps = 8;
 constexpr int k3Threads = 32 * k3Warps;
 
 // ---- temporally blocked 3-D kernel (stencil3d_tb.cu): two launches per sweep ----
-// thread tile 24 rows x 128 columns (8 warps x 3 rows, lane = 4 columns); a CTA writes 22 x 120 cells of it
-constexpr int kT3Rm = 3;
+// thread tile 32 rows x 128 columns (8 warps x 4 rows, lane = 2 column pairs); a CTA writes 30 x 128 cells of it
+constexpr int kT3Rm = 4;  // rows per lane: 3 -> 4 once the weights had moved to uniform registers (230-254 registers, no spills): +4..8 %
 constexpr int kT3Rows = kT3Rm * k3Warps;
 constexpr int kT3OutRows = kT3Rows - 2;
 constexpr int kT3OutCols = k3TileCols;      // the level-1 columns just outside a tile are extra cells (stencil3d_tb.cu)

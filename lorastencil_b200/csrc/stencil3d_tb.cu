@@ -9,18 +9,18 @@
 //   level-1 plane j --(same operator)--> level-2 plane j-1 --> global memory
 //
 // What keeps it inside the register file and off the shared-memory pipe:
-//   * a lane owns RM = 3 rows x 4 columns (not 4 x 4): two levels x two carried accumulators x 12 cells = 48 doubles
-//     of state; a 7-point (or separable) operator needs only TWO accumulators per level between planes -- the plane
-//     that completes is handed on at once;
-//   * level 1 reaches level 2 without a tile round trip: a lane's own 3 x 4 values stay in registers, the columns
+//   * a lane owns RM = 4 rows x 4 columns: two levels x two carried accumulators x 16 cells = 64 doubles of state; a
+//     7-point (or separable) operator needs only TWO accumulators per level between planes -- the plane that completes
+//     is handed on at once;
+//   * level 1 reaches level 2 without a tile round trip: a lane's own 4 x 4 values stay in registers, the columns
 //     left / right come from the neighbour lanes by warp shuffle, and only the first / last row of every warp goes
 //     through shared memory (2 x 128 doubles per warp and plane, double-buffered, ONE __syncthreads per plane);
-//   * overlapped tiling along the rows only: every level is computed on the full 24 x 128 thread tile and the outer
-//     rows only feed their neighbours (a CTA writes 22 rows); along the columns a tile writes ALL 128 columns it owns
+//   * overlapped tiling along the rows only: every level is computed on the full 32 x 128 thread tile and the outer
+//     rows only feed their neighbours (a CTA writes 30 rows); along the columns a tile writes ALL 128 columns it owns
 //     (512 columns = 4 tiles, not 5 of 120): the two level-1 columns just outside the tile, which level 2 needs, are
 //     computed as ONE extra cell per lane (lanes 0 .. 2 RM - 1: RM rows x {left, right}) from the level-0 box, which
-//     covers them anyway, and handed to lanes 0 / 31 by shuffle.  A CTA reads a 26 x 132 box per 22 x 128 outputs:
-//     17.2 B of DRAM traffic per cell per TWO launches against 2 x 16.8 unfused.
+//     covers them anyway, and handed to lanes 0 / 31 by shuffle.  A CTA reads a 34 x 132 box per 30 x 128 outputs:
+//     17.4 B of DRAM traffic per cell per TWO launches against 2 x 16.8 unfused.
 //
 // Reference semantics (S2) under fusion: a fused sweep starts at an even time -- level 0 sees the caller's halo, which
 // is physically in the source buffer's ring (the host copies the ring of buffer 0 into buffer 1 before the first sweep

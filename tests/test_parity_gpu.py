@@ -513,11 +513,11 @@ def test_copy_overlapped_operator_equals_plain_sequence(shape, dims, times, monk
 
 
 @pytest.mark.parametrize("dims", [(16, 16, 64), (40, 50, 130), (7, 33, 132), (64, 64, 64), (30, 22, 120), (33, 23, 122), (5, 100, 400),
-                                  (3, 3, 4), (70, 40, 250), (6, 30, 256), (4, 47, 384), (9, 45, 128), (5, 24, 258)])
+                                  (3, 3, 4), (70, 40, 250), (6, 30, 256), (4, 47, 384), (9, 45, 128), (5, 24, 258), (6, 31, 128), (5, 61, 130)])
 @pytest.mark.parametrize("shape", ["star3d1r", "box3d1r"])
 def test_temporal_blocking_3d_equals_unfused_launches(shape, dims):
     """3-D sweeps of 2 fused launches (level 1 handed on in registers, by warp shuffles and through two
-    shared-memory rows per warp; tiles of 22 x 128 outputs, the level-1 columns beside a tile as extra cells; zero halo at the intermediate level, the caller's ring
+    shared-memory rows per warp; tiles of 30 x 128 outputs, the level-1 columns beside a tile as extra cells; zero halo at the intermediate level, the caller's ring
     copied into buffer 1 for the odd sweeps and cleared afterwards) give the same bits as one launch per step, match
     the oracle, and leave both halo rings as the reference's ping-pong would."""
     import torch
