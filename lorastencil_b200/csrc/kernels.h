@@ -40,7 +40,12 @@ constexpr int kSmem12 = kWarpsPerCta * kStages * kStageElems * 8 + kWarpsPerCta 
 #endif
 constexpr int kMaxTb1 = LORA_TB_MAX;         // deepest temporal block of the 1-D kernel
 constexpr int kDefaultTb1 = 15;              // what lora_plan_run fuses unless told otherwise (LORA_TB / set_temporal_block)
-constexpr int kTbCellsPerLane = 16;
+#ifndef LORA_TB_CPL
+#define LORA_TB_CPL 16
+#endif
+constexpr int kTbCellsPerLane = LORA_TB_CPL;  // 16 or 32 (a multiple of 16: whole 128-byte swizzle rows per lane)
+constexpr int kTbLaneRows = kTbCellsPerLane / 16;  // rows of 16 doubles (= 128 B) a lane owns
+static_assert(kTbCellsPerLane % 16 == 0, "a lane owns whole rows of the tensor map");
 constexpr int kTbRowCells = 32 * kTbCellsPerLane;
 constexpr int kTbStages = LORA_TB_STAGES;    // TMA load ring depth (rows in flight per warp)
 constexpr int kTbOutBufs = LORA_TB_OUTBUFS;  // output staging rows per warp

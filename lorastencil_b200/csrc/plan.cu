@@ -348,7 +348,7 @@ static int get_tmap1d(lora_plan *p, const double *ptr, long long off, long long 
     m.off = off;
     cuuint64_t gdim[2] = {16, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {128};
-    cuuint32_t box[2] = {16, 32};
+    cuuint32_t box[2] = {16, (cuuint32_t)(kTbRowCells / 16)};  // one warp row
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&m.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(ptr + off), gdim, gstr, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
