@@ -968,7 +968,7 @@ static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long
         // A slab that faces neighbours: its bands (2 planes = radius x 2 launches) are FOLDED into the ordinary plane
         // chunks as in the unfused launch (step_unfused): the last chunk goes first in dispatch order -- its last
         // planes are the hi band, mirrored as they are stored, flag raised when its CTAs finish -- the first chunk next
-        // -- its first planes are the lo band, flag raised right after they are stored -- then the chunks in between
+        // -- its first planes are the lo band, flag raised when ITS CTAs finish -- then the chunks in between
         if ((bl && !ex->mirror_lo) || (bh && !ex->mirror_hi)) return fail(LORA_ERR_ARG, "exchange band without a mirror address");
         if (bl > L || bh > hi - last_lo)
             return fail(LORA_ERR_UNSUPPORTED, "fused 3-D slab of %lld planes is too thin for its bands: use fewer GPUs", hi - lo);
@@ -978,7 +978,7 @@ static int step_fused_3d(lora_plan *p, const double *src, double *dst, long long
         sc.mlo[0] = hi - bh, sc.mhi[0] = hi;
         sc.add(lo, lo + L, bl ? (long long)(ex->mirror_lo - dst) : 0, false, bl ? ex->flag_lo : nullptr,
                bl ? ex->count_lo : nullptr, bl ? ex->arrived_lo : nullptr);
-        sc.mlo[1] = lo, sc.mhi[1] = lo + bl, sc.early[1] = 1;
+        sc.mlo[1] = lo, sc.mhi[1] = lo + bl;  // (no early flag in the fused kernel: stencil3d_tb.cu)
         if (nchunks > 2) sc.add(lo + L, last_lo, 0, false, nullptr, nullptr, nullptr);
     } else {
         sc.add(lo, hi, 0, false, nullptr, nullptr, nullptr);

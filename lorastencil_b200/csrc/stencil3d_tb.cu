@@ -27,6 +27,8 @@
 // that reads buffer 1 and clears it again afterwards: lora_plan_run) -- and level 1 sits at an odd time, whose halo is
 // ZERO: level-1 cells outside the interior are forced to zero before they feed level 2.  Same operations in the same
 // order as two unfused launches: results are bit-identical.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "../../include/lorastencil.h"
@@ -230,11 +232,11 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const bool ein = gr0 + er >= 0 && gr0 + er < g.m && egc >= 0 && egc < g.n;
     double *optr = g.out + (long long)(h0 + 1) * g.plane_pitch + (long long)(gr0 + 2) * g.row_pitch + 4 + gcA;
     // multi-GPU slabs: planes [mlo, mhi) of this chunk are stored a second time at + mirror (the neighbour slab's ghost
-    // planes, peer memory over NVLink); `early_plane`: the lo band is complete once that plane is stored
+    // planes, peer memory over NVLink).  Both band chunks report to their flag when their CTAs finish: an early report of
+    // the lo band right after its planes are stored (as the unfused kernel does) puts a conditional CTA barrier into the
+    // plane loop, which cost this kernel 3-4 % (523 vs 551 GStencil/s for the separable form at 512^3)
     const long long mirror = SLAB ? g.sg.mirror[seg] : 0;
     const int mlo = SLAB ? (int)g.sg.mlo[seg] : 0, mhi = SLAB ? (int)g.sg.mhi[seg] : 0;
-    const bool early = SLAB && g.sg.flag[seg] != nullptr && g.sg.early[seg] != 0;
-    const int early_plane = early ? mhi - 1 : -1;
 
     LevelState L1, L2;
     EdgeState E1{0.0, 0.0};
@@ -381,14 +383,9 @@ k_stencil3d_tb(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                 }
             }
             optr += g.plane_pitch;
-            if (SLAB && hout == early_plane) {  // CTA-uniform: the lo band is complete -- tell the neighbour now, not at the end
-                __threadfence_system();
-                __syncthreads();
-                if (threadIdx.x == 0) seg_arrive(g.sg, seg);
-            }
         }
     }
-    if (SLAB && g.sg.flag[seg] != nullptr && !early) {  // the hi-band chunk: tell the neighbour once all its CTAs have stored
+    if (SLAB && g.sg.flag[seg] != nullptr) {  // a band chunk: tell the neighbour once all its CTAs have stored
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) seg_arrive(g.sg, seg);
@@ -418,6 +415,8 @@ cudaError_t launch_3d_tb(int form, const CUtensorMap &tmap, const Geom3DTB &g, c
     dim3 grid(g.tiles_m * g.tiles_n, chunks);
     bool slab = false;  // any segment with a mirror or a flag
     for (int i = 0; i < g.sg.nseg; i++) slab = slab || g.sg.mirror[i] != 0 || g.sg.flag[i] != nullptr;
+    static const bool force_slab = getenv("LORA_DEBUG_SLAB3D") != nullptr;  // measure what the slab code costs by itself
+    slab = slab || force_slab;
     if (form == LORA_FORM_STAR7) {
         if (slab) k_stencil3d_tb<LORA_FORM_STAR7, true><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
         else k_stencil3d_tb<LORA_FORM_STAR7, false><<<grid, k3Threads, kT3Smem, s>>>(tmap, g, w);
