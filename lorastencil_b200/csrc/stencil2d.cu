@@ -10,10 +10,11 @@
 //   * input rows reach shared memory through the warp's private TMA ring (cp.async.bulk.tensor.2d,
 //     boxes of 136 columns x 8 rows, 2 stages, one mbarrier per stage); no CTA-wide barrier exists.
 //   * per input row a lane reads its 12-double window with six 128-bit LDS, forms the horizontal
-//     profile sums h_t (FP64 FMA, weights straight from the constant bank) and PUSHES u_t[dr] * h_t
-//     into seven per-column register accumulators (one per pending output row).  The oldest
-//     accumulator is complete after every row and leaves with one 256-bit store.  The accumulator
-//     ring is rotated by unrolling the row loop 7x, so no register moves are issued.
+//     profile sums h_t (FP64 FMA, weights as uniform-register operands) and PUSHES u_t[dr] * h_t
+//     into the per-column register accumulators of the seven output rows it touches -- a shift
+//     register of six (stencil2d_push.cuh): the first FMA of every output row reads the neighbouring
+//     accumulator and writes this one, the completed row leaves with one 256-bit store.  A plain
+//     row loop, no register moves.
 //
 // MACs per cell: pyramid 31, cross 13, diamond 18, direct 49 (reference: 108 / 32 / 36+8 DMMA MACs).
 // FP64 DMMA (mma.sync m8n8k4, the only FP64 tensor shape on sm_100a) is not used here: the operands

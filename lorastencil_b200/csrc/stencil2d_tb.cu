@@ -1,16 +1,16 @@
-// stencil2d_tb.cu -- 2-D stencils with TEMPORAL BLOCKING: TB (odd) launches of the reference's 2-D kernels
+// stencil2d_tb.cu -- 2-D stencils with TEMPORAL BLOCKING: TB (3, or 2) launches of the reference's 2-D kernels
 // (src/2d/gpu.cu:31-273) fused into one sweep; the intermediate grids never leave the register file.
 // New functionality (the reference launches one kernel per time step).
 //
 // Same worker model as stencil2d.cu -- a warp owns a strip of 128 columns, lane l four of them, and sweeps a
 // chunk of rows top to bottom through its private TMA ring -- extended into a register pipeline of TB levels:
 //
-//   input row i  --push-->  A_1 (7 row accumulators)  --retire row-->  v_1 (4 values per lane)
+//   input row i  --push-->  A_1 (6 row accumulators: a shift register, stencil2d_push.cuh)  --completed row-->  v_1
 //   v_1 + 3 columns from either neighbour lane (6 FP64 warp shuffles)  --push-->  A_2  --retire-->  v_2 ...
 //   ... v_TB leaves with one 256-bit store.
 //
 // Every level lags the one before by 3 rows (the radius), so one loop iteration advances all TB levels by one
-// row and the accumulator rings of all levels rotate in lock step (row loop unrolled 7x, no register moves).
+// row: a plain row loop (the accumulators shift by register renaming inside the push, nothing is unrolled).
 // Lanes 0 and 31 have no neighbour on one side, so the valid strip shrinks by one lane (4 columns >= radius 3)
 // per level and side: a warp reads 136 columns, computes 128 at every level and writes 128 - 8 (TB - 1)
 // (overlapped tiling across strips: 14 % redundant FP64 work at TB = 3, no inter-warp synchronisation at all).
@@ -19,8 +19,9 @@
 // Reference semantics under fusion (S2): the halo ring of the grid launch t reads is the
 // caller's halo when t is even and zero when t is odd, and no launch ever writes it.  Intermediate levels are
 // therefore PATCHED before they feed the next level: a retired cell outside the interior takes
-// (its time is even) ? caller's halo (buffer 0 of the ping-pong) : 0.  Only odd TB are offered, so that the time
-// parity equals the buffer parity at level 0 and the source buffer's own halo ring is already the right one.
+// (its time is even) ? caller's halo (buffer 0 of the ping-pong) : 0.  With TB = 3 the time parity equals the buffer
+// parity at level 0 and the source buffer's own halo ring is already the right one; sweeps of TB = 2 all start at even
+// times, so their callers put the caller's ring around BOTH buffers while they run (plan.cu: lora_plan_run).
 #include "common.cuh"
 #include "kernels.h"
 #include "stencil2d_push.cuh"
