@@ -632,7 +632,7 @@ extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
 }
 
 // Task geometry of a fused 2-D launch over `rows` rows (g.nstrips set): see decode_task_2dtb in kernels.h
-static void plan_tasks_2dtb(Geom2DTB &g, long long rows, long long slots) {
+static void plan_tasks_2dtb(Geom2DTB &g, long long rows, long long slots, long long min_waves = 1) {
     if (g.nstrips >= 3) {
         // Inner strips are cut into nchunks tasks each; the two edge strips patch every row (about twice the time
         // per row), so they are cut into tasks of half that length (<= kEdgeRows2Tb rows: their halo columns are
@@ -643,7 +643,7 @@ static void plan_tasks_2dtb(Geom2DTB &g, long long rows, long long slots) {
             const long long v = atoll(e);
             if (v >= 8 && v <= kEdgeRows2Tb) edge_cap = v;
         }
-        long long best_chunks = 0, k0 = 1;
+        long long best_chunks = 0, k0 = min_waves;
         if (const char *e = getenv("LORA_TB2_MIN_WAVES")) {  // tuning knob
             const long long v = atoll(e);
             if (v >= 1 && v <= 16) k0 = v;
@@ -709,7 +709,10 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
         if (i == sc.n - 1) {  // the main segment (the only one of a plain launch): the planner of plan_tasks_2dtb
             g.row_lo = (int)sc.lo[i];
             g.row_hi = (int)sc.hi[i];
-            plan_tasks_2dtb(g, rows, (long long)p->sm_count * (tb == 2 ? 3 : 2) * kWarpsPerCta);  // resident warps: stencil2d_tb.cu
+            // resident warps: 3 CTAs per SM for sweeps of two, 2 for sweeps of three (stencil2d_tb.cu); the two-launch sweeps
+            // want two waves of shorter tasks (10240^2: pyramid 425 -> 458, diamond 564 -> 589 GStencil/s), the
+            // three-launch sweeps one
+            plan_tasks_2dtb(g, rows, (long long)p->sm_count * (tb == 2 ? 3 : 2) * kWarpsPerCta, tb == 2 ? 2 : 1);
             chunk[i] = g.rows_per_chunk;
             tasks[i] = g.ntasks;
         } else {  // a band: short tasks, every strip
