@@ -265,6 +265,9 @@ const char *lora_last_error(void);
  * lora_debug_tasks_2dtb: the warp tasks (strip, first row, rows) of one fused 2-D launch over rows [lo, hi) of an
  * m x n grid on a GPU with sm_count SMs, in launch order; returns the number of tasks. */
 int lora_debug_temporal_schedule(int times, int max_tb, int *blocks_out, int cap);
+/* the sweeps of a plan that fuses TWO launches (2-D diamond / pyramid forms, 3-D): an even number of 2s, then the
+ * remaining 0..3 launches one by one (no 2s below 4 launches); returns the number of sweeps */
+int lora_debug_pair_schedule(int times, int *blocks_out, int cap);
 /* what the last fused-or-not probe of a 2-D plan measured (milliseconds for 3 single launches / for 1 fused sweep of
  * 3 on the scratch grid); returns the number of cached verdicts */
 int lora_debug_tb2_probe(double *ms_unfused3, double *ms_fused);

@@ -712,7 +712,10 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
             // resident warps: 3 CTAs per SM for sweeps of two, 2 for sweeps of three (stencil2d_tb.cu); the two-launch sweeps
             // want two waves of shorter tasks (10240^2: pyramid 425 -> 458, diamond 564 -> 589 GStencil/s), the
             // three-launch sweeps one
+            // -- as long as the tasks stay long against their 12 warm-up rows (a band of the drop-in operators, ~2000
+            // rows, is better off with one wave of 100-row tasks than with two of 50)
             plan_tasks_2dtb(g, rows, (long long)p->sm_count * (tb == 2 ? 3 : 2) * kWarpsPerCta, tb == 2 ? 2 : 1);
+            if (tb == 2 && g.rows_per_chunk < 192) plan_tasks_2dtb(g, rows, (long long)p->sm_count * 3 * kWarpsPerCta, 1);
             chunk[i] = g.rows_per_chunk;
             tasks[i] = g.ntasks;
         } else {  // a band: short tasks, every strip
@@ -1151,6 +1154,22 @@ extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int tim
 // ---------------------------------------------------------------------------------------------
 // host-side planning, exposed for the CPU tests (no GPU needed)
 // ---------------------------------------------------------------------------------------------
+// sweeps of two launches (2-D diamond / pyramid, 3-D): an even number of pairs, then the remaining 0..3 launches one by one
+static std::vector<int> pair_schedule(int times) {
+    std::vector<int> tbs;
+    int a = times >= 4 ? times / 2 : 0;
+    a -= a % 2;
+    tbs.assign(a, 2);
+    tbs.insert(tbs.end(), times - 2 * a, 1);
+    return tbs;
+}
+extern "C" int lora_debug_pair_schedule(int times, int *out, int cap) {
+    if (times < 0) return -1;
+    const std::vector<int> tbs = pair_schedule(times);
+    for (size_t i = 0; i < tbs.size() && (int)i < cap; i++) out[i] = tbs[i];
+    return (int)tbs.size();
+}
+
 extern "C" int lora_debug_temporal_schedule(int times, int max_tb, int *out, int cap) {
     const std::vector<int> tbs = temporal_schedule(times, max_tb);
     for (size_t i = 0; i < tbs.size() && (int)i < cap; i++) out[i] = tbs[i];
@@ -1487,14 +1506,7 @@ static std::vector<int> plan_schedule(const lora_plan *p, int times) {
         }
         return tbs;
     }
-    if (pair_sweeps(p) && times >= 4) {
-        // sweeps of two launches, an even number of them, then the remaining 0..3 launches one by one (lora_plan_run)
-        int a = times / 2;
-        a -= a % 2;
-        tbs.assign(a, 2);
-        tbs.insert(tbs.end(), times - 2 * a, 1);
-        return tbs;
-    }
+    if (pair_sweeps(p) && times >= 4) return pair_schedule(times);  // as lora_plan_run
     tbs.assign(times, 1);
     return tbs;
 }

@@ -112,10 +112,9 @@ std::vector<int> schedule_for(int dim, int times, int max_tb) {
     } else if ((dim == 2 || dim == 3) && max_tb == 2 && times >= 4) {
         // sweeps of two launches, an even number of them (the data is back in buffer 0), the rest one by one; the ring
         // of buffer 1 holds the caller's halo while they run (pair_ring below; same rule as lora_plan_run)
-        int a = times / 2;
-        a -= a % 2;
-        tbs.assign(a, 2);
-        tbs.insert(tbs.end(), times - 2 * a, 1);
+        int n = lora_debug_pair_schedule(times, nullptr, 0);
+        tbs.resize(n);
+        lora_debug_pair_schedule(times, tbs.data(), n);
     } else {
         tbs.assign(times, 1);
     }

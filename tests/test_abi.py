@@ -152,6 +152,20 @@ def test_temporal_schedule_of_the_library_matches_the_python_mirror():
             assert sum(got) == times and len(got) % 2 == times % 2 and all(1 <= t <= max_tb for t in got)
 
 
+def test_pair_schedule_of_the_library_matches_the_python_mirror():
+    """The sweeps of plans that fuse two launches (C++: lora_plan_run, the time-skewed bands, the slab drivers) == the
+    Python mirror the multi-GPU runner counts its buffer flips with."""
+    import ctypes
+    from lorastencil_b200.slab import temporal_schedule_2d
+    L = ls.lib()
+    buf = (ctypes.c_int * 4096)()
+    for times in list(range(0, 70)) + [100, 999, 1000, 1001]:
+        k = L.lora_debug_pair_schedule(times, buf, 4096)
+        got = [buf[i] for i in range(k)]
+        assert got == temporal_schedule_2d(times, 2), times
+        assert sum(got) == times and len(got) % 2 == times % 2 and got.count(2) % 2 == 0
+
+
 def test_fused_2d_task_plan_covers_every_row_of_every_strip_exactly_once():
     """Host-side planning of a fused 2-D launch (lora_debug_tasks_2dtb = the kernel's own task decode): the tasks tile
     strips x rows exactly once, edge-strip tasks fit the shared-memory staging area (<= 160 rows) and come first, and

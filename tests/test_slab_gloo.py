@@ -205,3 +205,24 @@ def test_host_segments_cover_the_line_and_carry_the_dependency_cone():
                 assert hi == nxt[0]
             assert gl == min(4 * times + 8, lo) and gr == min(4 * times + 8, n - hi)
             assert lo - gl >= 0 and hi + gr <= n
+
+
+def test_pair_schedule_for_two_launch_sweeps():
+    """Sweeps of two launches (2-D diamond / pyramid, 3-D): an EVEN number of them first -- every pair sweep starts at an
+    even time with the data parity of the buffers restored at the end of the pairs -- then 0..3 single launches, so the
+    result lands in buf[times % 2] (S3).  Fewer than 4 launches: no pairs at all (csrc/plan.cu: lora_plan_run,
+    csrc/slab.cu: schedule_for, and this mirror must agree)."""
+    from lorastencil_b200.slab import temporal_schedule_2d
+    for times in range(0, 60):
+        tbs = temporal_schedule_2d(times, 2)
+        assert sum(tbs) == times and all(t in (1, 2) for t in tbs)
+        pairs = [t for t in tbs if t == 2]
+        assert len(pairs) % 2 == 0 and tbs[:len(pairs)] == pairs      # pairs first, an even number of them
+        assert len(tbs) - len(pairs) <= 3                            # at most three single launches behind them
+        assert (len(pairs) == 0) == (times < 4)
+        assert len(tbs) % 2 == times % 2                             # one buffer flip per sweep
+        done = 0
+        for t in tbs:
+            if t == 2:
+                assert done % 2 == 0                                 # a pair sweep starts at an even time
+            done += t
