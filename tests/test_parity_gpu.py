@@ -581,3 +581,50 @@ def test_run_to_run_determinism(shape, dims, times):
                 first = res
             else:
                 assert torch.equal(first, res), (shape, dims, tb, rep)
+
+
+def test_general_weight_tables_under_fusion():
+    """Fused sweeps honour arbitrary tables too (LORA_WEIGHTS_GENERAL): a pyramid WITH a centre remainder (the unpruned
+    form, sweeps of two), an asymmetric cross (three), a general diamond (two and three), a general 7-point star and a
+    general separable 27-point table in 3-D (two) -- same bits as single launches, the oracle's values."""
+    import torch
+    rng = np.random.default_rng(17)
+    W = np.zeros((7, 7))
+    for t in range(3):
+        u, v = np.zeros(7), np.zeros(7)
+        u[t:7 - t] = rng.uniform(0.5, 1.5, 7 - 2 * t)
+        v[t:7 - t] = rng.uniform(0.5, 1.5, 7 - 2 * t)
+        W += np.outer(u, v)
+    W[3, 3] += 0.37
+    cross = np.zeros((7, 7))
+    cross[:, 3] = rng.standard_normal(7)
+    cross[3, :] = rng.standard_normal(7)
+    dia = oracle.reference_params("star2d1r").reshape(7, 7).copy()
+    dia[3, 0] = 0.25
+    dia[1, 1] = -3.0
+    st = np.zeros(27)
+    st[[13, 12, 14, 10, 16, 4, 22]] = rng.standard_normal(7)
+    sep = np.einsum("i,j,k->ijk", *[rng.uniform(0.5, 1.5, 3) for _ in range(3)]).ravel()
+    cases = [("box2d3r", (300, 258), W.ravel(), "pyramid", (2,)), ("box2d3r", (257, 400), cross.ravel(), "cross", (3,)),
+             ("box2d3r", (129, 386), dia.ravel(), "diamond", (2, 3)), ("box3d1r", (40, 50, 130), st, None, (2,)),
+             ("box3d1r", (33, 61, 256), sep, None, (2,))]
+    for shape, dims, w, form, tbs in cases:
+        if form:
+            assert ls.decompose_2d(shape, w)["form"] == form
+        a = rng.uniform(-1, 1, oracle.padded_shape(shape, dims))
+        plan = ls.Plan(shape, dims, params=w, mode=ls.WEIGHTS_GENERAL)
+        for times in (4, 7, 9):
+            results = []
+            for tb in (1,) + tbs:
+                plan.temporal_block = tb
+                assert plan.temporal_block == tb, (shape, form, tb)
+                b0, b1 = torch.from_numpy(a).cuda(), plan.new_buffer()
+                n0 = plan.launches
+                res = plan.run(b0, b1, times)
+                torch.cuda.synchronize()
+                if tb > 1:
+                    assert plan.launches - n0 < times  # really fused
+                results.append(res.cpu().numpy())
+            for other in results[1:]:
+                assert np.array_equal(results[0], other), (shape, form, times)
+            assert max_rel_err(results[0], oracle.run(oracle.dim_of(shape), a, w, times)) <= RTOL, (shape, form, times)
