@@ -272,6 +272,8 @@ int lora_debug_pair_schedule(int times, int *blocks_out, int cap);
  * 3 on the scratch grid); returns the number of cached verdicts */
 int lora_debug_tb2_probe(double *ms_unfused3, double *ms_fused);
 int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int *strip_row_rows_out, int cap);
+/* the same for a sweep of TWO launches (diamond / pyramid forms: strips of 120 columns, 12 resident warps per SM) */
+int lora_debug_tasks_2dtb_pairs(int m, int n, int lo, int hi, int sm_count, int *out3, int cap);
 
 /* ------------------------------------------------------------------------------------------
  * Layer 3: host low-rank decomposition (inspection / tests)

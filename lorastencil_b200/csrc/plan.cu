@@ -632,6 +632,7 @@ extern "C" int lora_plan_set_temporal_block(lora_plan_t *p, int tb) {
 }
 
 // Task geometry of a fused 2-D launch over `rows` rows (g.nstrips set): see decode_task_2dtb in kernels.h
+static void plan_main_2dtb(Geom2DTB &g, long long rows, int sm_count, int tb);
 static void plan_tasks_2dtb(Geom2DTB &g, long long rows, long long slots, long long min_waves = 1) {
     if (g.nstrips >= 3) {
         // Inner strips are cut into nchunks tasks each; the two edge strips patch every row (about twice the time
@@ -709,13 +710,7 @@ static int step_fused_2d(lora_plan *p, const double *src, double *dst, const dou
         if (i == sc.n - 1) {  // the main segment (the only one of a plain launch): the planner of plan_tasks_2dtb
             g.row_lo = (int)sc.lo[i];
             g.row_hi = (int)sc.hi[i];
-            // resident warps: 3 CTAs per SM for sweeps of two, 2 for sweeps of three (stencil2d_tb.cu); the two-launch sweeps
-            // want two waves of shorter tasks (10240^2: pyramid 425 -> 458, diamond 564 -> 589 GStencil/s), the
-            // three-launch sweeps one
-            // -- as long as the tasks stay long against their 12 warm-up rows (a band of the drop-in operators, ~2000
-            // rows, is better off with one wave of 100-row tasks than with two of 50)
-            plan_tasks_2dtb(g, rows, (long long)p->sm_count * (tb == 2 ? 3 : 2) * kWarpsPerCta, tb == 2 ? 2 : 1);
-            if (tb == 2 && g.rows_per_chunk < 192) plan_tasks_2dtb(g, rows, (long long)p->sm_count * 3 * kWarpsPerCta, 1);
+            plan_main_2dtb(g, rows, p->sm_count, tb);
             chunk[i] = g.rows_per_chunk;
             tasks[i] = g.ntasks;
         } else {  // a band: short tasks, every strip
@@ -1176,16 +1171,26 @@ extern "C" int lora_debug_temporal_schedule(int times, int max_tb, int *out, int
     return (int)tbs.size();
 }
 
-extern "C" int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int *out3, int cap) {
-    if (m <= 0 || n <= 0 || lo < 0 || hi > m || lo >= hi || sm_count <= 0) return -1;
+// the main-segment task plan of a fused 2-D launch of `tb` (3 or 2) launches, as step_fused_2d makes it
+static void plan_main_2dtb(Geom2DTB &g, long long rows, int sm_count, int tb) {
+    // resident warps: 3 CTAs per SM for sweeps of two, 2 for sweeps of three (stencil2d_tb.cu); the two-launch sweeps
+    // want two waves of shorter tasks (10240^2: pyramid 425 -> 458, diamond 564 -> 589 GStencil/s), the three-launch
+    // sweeps one -- as long as the tasks stay long against their 12 warm-up rows (a band of the drop-in operators,
+    // ~2000 rows, is better off with one wave of 100-row tasks than with two of 50)
+    plan_tasks_2dtb(g, rows, (long long)sm_count * (tb == 2 ? 3 : 2) * kWarpsPerCta, tb == 2 ? 2 : 1);
+    if (tb == 2 && g.rows_per_chunk < 192) plan_tasks_2dtb(g, rows, (long long)sm_count * 3 * kWarpsPerCta, 1);
+}
+
+static int debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int tb, int *out3, int cap) {
+    if (m <= 0 || n <= 0 || lo < 0 || hi > m || lo >= hi || sm_count <= 0 || (tb != 2 && tb != kTb2)) return -1;
     Geom2DTB g{};
     g.m = m;
     g.n = n;
     g.row_lo = lo;
     g.row_hi = hi;
-    const int wout = strip_out_cols_2d_tb(kTb2);
+    const int wout = strip_out_cols_2d_tb(tb);
     g.nstrips = (n + wout - 1) / wout;
-    plan_tasks_2dtb(g, hi - lo, (long long)sm_count * 2 * kWarpsPerCta);
+    plan_main_2dtb(g, hi - lo, sm_count, tb);
     g.sg.nseg = 1;
     g.sg.lo[0] = lo;
     g.sg.hi[0] = hi;
@@ -1200,6 +1205,12 @@ extern "C" int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count,
         out3[3 * t + 2] = R;
     }
     return g.ntasks;
+}
+extern "C" int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int *out3, int cap) {
+    return debug_tasks_2dtb(m, n, lo, hi, sm_count, kTb2, out3, cap);
+}
+extern "C" int lora_debug_tasks_2dtb_pairs(int m, int n, int lo, int hi, int sm_count, int *out3, int cap) {
+    return debug_tasks_2dtb(m, n, lo, hi, sm_count, 2, out3, cap);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -179,10 +179,11 @@ def test_fused_2d_task_plan_covers_every_row_of_every_strip_exactly_once():
              (100000, 200, 0, 100000), (50, 100000, 0, 50), (2048, 1024, 5, 1029), (1000, 130, 991, 1000)]
     cases += [(int(m), int(n), 0, int(m)) for m, n in zip(rng.integers(1, 5000, 12), rng.integers(1, 5000, 12))]
     for m, n, lo, hi in cases:
+      for fn, wout in ((L.lora_debug_tasks_2dtb, 112), (L.lora_debug_tasks_2dtb_pairs, 120)):  # sweeps of 3 / of 2 launches
         for sms in (148, 4):
-            k = L.lora_debug_tasks_2dtb(m, n, lo, hi, sms, buf, cap)
+            k = fn(m, n, lo, hi, sms, buf, cap)
             assert 0 < k <= cap, (m, n, lo, hi)
-            nstrips = -(-n // 112)
+            nstrips = -(-n // wout)
             cover = np.zeros((nstrips, hi - lo), dtype=np.int32)
             first_inner = None
             for t in range(k):
@@ -200,7 +201,8 @@ def test_fused_2d_task_plan_covers_every_row_of_every_strip_exactly_once():
                     first_inner = t
             assert (cover == 1).all(), (m, n, lo, hi, sms)
             if sms == 148 and m == n == 10240:
-                assert k <= 2 * 148 * 8  # two whole waves of the 8 resident warps per SM
+                # whole waves of the resident warps: two of 8 warps per SM (sweeps of three), two of 12 (sweeps of two)
+                assert k <= 2 * 148 * (8 if wout == 112 else 12)
 
 
 def _reconstruct_2d(d):
