@@ -9,10 +9,15 @@
 // cell whose absolute difference exceeds 1e-7 is printed, then "Correct!" (src/2d/main.cu:282-328);
 // the process additionally returns 2 when a mismatch was found.  A trailing "--gpus k" (or LORA_NGPU=k in the
 // environment) cuts the grid into k slabs along its outermost axis, one per GPU, ghost zones exchanged over NVLink.
+// A trailing "--weights FILE" replaces the reference's hard-coded table (src/2d/main.cu:139-195 and siblings) by the
+// 9 / 49 / 27 whitespace-separated values of FILE (row-major, as the reference lays its tables out) and runs the
+// operator in LORA_WEIGHTS_GENERAL mode: EVERY weight is honoured -- which is what --check then verifies -- where the
+// reference operators ignore or drop some of theirs.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -133,10 +138,32 @@ int main(int argc, char *argv[]) {
 #if defined(CHECK_ERROR)
     check = true;
 #endif
+    const char *weights_path = nullptr;
     for (int i = kDim + 3; i < argc; i++) {
         if (std::strcmp(argv[i], "--check") == 0) check = true;
         // trailing "--gpus k": slab-decompose the grid over k GPUs of this box (same as LORA_NGPU=k)
         if (std::strcmp(argv[i], "--gpus") == 0 && i + 1 < argc) lora_set_gpus(atoi(argv[++i]));
+        // trailing "--weights FILE": a caller's table instead of the hard-coded one, every weight honoured
+        if (std::strcmp(argv[i], "--weights") == 0 && i + 1 < argc) weights_path = argv[++i];
+    }
+    double params[49];
+    lora_reference_table(sn->shape, params);
+    int mode = LORA_WEIGHTS_REFERENCE;
+    if (weights_path) {
+        std::ifstream f(weights_path);
+        if (!f) {
+            std::cerr << "Invalid argument: cannot open the weight file " << weights_path << ".\n";
+            return 1;
+        }
+        std::vector<double> w;
+        for (double v; f >> v;) w.push_back(v);
+        if (!f.eof() || (int)w.size() != kNParams) {
+            std::cerr << "Invalid argument: the weight file must hold exactly " << kNParams << " numbers (found " << w.size()
+                      << (f.eof() ? "" : ", then something that is not a number") << ").\n";
+            return 1;
+        }
+        for (int i = 0; i < kNParams; i++) params[i] = w[i];
+        mode = LORA_WEIGHTS_GENERAL;
     }
 
 #if LORA_CLI_DIM == 1
@@ -148,8 +175,7 @@ int main(int argc, char *argv[]) {
            times);
 #endif
 
-    double params[49];
-    lora_reference_table(sn->shape, params);
+    if (weights_path) printf("INFO: weights = %s (%d values, every one honoured)\n", weights_path, kNParams);
 
     long long pd[3] = {1, 1, 1}, total = 1;
     for (int i = 0; i < kDim; i++) {
@@ -184,14 +210,14 @@ int main(int argc, char *argv[]) {
 #endif
     }
 
-    lora_gpu_run_host(sn->shape, LORA_WEIGHTS_REFERENCE, matrix.data(), output.data(), params, times, dims);
+    lora_gpu_run_host(sn->shape, mode, matrix.data(), output.data(), params, times, dims);
 
     int rc = 0;
     if (check) {
         printf("\nChecking Correctness... \n");
         std::vector<double> naive((size_t)total + 1, 0.0), lora((size_t)total + 1, 0.0);
         cpu_step(matrix, naive, params, pd);
-        lora_gpu_run_host(sn->shape, LORA_WEIGHTS_REFERENCE, matrix.data(), lora.data(), params, 1, dims);
+        lora_gpu_run_host(sn->shape, mode, matrix.data(), lora.data(), params, 1, dims);
         printf("Comparing naive and lora\n");
         long long bad = 0;
         const long long lo[3] = {kHalo[0], kHalo[1], kHalo[2]};
