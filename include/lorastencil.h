@@ -159,11 +159,19 @@ int lora_plan_temporal_block(const lora_plan_t *plan);
  * launch writes a halo cell, buffer 0 holds the caller's halo, buffer 1 zeros, so even launches see the caller's halo
  * and odd launches a zero halo (S2: src/2d/gpu.cu:396-400, store offsets :106).  LORA_BOUNDARY_DIRICHLET: the caller's
  * halo values are the boundary condition of EVERY launch (lora_plan_run copies the halo ring of buf0 into buf1 first).
- * LORA_BOUNDARY_ZERO: zero halo for every launch (the ring of both buffers is cleared, buf0's included).  Applies to
- * lora_plan_run / lora_plan_step*; the drop-in operators and the slab drivers always use REFERENCE. */
-enum { LORA_BOUNDARY_REFERENCE = 0, LORA_BOUNDARY_DIRICHLET = 1, LORA_BOUNDARY_ZERO = 2 };
+ * LORA_BOUNDARY_ZERO: zero halo for every launch (the ring of both buffers is cleared, buf0's included).
+ * LORA_BOUNDARY_PERIODIC: the grid is a torus -- before every launch lora_plan_run rewrites the halo ring of the
+ * source buffer with the interior cells it wraps around to (corners included), and once more on the result buffer, so
+ * the caller's halo values are never read; one launch per time step (a fused sweep would need a ghost zone of radius x
+ * depth cells, the storage halo of S1 holds one radius), every axis at least as long as its storage halo (4 / 4,4 /
+ * 1,2,4).  Applies to lora_plan_run / lora_plan_step*; the drop-in operators and the slab drivers always use
+ * REFERENCE. */
+enum { LORA_BOUNDARY_REFERENCE = 0, LORA_BOUNDARY_DIRICHLET = 1, LORA_BOUNDARY_ZERO = 2, LORA_BOUNDARY_PERIODIC = 3 };
 int lora_plan_set_boundary(lora_plan_t *plan, int mode);
 int lora_plan_boundary(const lora_plan_t *plan);
+/* The periodic refresh on its own: halo ring of `buf` <- periodic image of its interior (for callers that drive
+ * lora_plan_step themselves).  Asynchronous on `stream`. */
+int lora_plan_wrap_ring(lora_plan_t *plan, double *buf, void *stream);
 
 /* One FUSED launch of `tb` time steps over interior range [lo, hi) of the outermost axis.
  * 2-D (tb = 1 or 3): rows [lo, hi); the ring of src must be the one its time parity calls for (caller's halo at even
@@ -274,6 +282,9 @@ int lora_debug_tb2_probe(double *ms_unfused3, double *ms_fused);
 int lora_debug_tasks_2dtb(int m, int n, int lo, int hi, int sm_count, int *strip_row_rows_out, int cap);
 /* the same for a sweep of TWO launches (diamond / pyramid forms: strips of 120 columns, 12 resident warps per SM) */
 int lora_debug_tasks_2dtb_pairs(int m, int n, int lo, int hi, int sm_count, int *out3, int cap);
+/* the periodic halo refresh (lora_plan_wrap_ring: same work items, same axis order) applied to a HOST array of the padded
+ * size of a dim-D grid with interior sizes dims[0..dim) */
+int lora_debug_wrap_ring_host(int dim, const long long *dims, double *buf);
 
 /* ------------------------------------------------------------------------------------------
  * Layer 3: host low-rank decomposition (inspection / tests)

@@ -267,6 +267,11 @@ struct GeomDirect {
 };
 cudaError_t launch_direct(int dim, const GeomDirect &g, const WeightsDirect49 &w, cudaStream_t s);
 
+// periodic halo ring (boundary.cu): one axis of an array seen as [outer][len + 2 halo][inner]
+cudaError_t launch_wrap_axis(double *buf, long long outer, long long len, int halo, long long inner, int sm_count,
+                             cudaStream_t s);
+void wrap_axis_host(double *buf, long long outer, long long len, int halo, long long inner);
+
 cudaError_t launch_1d(const Geom1D &g, const Weights1D &w, cudaStream_t s);
 cudaError_t launch_1d_tb(const CUtensorMap &imap, const CUtensorMap &omap, const Geom1DTB &g, const Weights1D &w,
                          cudaStream_t s);

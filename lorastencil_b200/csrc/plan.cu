@@ -764,6 +764,8 @@ static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const
                            long long hi, int tb, int launches_before, int virt_lo, int virt_hi, const lora_exchange *ex,
                            const double *mirror_base, void *stream) {
     if (!p || !src || !dst) return fail(LORA_ERR_ARG, "null argument");
+    if (p->boundary == LORA_BOUNDARY_PERIODIC && tb > 1)
+        return fail(LORA_ERR_UNSUPPORTED, "a periodic boundary refreshes the halo ring before every launch: no fused sweeps");
     if (p->dim == 2)
         return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, ex, mirror_base, stream);
     if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D and 2-D shapes");
@@ -865,8 +867,16 @@ static int run_fused_1d(lora_plan *p, double *buf0, double *buf1, int times, int
 // alternates caller's / zero (S2).  DIRICHLET keeps the caller's halo values fixed for every launch, ZERO keeps a zero
 // halo: both ping-pong buffers then carry the same ring, and the fused kernels' virtual halo stops alternating.
 extern "C" int lora_plan_set_boundary(lora_plan_t *p, int mode) {
-    if (!p || (mode != LORA_BOUNDARY_REFERENCE && mode != LORA_BOUNDARY_DIRICHLET && mode != LORA_BOUNDARY_ZERO))
+    if (!p || (mode != LORA_BOUNDARY_REFERENCE && mode != LORA_BOUNDARY_DIRICHLET && mode != LORA_BOUNDARY_ZERO &&
+               mode != LORA_BOUNDARY_PERIODIC))
         return fail(LORA_ERR_ARG, "bad boundary mode");
+    if (mode == LORA_BOUNDARY_PERIODIC) {  // the wrap reads `halo` interior cells behind each face
+        static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
+        for (int i = 0; i < p->dim; i++)
+            if (p->dims[i] < halo[p->dim][i])
+                return fail(LORA_ERR_UNSUPPORTED, "a periodic boundary needs at least %d cells along axis %d (the storage halo), got %lld",
+                            halo[p->dim][i], i, p->dims[i]);
+    }
     p->boundary = mode;
     return LORA_OK;
 }
@@ -913,6 +923,46 @@ static int copy_ring_rows(const lora_plan *p, double *dst, const double *src, lo
 static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStream_t st) {
     return copy_ring_rows(p, dst, src, 0, p->padded[0], st);
 }
+// LORA_BOUNDARY_PERIODIC: halo ring of buf <- the periodic image of buf's interior (boundary.cu), innermost axis first
+static int wrap_ring(const lora_plan *p, double *buf, cudaStream_t st) {
+    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
+    long long inner = 1;
+    for (int ax = p->dim - 1; ax >= 0; ax--) {
+        const long long line = p->padded[ax] * inner;  // doubles in one padded line of this axis
+        CU_TRY(launch_wrap_axis(buf, p->elems / line, p->dims[ax], halo[p->dim][ax], inner, p->sm_count, st));
+        inner = line;
+    }
+    return LORA_OK;
+}
+extern "C" int lora_plan_wrap_ring(lora_plan_t *p, double *buf, void *stream) {
+    if (!p || !buf) return fail(LORA_ERR_ARG, "null argument");
+    if (int rc = check_device(p)) return rc;
+    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
+    for (int i = 0; i < p->dim; i++)
+        if (p->dims[i] < halo[p->dim][i]) return fail(LORA_ERR_UNSUPPORTED, "grid thinner than its storage halo along axis %d", i);
+    return wrap_ring(p, buf, static_cast<cudaStream_t>(stream));
+}
+
+// the axis order and geometry of wrap_ring on a HOST array of the padded size (interior sizes dims[0..dim)): what the CPU
+// tests compare with numpy's wrap padding -- no CUDA call
+extern "C" int lora_debug_wrap_ring_host(int dim, const long long *dims, double *buf) {
+    if (dim < 1 || dim > 3 || !dims || !buf) return fail(LORA_ERR_ARG, "bad argument");
+    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
+    long long padded[3], elems = 1;
+    for (int i = 0; i < dim; i++) {
+        if (dims[i] < halo[dim][i]) return fail(LORA_ERR_UNSUPPORTED, "grid thinner than its storage halo along axis %d", i);
+        padded[i] = dims[i] + 2 * halo[dim][i];
+        elems *= padded[i];
+    }
+    long long inner = 1;
+    for (int ax = dim - 1; ax >= 0; ax--) {
+        const long long line = padded[ax] * inner;
+        wrap_axis_host(buf, elems / line, dims[ax], halo[dim][ax], inner);
+        inner = line;
+    }
+    return LORA_OK;
+}
+
 // for the slab driver (exchange.h): the ring of a slab's local array -- the side halo of every local row / plane, and the
 // leading / trailing halo rows only where the slab ends the grid
 int lora_plan_copy_ring(lora_plan_t *p, double *dst, const double *src, int lead, int trail, void *stream) {
@@ -1075,9 +1125,21 @@ static void probe_tb2(lora_plan *p) {
 
 extern "C" int lora_plan_run(lora_plan_t *p, double *buf0, double *buf1, int times, void *stream) {
     if (!p || !buf0 || !buf1) return fail(LORA_ERR_ARG, "null argument");
-    if (p->tb_auto && times >= kTb2) {
+    if (p->tb_auto && times >= kTb2 && p->boundary != LORA_BOUNDARY_PERIODIC) {
         if (int rc = check_device(p)) return rc;
         probe_tb2(p);
+    }
+    if (p->boundary == LORA_BOUNDARY_PERIODIC) {
+        // one launch per time step, the source's ring refreshed from its interior before each; the result buffer's ring
+        // is refreshed once more at the end, so that what comes back is a consistent periodic array
+        if (int rc = check_device(p)) return rc;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        double *pb[2] = {buf0, buf1};
+        for (int i = 0; i < times; i++) {
+            if (int rc = wrap_ring(p, pb[i % 2], st)) return rc;
+            if (int rc = lora_plan_step(p, pb[i % 2], pb[(i + 1) % 2], 0, p->dims[0], stream)) return rc;
+        }
+        return wrap_ring(p, pb[times % 2], st);
     }
     if (p->boundary != LORA_BOUNDARY_REFERENCE) {  // both buffers carry the same ring: the caller's, or zeros
         if (int rc = check_device(p)) return rc;

@@ -11,7 +11,7 @@ from . import _lib
 HALO = {1: (4,), 2: (4, 4), 3: (1, 2, 4)}  # S1: src/1d/main.cu:96, src/2d/main.cu:217-218, src/3d/main.cu:21-23
 MAX_TB_1D = 15     # deepest temporal block of the 1-D kernel (kMaxTb1 in csrc/kernels.h)
 DEFAULT_TB_1D = 15  # kDefaultTb1
-BOUNDARY_NAMES = ["reference", "dirichlet", "zero"]
+BOUNDARY_NAMES = ["reference", "dirichlet", "zero", "periodic"]
 FORM_NAMES = {0: "taps9", 1: "cross", 2: "pyramid", 3: "diamond", 4: "direct49", 5: "sep3", 6: "star7", 7: "direct27",
               8: "pyramid_pruned", 9: "rank2", 10: "rank3"}
 
@@ -109,12 +109,22 @@ class Plan:
     @property
     def boundary(self) -> str:
         """'reference' (the reference's alternating caller's / zero halo, S2), 'dirichlet' (the caller's halo is the
-        boundary condition of every launch) or 'zero' (zero halo for every launch)."""
+        boundary condition of every launch), 'zero' (zero halo for every launch) or 'periodic' (the grid is a torus:
+        `run` rewrites the halo ring from the interior before every launch and on the result; one launch per step)."""
         return BOUNDARY_NAMES[int(_lib.lib().lora_plan_boundary(self._h))]
 
     @boundary.setter
     def boundary(self, mode: str):
         _lib.check(_lib.lib().lora_plan_set_boundary(self._h, BOUNDARY_NAMES.index(mode)), "lora_plan_set_boundary")
+
+    def wrap_ring(self, buf, stream=None):
+        """Halo ring of ``buf`` <- the periodic image of its interior (what `run` does before every launch of a
+        periodic plan), for callers that drive `step` themselves.  Asynchronous."""
+        import torch
+        self._check_buf(buf)
+        s = torch.cuda.current_stream(buf.device) if stream is None else stream
+        _lib.check(_lib.lib().lora_plan_wrap_ring(self._h, c_void_p(buf.data_ptr()), c_void_p(s.cuda_stream)),
+                   "lora_plan_wrap_ring")
 
     def step_fused(self, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, stream=None, mirror=None):
         """One fused launch of `tb` time steps: see lora_plan_step_fused in include/lorastencil.h.  ``mirror``: device

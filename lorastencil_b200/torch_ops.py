@@ -4,13 +4,14 @@ The reference has no Python surface; its host operators are ``gpu_X(in, out, par
 arrays (src/1d/1d_utils.h:45-47, src/2d/2d_utils.h:47-51, src/3d/3d_utils.h:44-48).  These ops are the same operators
 for callers whose grids already live in HBM:
 
-    out = torch.ops.lorastencil.stencil2d(x, "box2d3r", times, params=None, mode=0)
+    out = torch.ops.lorastencil.stencil2d(x, "box2d3r", times, params=None, mode=0, boundary=0)
 
 ``x``: contiguous float64 CUDA tensor of the PADDED shape (1-D ``n+8``; 2-D ``(m+8, n+8)``; 3-D ``(h+2, m+4, n+8)``),
 halo included.  Returns a new tensor of the same shape holding the whole padded buffer ``times % 2`` of the reference's
 ping-pong (S2/S3: halo = the caller's for even ``times``, zero for odd).  ``params``: 9 / 49 / 27 weights (None = the
 reference CLI's table for the shape); ``mode``: 0 = what the reference GPU operator does with ``params``, 1 = every
-weight honoured.  Registered through ``torch.library`` (dispatch key CUDA + a Meta kernel for shape propagation); there
+weight honoured; ``boundary``: 0 = the reference's ping-pong halo (S2), 1 = Dirichlet (the caller's halo at every
+launch), 2 = zero halo, 3 = periodic (include/lorastencil.h: LORA_BOUNDARY_*).  Registered through ``torch.library`` (dispatch key CUDA + a Meta kernel for shape propagation); there
 is no CPU kernel: a CPU tensor raises, like everything else in this package.
 """
 from __future__ import annotations
@@ -21,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .plan import HALO, Plan
+from .plan import BOUNDARY_NAMES, HALO, Plan
 
 _PLANS: dict = {}
 _DIM_SHAPES = {1: ("1d1r", "1d2r"), 2: ("star2d1r", "box2d1r", "star2d3r", "box2d3r"), 3: ("box3d1r", "star3d1r")}
@@ -47,10 +48,14 @@ def _plan_for(x: torch.Tensor, dim: int, shape: str, params: Optional[torch.Tens
     return plan
 
 
-def _run(x: torch.Tensor, dim: int, shape: str, times: int, params: Optional[torch.Tensor], mode: int) -> torch.Tensor:
+def _run(x: torch.Tensor, dim: int, shape: str, times: int, params: Optional[torch.Tensor], mode: int,
+         boundary: int = 0) -> torch.Tensor:
     if times < 0:
         raise ValueError("times must be >= 0")
+    if not 0 <= int(boundary) < len(BOUNDARY_NAMES):
+        raise ValueError(f"boundary must be 0..{len(BOUNDARY_NAMES) - 1} ({', '.join(BOUNDARY_NAMES)})")
     plan = _plan_for(x, dim, shape, params, mode)
+    plan.boundary = BOUNDARY_NAMES[int(boundary)]  # plans are cached per (shape, size, weights): set it on every call
     with torch.cuda.device(x.device):
         b0 = x.clone()            # the operator never writes its input (the reference's `in` is const)
         b1 = torch.zeros_like(x)  # S2: the second ping-pong buffer starts as zeros
@@ -60,21 +65,21 @@ def _run(x: torch.Tensor, dim: int, shape: str, times: int, params: Optional[tor
 
 _lib_def = torch.library.Library("lorastencil", "DEF")
 for _d in (1, 2, 3):
-    _lib_def.define(f"stencil{_d}d(Tensor x, str shape, int times, Tensor? params=None, int mode=0) -> Tensor")
+    _lib_def.define(f"stencil{_d}d(Tensor x, str shape, int times, Tensor? params=None, int mode=0, int boundary=0) -> Tensor")
 
 
 def _make_cuda(dim):
-    def impl(x, shape, times, params=None, mode=0):
-        return _run(x, dim, shape, times, params, mode)
+    def impl(x, shape, times, params=None, mode=0, boundary=0):
+        return _run(x, dim, shape, times, params, mode, boundary)
     return impl
 
 
-def _meta(x, shape, times, params=None, mode=0):
+def _meta(x, shape, times, params=None, mode=0, boundary=0):
     return torch.empty_like(x)
 
 
 def _make_cpu(dim):
-    def impl(x, shape, times, params=None, mode=0):
+    def impl(x, shape, times, params=None, mode=0, boundary=0):
         raise _lib.LoraError(f"torch.ops.lorastencil.stencil{dim}d has no CPU kernel: pass a CUDA tensor "
                              "(this package has no CPU fallback)")
     return impl

@@ -145,6 +145,25 @@ def run(shape_or_dim, a: np.ndarray, params: np.ndarray, times: int, out: np.nda
     return out
 
 
+def wrap_ring(a: np.ndarray) -> np.ndarray:
+    """The padded array whose halo ring is the periodic image of ``a``'s interior (numpy's wrap padding of the
+    interior by the storage halo of S1).  The reference has no boundary update (S2); this and ``run_periodic`` are
+    the checker of the product's LORA_BOUNDARY_PERIODIC mode."""
+    h = HALO[a.ndim]
+    inner = tuple(slice(k, -k) for k in h)
+    return np.pad(a[inner], [(k, k) for k in h], mode="wrap")
+
+
+def run_periodic(shape_or_dim, a: np.ndarray, params: np.ndarray, times: int) -> np.ndarray:
+    """``times`` direct-tap steps (``step`` = test_cpu) on a torus: the ring is rewritten from the interior before
+    every step and once more on the result; the caller's halo values are never read."""
+    d = shape_or_dim if isinstance(shape_or_dim, int) else dim_of(shape_or_dim)
+    cur = wrap_ring(np.ascontiguousarray(a, dtype=np.float64))
+    for _ in range(times):
+        cur = wrap_ring(step(d, np.ascontiguousarray(cur), params))
+    return cur
+
+
 # --------------------------------------------------------------------------------------------
 # weight tables of the reference CLIs
 # --------------------------------------------------------------------------------------------

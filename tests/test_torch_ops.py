@@ -45,3 +45,31 @@ def test_ops_match_the_oracle(shape, dims, times):
     if d == 1:
         got, ref = got[:-1], ref[:-1]
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_boundary_argument_is_validated_before_any_plan_is_made():
+    op = torch.ops.lorastencil.stencil2d
+    y = op(torch.empty((72, 136), dtype=torch.float64, device="meta"), "box2d3r", 3, None, 0, 3)
+    assert y.shape == (72, 136)
+    assert "int boundary=0" in str(op.default._schema)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dims", [("1d2r", (5000,)), ("star2d3r", (70, 250)), ("box3d1r", (9, 34, 130))])
+def test_ops_periodic_boundary(shape, dims):
+    d = len(dims)
+    rng = np.random.default_rng(17)
+    a = rng.uniform(-1, 1, oracle.padded_shape(shape, dims))
+    op = getattr(torch.ops.lorastencil, f"stencil{d}d")
+    y = op(torch.from_numpy(a).cuda(), shape, 5, None, 0, 3)
+    ref = oracle.run_periodic(shape, a, oracle.effective_params(shape), 5)
+    assert np.abs(y.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+    # the cached plan goes back to the reference's halo semantics when the next call asks for them
+    y = op(torch.from_numpy(a).cuda(), shape, 5)
+    ref = oracle.run(shape, a, oracle.effective_params(shape), 5)
+    got = y.cpu().numpy()
+    if d == 1:
+        got, ref = got[:-1], ref[:-1]
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    with pytest.raises(ValueError, match="boundary"):
+        op(torch.from_numpy(a).cuda(), shape, 1, None, 0, 7)
