@@ -37,7 +37,15 @@ typedef enum {
     LORA_BOX2D3R = 5,
     LORA_BOX3D1R = 6,
     LORA_STAR3D1R = 7,
-    LORA_NUM_SHAPES = 8
+    LORA_NUM_SHAPES = 8,   /* the reference's shapes (src/3d/3d_utils.h:39-42 and siblings) end here */
+    /* radius-2 members of the family the reference does not have.  Their own layout:
+     * (h+4) x (m+4) x (n+8) doubles (the reference's 3-D layout with the plane halo widened to the radius), 125 weights
+     * [(dh+2)*25 + (dr+2)*5 + dc+2], every weight honoured in both modes (there is no reference operator whose quirks
+     * REFERENCE mode could restate).  Available through lora_gpu_run_host / lora_gpu_{box,star}_3d2r and the plan API
+     * on one GPU, one launch per time step; slabs, fused sweeps and the CLI do not know them. */
+    LORA_BOX3D2R = 8,
+    LORA_STAR3D2R = 9,
+    LORA_NUM_SHAPES_EXT = 10
 } lora_shape_t;
 
 /* how `params` is interpreted when a plan is built */
@@ -75,6 +83,9 @@ void lora_gpu_star_2d3r(const double *in, double *out, const double *params, int
 void lora_gpu_box_2d3r(const double *in, double *out, const double *params, int times, int input_m, int input_n);
 void lora_gpu_box_3d1r(const double *in, double *out, const double *params, int times, int input_h, int input_m, int input_n);
 void lora_gpu_star_3d1r(const double *in, double *out, const double *params, int times, int input_h, int input_m, int input_n);
+/* radius-2 shapes (new): in / out (h+4) x (m+4) x (n+8) doubles, params 125 doubles (NULL = lora_reference_table) */
+void lora_gpu_box_3d2r(const double *in, double *out, const double *params, int times, int input_h, int input_m, int input_n);
+void lora_gpu_star_3d2r(const double *in, double *out, const double *params, int times, int input_h, int input_m, int input_n);
 
 /* generic form of the seven above: shape selects the operator (box2d1r and box2d3r both run
  * gpu_box_2d3r, src/2d/main.cu:276-279); dims = {n} | {m,n} | {h,m,n}.  Same fatal-error
@@ -302,7 +313,10 @@ enum {
                                     zero (true for the reference's box table): those taps are not computed at all */
     LORA_FORM_RANK2 = 9,      /* 2-D: sum of 2 rank-1 terms of full support 7 (LU / cross approximation with full
                                  pivoting) -- any rank-2 table that is not pyramidal: 28 instead of 49 taps */
-    LORA_FORM_RANK3 = 10      /* 2-D: sum of 3 such terms: 42 taps */
+    LORA_FORM_RANK3 = 10,     /* 2-D: sum of 3 such terms: 42 taps */
+    LORA_FORM_STAR13 = 11,    /* 3-D radius 2: 13 taps */
+    LORA_FORM_HSEP5 = 12,     /* 3-D radius 2: a(h) (x) Q(m, n), rank 1 along the plane axis, any in-plane 5 x 5 table: 30 taps */
+    LORA_FORM_DIRECT125 = 13  /* 3-D radius 2: all 125 taps */
 };
 
 typedef struct {
@@ -320,10 +334,11 @@ typedef struct {
 int lora_decompose_2d(int shape, int mode, const double *params49, lora_decomp2d_t *out);
 
 /* the weight table the reference CLI passes for `shape` (src/1d/main.cu:77-78, src/2d/main.cu:139-195,
- * src/3d/main.cu:112-125): 9 / 49 / 27 doubles */
+ * src/3d/main.cu:112-125): 9 / 49 / 27 doubles; for the radius-2 shapes our own default, 125 doubles (box3d2r:
+ * [1,2,3,2,1] (x) [1,2,3,2,1] (x) [1,2,3,2,1]; star3d2r: centre 3, arms 2 then 1) */
 int lora_reference_table(int shape, double *table_out);
 
-/* effective direct-tap weights (9 / 49 / 27 doubles) a plan built from (shape, mode, params)
+/* effective direct-tap weights (9 / 49 / 27 / 125 doubles) a plan built from (shape, mode, params)
  * applies -- what the parity tests feed to the CPU oracle */
 int lora_effective_weights(int shape, int mode, const double *params, double *weights_out);
 

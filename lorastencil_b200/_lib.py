@@ -9,15 +9,30 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_longlong, c_
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-SHAPES = ("1d1r", "1d2r", "star2d1r", "box2d1r", "star2d3r", "box2d3r", "box3d1r", "star3d1r")
-SHAPE_IDS = {name: i for i, name in enumerate(SHAPES)}  # == lora_shape_t
+SHAPES = ("1d1r", "1d2r", "star2d1r", "box2d1r", "star2d3r", "box2d3r", "box3d1r", "star3d1r")  # the reference's
+R2_SHAPES = ("box3d2r", "star3d2r")  # radius-2 3-D shapes (new): own layout (h+4, m+4, n+8), 125 weights
+SHAPE_IDS = {name: i for i, name in enumerate(SHAPES + R2_SHAPES)}  # == lora_shape_t
+
+
+def nparams(shape: str) -> int:
+    """Length of the weight table of ``shape``: 9 (1-D), 49 (2-D), 27 (3-D), 125 (3-D radius 2)."""
+    sid = SHAPE_IDS[shape]
+    return 9 if sid < 2 else (49 if sid < 6 else (27 if sid < 8 else 125))
+
+
+def halo_of(shape: str) -> tuple:
+    """Storage halo per axis (S1: src/1d/main.cu:96, src/2d/main.cu:217-218, src/3d/main.cu:21-23; radius-2: ours)."""
+    sid = SHAPE_IDS[shape]
+    return (4,) if sid < 2 else ((4, 4) if sid < 6 else ((1, 2, 4) if sid < 8 else (2, 2, 4)))
+
+
 WEIGHTS_REFERENCE = 0
 WEIGHTS_GENERAL = 1
 
 # every symbol include/lorastencil.h declares (tests/test_abi.py checks the library exports them all)
 C_ABI_SYMBOLS = (
     "lora_gpu_1d1r", "lora_gpu_1d2r", "lora_gpu_star_2d1r", "lora_gpu_star_2d3r", "lora_gpu_box_2d3r",
-    "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
+    "lora_gpu_box_3d1r", "lora_gpu_star_3d1r", "lora_gpu_box_3d2r", "lora_gpu_star_3d2r", "lora_gpu_run_host", "lora_set_verbose", "lora_last_loop_ms",
     "lora_last_total_ms", "lora_last_chunks", "lora_last_bands", "lora_release_workspace", "lora_plan_create", "lora_plan_destroy",
     "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_set_temporal_block",
     "lora_plan_temporal_block", "lora_plan_set_boundary", "lora_plan_boundary", "lora_plan_wrap_ring", "lora_plan_step_fused", "lora_plan_step_mirror", "lora_plan_step_fused_mirror",
@@ -76,7 +91,8 @@ def lib() -> ctypes.CDLL:
     L = ctypes.CDLL(lib_path())
     dp = POINTER(c_double)
     for name, nd in (("lora_gpu_1d1r", 1), ("lora_gpu_1d2r", 1), ("lora_gpu_star_2d1r", 2), ("lora_gpu_star_2d3r", 2),
-                     ("lora_gpu_box_2d3r", 2), ("lora_gpu_box_3d1r", 3), ("lora_gpu_star_3d1r", 3)):
+                     ("lora_gpu_box_2d3r", 2), ("lora_gpu_box_3d1r", 3), ("lora_gpu_star_3d1r", 3),
+                     ("lora_gpu_box_3d2r", 3), ("lora_gpu_star_3d2r", 3)):
         f = getattr(L, name)
         f.argtypes = [c_void_p, c_void_p, dp, c_int] + [c_int] * nd
         f.restype = None

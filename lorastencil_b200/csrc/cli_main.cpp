@@ -35,6 +35,7 @@ struct ShapeName {
     const char *cli;   // argv[1]
     const char *info;  // ShapeStr[] of the reference
     int shape;
+    bool r2 = false;   // radius-2 3-D extension: layout (h+4) x (m+4) x (n+8), 125 weights (include/lorastencil.h)
 };
 
 #if LORA_CLI_DIM == 1
@@ -62,12 +63,14 @@ const int kFillMod = 100;  // src/2d/main.cu:235
 const int kNParams = 49;
 #else
 constexpr int kDim = 3;
-const ShapeName kShapes[] = {{"box3d1r", "box_3d1r", LORA_BOX3D1R}, {"star3d1r", "star_3d1r", LORA_STAR3D1R}};
+const ShapeName kShapes[] = {{"box3d1r", "box_3d1r", LORA_BOX3D1R}, {"star3d1r", "star_3d1r", LORA_STAR3D1R},
+                             {"box3d2r", "box_3d2r", LORA_BOX3D2R, true}, {"star3d2r", "star_3d2r", LORA_STAR3D2R, true}};
 const char *kHelp =
     "Program name: lorastencil_3d\n"
     "Usage: lorastencil_3d shape input_size_of_first_dimension input_size_of_second_dimension "
     "input_size_of_third_dimension time_size\n"
-    "Shape: box3d1r or star3d1r\n";
+    "Shape: box3d1r or star3d1r\n"
+    "Extra shapes (not in the reference): box3d2r or star3d2r\n";
 const int kHalo[3] = {1, 2, 4};
 const int kFillMod = 100;  // src/3d/main.cu:167
 const int kNParams = 27;
@@ -76,7 +79,10 @@ const int kNParams = 27;
 void print_help() { printf("%s\n", kHelp); }
 
 // one direct-tap step over the interior (the protocol of test_cpu, written for any dimension)
-void cpu_step(const std::vector<double> &in, std::vector<double> &out, const double *w, const long long *pd) {
+void cpu_step(const std::vector<double> &in, std::vector<double> &out, const double *w, const long long *pd,
+              const int *halo, int R) {
+    (void)halo;
+    (void)R;
 #if LORA_CLI_DIM == 1
     for (long long c = 4; c < pd[0] - 4; c++) {
         double a = 0;
@@ -92,14 +98,15 @@ void cpu_step(const std::vector<double> &in, std::vector<double> &out, const dou
             out[r * pd[1] + c] = a;
         }
 #else
-    for (long long h = 1; h < pd[0] - 1; h++)
-        for (long long r = 2; r < pd[1] - 2; r++)
-            for (long long c = 4; c < pd[2] - 4; c++) {
+    const int W = 2 * R + 1;  // 3 (the reference's window, src/3d/main.cu:33-68) or 5
+    for (long long h = halo[0]; h < pd[0] - halo[0]; h++)
+        for (long long r = halo[1]; r < pd[1] - halo[1]; r++)
+            for (long long c = halo[2]; c < pd[2] - halo[2]; c++) {
                 double a = 0;
-                for (int dh = -1; dh <= 1; dh++)
-                    for (int dr = -1; dr <= 1; dr++)
-                        for (int dc = -1; dc <= 1; dc++)
-                            a += w[(dh + 1) * 9 + (dr + 1) * 3 + dc + 1] *
+                for (int dh = -R; dh <= R; dh++)
+                    for (int dr = -R; dr <= R; dr++)
+                        for (int dc = -R; dc <= R; dc++)
+                            a += w[((dh + R) * W + dr + R) * W + dc + R] *
                                  in[((h + dh) * pd[1] + r + dr) * pd[2] + c + dc];
                 out[(h * pd[1] + r) * pd[2] + c] = a;
             }
@@ -139,6 +146,8 @@ int main(int argc, char *argv[]) {
     check = true;
 #endif
     const char *weights_path = nullptr;
+    int halo[3] = {kHalo[0], kHalo[1], kHalo[2]}, nparams = kNParams, radius = 1;
+    if (sn->r2) halo[0] = 2, nparams = 125, radius = 2;
     for (int i = kDim + 3; i < argc; i++) {
         if (std::strcmp(argv[i], "--check") == 0) check = true;
         // trailing "--gpus k": slab-decompose the grid over k GPUs of this box (same as LORA_NGPU=k)
@@ -146,7 +155,7 @@ int main(int argc, char *argv[]) {
         // trailing "--weights FILE": a caller's table instead of the hard-coded one, every weight honoured
         if (std::strcmp(argv[i], "--weights") == 0 && i + 1 < argc) weights_path = argv[++i];
     }
-    double params[49];
+    double params[125];
     lora_reference_table(sn->shape, params);
     int mode = LORA_WEIGHTS_REFERENCE;
     if (weights_path) {
@@ -157,12 +166,12 @@ int main(int argc, char *argv[]) {
         }
         std::vector<double> w;
         for (double v; f >> v;) w.push_back(v);
-        if (!f.eof() || (int)w.size() != kNParams) {
-            std::cerr << "Invalid argument: the weight file must hold exactly " << kNParams << " numbers (found " << w.size()
+        if (!f.eof() || (int)w.size() != nparams) {
+            std::cerr << "Invalid argument: the weight file must hold exactly " << nparams << " numbers (found " << w.size()
                       << (f.eof() ? "" : ", then something that is not a number") << ").\n";
             return 1;
         }
-        for (int i = 0; i < kNParams; i++) params[i] = w[i];
+        for (int i = 0; i < nparams; i++) params[i] = w[i];
         mode = LORA_WEIGHTS_GENERAL;
     }
 
@@ -175,7 +184,7 @@ int main(int argc, char *argv[]) {
            times);
 #endif
 
-    if (weights_path) printf("INFO: weights = %s (%d values, every one honoured)\n", weights_path, kNParams);
+    if (weights_path) printf("INFO: weights = %s (%d values, every one honoured)\n", weights_path, nparams);
 
     long long pd[3] = {1, 1, 1}, total = 1;
     for (int i = 0; i < kDim; i++) {
@@ -183,7 +192,7 @@ int main(int argc, char *argv[]) {
             std::cerr << "Argument out of range: sizes must be positive.\n";
             return 1;
         }
-        pd[i] = dims[i] + 2 * kHalo[i];
+        pd[i] = dims[i] + 2 * halo[i];
         total *= pd[i];
     }
     std::vector<double> matrix((size_t)total + 1), output((size_t)total + 1, 0.0);
@@ -200,9 +209,10 @@ int main(int argc, char *argv[]) {
             std::cout << std::endl;
         }
 #else
-        for (int h = 0; h < 3; h++) {
-            for (int r = 0; r < 3; r++) {
-                for (int c = 0; c < 3; c++) std::cout << params[h * 9 + r * 3 + c] << " ";
+        const int W = 2 * radius + 1;
+        for (int h = 0; h < W; h++) {
+            for (int r = 0; r < W; r++) {
+                for (int c = 0; c < W; c++) std::cout << params[(h * W + r) * W + c] << " ";
                 std::cout << std::endl;
             }
             std::cout << std::endl;
@@ -216,11 +226,11 @@ int main(int argc, char *argv[]) {
     if (check) {
         printf("\nChecking Correctness... \n");
         std::vector<double> naive((size_t)total + 1, 0.0), lora((size_t)total + 1, 0.0);
-        cpu_step(matrix, naive, params, pd);
+        cpu_step(matrix, naive, params, pd, halo, radius);
         lora_gpu_run_host(sn->shape, mode, matrix.data(), lora.data(), params, 1, dims);
         printf("Comparing naive and lora\n");
         long long bad = 0;
-        const long long lo[3] = {kHalo[0], kHalo[1], kHalo[2]};
+        const long long lo[3] = {halo[0], halo[1], halo[2]};
         for (long long a = lo[0]; a < pd[0] - lo[0]; a++)
             for (long long b = (kDim > 1 ? lo[1] : 0); b < (kDim > 1 ? pd[1] - lo[1] : 1); b++)
                 for (long long c = (kDim > 2 ? lo[2] : 0); c < (kDim > 2 ? pd[2] - lo[2] : 1); c++) {

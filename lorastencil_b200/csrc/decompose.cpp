@@ -17,13 +17,17 @@ int shape_dim(int s) {
     }
 }
 
+bool shape_is_r2(int s) { return s == LORA_BOX3D2R || s == LORA_STAR3D2R; }
+
 int shape_nparams(int s) {
+    if (shape_is_r2(s)) return 125;
     switch (shape_dim(s)) { case 1: return 9; case 2: return 49; case 3: return 27; default: return 0; }
 }
 
 const char *shape_cli_name(int s) {
-    static const char *n[] = {"1d1r", "1d2r", "star2d1r", "box2d1r", "star2d3r", "box2d3r", "box3d1r", "star3d1r"};
-    return (s >= 0 && s < LORA_NUM_SHAPES) ? n[s] : "?";
+    static const char *n[] = {"1d1r", "1d2r", "star2d1r", "box2d1r", "star2d3r", "box2d3r", "box3d1r", "star3d1r",
+                              "box3d2r", "star3d2r"};
+    return (s >= 0 && s < LORA_NUM_SHAPES_EXT) ? n[s] : "?";
 }
 
 // banners of the reference operators: src/1d/gpu_1r.cu:127, src/1d/gpu_2r.cu:129,
@@ -31,8 +35,8 @@ const char *shape_cli_name(int s) {
 // box2d1r runs gpu_box_2d3r and therefore prints "box_2d3r" (src/2d/main.cu:276-279).
 const char *shape_banner(int s) {
     static const char *n[] = {"1D 1d1r", "1D 1d2r", "2D star_2d1r", "2D box_2d3r", "2D star_2d3r", "2D box_2d3r",
-                              "3D box_3d1r", "3D star_3d1r"};
-    return (s >= 0 && s < LORA_NUM_SHAPES) ? n[s] : "?";
+                              "3D box_3d1r", "3D star_3d1r", "3D box_3d2r", "3D star_3d2r"};
+    return (s >= 0 && s < LORA_NUM_SHAPES_EXT) ? n[s] : "?";
 }
 
 // src/1d/gpu_1r.cu:132 (x3), src/1d/gpu_2r.cu:134 (x2), src/2d/gpu.cu:419 (x3), :478 (x1), :553 (x3),
@@ -98,6 +102,24 @@ void reference_table(int shape, double *out) {
             std::fill(out, out + 27, 0.0);
             out[13] = 2;
             out[4] = out[22] = out[10] = out[16] = out[12] = out[14] = 1;
+            return;
+        }
+        // radius-2 shapes: no reference table exists; small integers like the reference's, so that the first launches
+        // are exact in FP64
+        case LORA_BOX3D2R: {
+            const double a[5] = {1, 2, 3, 2, 1};
+            for (int h = 0; h < 5; h++)
+                for (int r = 0; r < 5; r++)
+                    for (int c = 0; c < 5; c++) out[h * 25 + r * 5 + c] = a[h] * a[r] * a[c];
+            return;
+        }
+        case LORA_STAR3D2R: {
+            std::fill(out, out + 125, 0.0);
+            out[62] = 3;
+            for (int d = 1; d <= 2; d++) {
+                const double v = 3 - d;
+                out[62 - d] = out[62 + d] = out[62 - 5 * d] = out[62 + 5 * d] = out[62 - 25 * d] = out[62 + 25 * d] = v;
+            }
             return;
         }
         default:
@@ -515,6 +537,82 @@ bool decompose_3d(int shape, int mode, const double *params, Decomp3D &d) {
     d.macs = 27;
     d.desc = "3d direct 27 taps (table is neither a star nor rank-1)";
     finish3(d, params);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3-D radius 2 (no reference counterpart: src/3d/3d_utils.h:39-42 stops at radius 1).  Every weight is honoured; the
+// form is what the STRUCTURE of the table allows: 13-point star, rank 1 along the plane axis, or all 125 taps.
+// ---------------------------------------------------------------------------------------------
+bool decompose_3d_r2(int shape, const double *params, Decomp3DR2 &d) {
+    if (!shape_is_r2(shape)) return false;
+    d = Decomp3DR2();
+    std::memcpy(d.w, params, sizeof d.w);
+    bool star = true;
+    for (int h = -2; h <= 2 && star; h++)
+        for (int r = -2; r <= 2 && star; r++)
+            for (int c = -2; c <= 2; c++) {
+                const bool on_axis = (h == 0 && r == 0) || (h == 0 && c == 0) || (r == 0 && c == 0);
+                if (!on_axis && params[(h + 2) * 25 + (r + 2) * 5 + c + 2] != 0.0) {
+                    star = false;
+                    break;
+                }
+            }
+    if (star) {
+        d.form = LORA_FORM_STAR13;
+        d.macs = 13;
+        d.desc = "3d radius-2 13-point star";
+        return true;
+    }
+    // rank 1 along the plane axis: w[dh] = a[dh] * Q with Q = the plane through the largest entry, a = the column of
+    // ratios through that entry -- accepted only when the product reproduces every weight to a few ulps; the kernel
+    // then applies a[dh] * Q, and the effective taps reported are those products
+    const double scale = std::max(max_abs(params, 125), 1e-300);
+    const double tol = 64 * 2.220446049250313e-16 * scale;
+    int best = 0;
+    for (int i = 1; i < 125; i++)
+        if (std::fabs(params[i]) > std::fabs(params[best])) best = i;
+    const int h0 = best / 25, i0 = best % 25;
+    if (std::fabs(params[best]) > 0) {
+        // a = column / s, Q = plane * s / pivot for any s: try the smallest column entry first (integer tables such as
+        // [1,2,3,2,1] (x) Q then factor into integers again and the kernel's sums stay exact), then the pivot, then 1;
+        // the first scaling that reproduces every weight EXACTLY wins, otherwise the closest
+        const double piv = params[best];
+        double smin = std::fabs(piv);
+        for (int h = 0; h < 5; h++) {
+            const double v = std::fabs(params[h * 25 + i0]);
+            if (v > 0 && v < smin) smin = v;
+        }
+        const double cand[3] = {smin, piv, 1.0};
+        double best_err = -1, a[5], q[25];
+        for (double sc : cand) {
+            double ta[5], tq[25], err = 0;
+            for (int h = 0; h < 5; h++) ta[h] = params[h * 25 + i0] / sc;
+            for (int i = 0; i < 25; i++) tq[i] = params[h0 * 25 + i] * sc / piv;
+            for (int h = 0; h < 5; h++)
+                for (int i = 0; i < 25; i++) err = std::max(err, std::fabs(ta[h] * tq[i] - params[h * 25 + i]));
+            if (best_err < 0 || err < best_err) {
+                best_err = err;
+                std::memcpy(a, ta, sizeof a);
+                std::memcpy(q, tq, sizeof q);
+            }
+            if (err == 0) break;
+        }
+        if (best_err <= tol) {
+            d.form = LORA_FORM_HSEP5;
+            std::memcpy(d.a, a, sizeof a);
+            std::memcpy(d.q, q, sizeof q);
+            for (int h = 0; h < 5; h++)
+                for (int i = 0; i < 25; i++) d.w[h * 25 + i] = d.a[h] * d.q[i];
+            d.recon_err = best_err;
+            d.macs = 30;
+            d.desc = "3d radius-2 a(h) x Q(m,n): rank 1 along the plane axis, 25 + 5 taps";
+            return true;
+        }
+    }
+    d.form = LORA_FORM_DIRECT125;
+    d.macs = 125;
+    d.desc = "3d radius-2 direct 125 taps";
     return true;
 }
 

@@ -44,8 +44,21 @@ struct Decomp3D {
     std::string desc;
 };
 
-int shape_dim(int shape);                 // 1, 2, 3 or 0 when invalid
-int shape_nparams(int shape);             // 9, 49, 27
+// radius-2 3-D shapes (box3d2r / star3d2r; stencil3d_r2.cu): their own layout and 125 weights
+struct Decomp3DR2 {
+    int form = LORA_FORM_DIRECT125;
+    double w[125] = {};   // effective taps [(dh+2)*25 + (dr+2)*5 + dc+2] (== the table: every weight is honoured)
+    double q[25] = {};    // HSEP5: w[dh][dr][dc] = a[dh+2] * q[(dr+2)*5 + dc+2]
+    double a[5] = {};
+    double recon_err = 0.0;
+    int macs = 125;
+    std::string desc;
+};
+
+int shape_dim(int shape);                 // 1, 2, 3 -- or 0 when invalid AND for the radius-2 shapes, which only the code
+                                          // paths that ask shape_is_r2() know (everything else refuses them)
+bool shape_is_r2(int shape);              // LORA_BOX3D2R / LORA_STAR3D2R
+int shape_nparams(int shape);             // 9, 49, 27, 125
 const char *shape_cli_name(int shape);    // "box2d1r" ...
 const char *shape_banner(int shape);      // "2D box_2d3r" ... as printed by the reference operator
 int shape_artifact_k(int shape);          // the K multiplier of the reference's GStencil/s printout
@@ -56,5 +69,6 @@ void reference_table(int shape, double *out);
 bool decompose_1d(int shape, int mode, const double *params, Decomp1D &d);
 bool decompose_2d(int shape, int mode, const double *params, Decomp2D &d);
 bool decompose_3d(int shape, int mode, const double *params, Decomp3D &d);
+bool decompose_3d_r2(int shape, const double *params, Decomp3DR2 &d);
 
 }  // namespace lora

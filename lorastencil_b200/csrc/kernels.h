@@ -267,6 +267,24 @@ struct GeomDirect {
 };
 cudaError_t launch_direct(int dim, const GeomDirect &g, const WeightsDirect49 &w, cudaStream_t s);
 
+// radius-2 3-D shapes (stencil3d_r2.cu): layout (h + 4) x (m + 4) x (n + 8), interior planes [lo, hi) of the launch
+struct Geom3DR2 {
+    const double *in;
+    double *out;
+    long long row_pitch, plane_pitch;  // padded columns; padded rows * padded columns
+    int m, n;                          // interior rows per plane, columns
+    long long lo, hi;                  // output planes of this launch
+    int planes_per_chunk;              // blockIdx.z walks chunks of this many output planes (+ 4 planes of warm-up)
+};
+struct WeightsR2 {
+    double w[125];  // [(dh + 2) * 25 + (dr + 2) * 5 + dc + 2]: every form's effective taps (STAR13 / DIRECT125 read these)
+    double q[25];   // HSEP5: in-plane table, w[dh][dr][dc] = a[dh + 2] * q[(dr + 2) * 5 + dc + 2]
+    double a[5];
+};
+cudaError_t launch_3d_r2(int form, const Geom3DR2 &g, const WeightsR2 &w, cudaStream_t s);
+int r2_rows_per_cta();
+int r2_cols_per_cta();
+
 // periodic halo ring (boundary.cu): one axis of an array seen as [outer][len + 2 halo][inner]
 cudaError_t launch_wrap_axis(double *buf, long long outer, long long len, int halo, long long inner, int sm_count,
                              cudaStream_t s);

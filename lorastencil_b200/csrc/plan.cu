@@ -87,6 +87,10 @@ struct lora_plan {
     int shape = 0, mode = 0, dim = 0;
     long long dims[3] = {0, 0, 0};    // interior
     long long padded[3] = {0, 0, 0};  // with halos
+    int halo[3] = {0, 0, 0};          // storage halo per axis: S1 (4 | 4,4 | 1,2,4); radius-2 3-D shapes 2,2,4
+    int radius0 = 0;                  // stencil radius along the outermost axis (4 | 3 | 1; radius-2 shapes 2)
+    bool r2 = false;                  // LORA_BOX3D2R / LORA_STAR3D2R: own layout, own kernel (stencil3d_r2.cu)
+    WeightsR2 wr2{};
     long long elems = 0;
     int form = 0;
     Weights1D w1{};
@@ -164,7 +168,8 @@ static int check_device(const lora_plan *p) {
 
 extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const double *params, const long long *dims) {
     if (!out || !dims) return fail(LORA_ERR_ARG, "null argument");
-    const int dim = shape_dim(shape);
+    const bool r2 = shape_is_r2(shape);
+    const int dim = r2 ? 3 : shape_dim(shape);
     if (dim == 0) return fail(LORA_ERR_ARG, "unknown shape %d", shape);
     if (mode != LORA_WEIGHTS_REFERENCE && mode != LORA_WEIGHTS_GENERAL) return fail(LORA_ERR_ARG, "bad mode %d", mode);
     for (int i = 0; i < dim; i++)
@@ -176,19 +181,31 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
     p->shape = shape;
     p->mode = mode;
     p->dim = dim;
-    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
+    p->r2 = r2;
+    static const int halo[5][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}, {2, 2, 4}};
+    static const int radius0[5] = {0, 4, 3, 1, 2};
+    p->radius0 = radius0[r2 ? 4 : dim];
     p->elems = 1;
     for (int i = 0; i < dim; i++) {
         p->dims[i] = dims[i];
-        p->padded[i] = dims[i] + 2 * halo[dim][i];
+        p->halo[i] = halo[r2 ? 4 : dim][i];
+        p->padded[i] = dims[i] + 2 * p->halo[i];
         p->elems *= p->padded[i];
     }
-    double table[49];
+    double table[125];
     if (!params) {
         reference_table(shape, table);
         params = table;
     }
-    if (dim == 1) {
+    if (r2) {
+        Decomp3DR2 d;
+        decompose_3d_r2(shape, params, d);
+        std::memcpy(p->wr2.w, d.w, sizeof d.w);
+        std::memcpy(p->wr2.q, d.q, sizeof d.q);
+        std::memcpy(p->wr2.a, d.a, sizeof d.a);
+        p->form = d.form;
+        p->desc = d.desc;
+    } else if (dim == 1) {
         Decomp1D d;
         decompose_1d(shape, mode, params, d);
         std::memcpy(p->w1.w, d.w, sizeof d.w);
@@ -218,7 +235,7 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         p->form = d.form;
         p->desc = d.desc;
     }
-    if (dim >= 2 && p->padded[dim - 1] % 2) {
+    if (!r2 && dim >= 2 && p->padded[dim - 1] % 2) {
         // odd row length: rows are not 16-byte aligned, no TMA descriptor exists for this grid (stencil_direct.cu)
         p->odd_cols = true;
         p->desc += " [odd column count: direct taps without TMA]";
@@ -237,6 +254,10 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         if (v >= 1 && v <= 64) warps_per_sm = v;
     }
     p->slots = (dim == 3) ? p->sm_count : p->sm_count * warps_per_sm;
+    if (r2) {  // one launch per time step, no TMA descriptor, no fused sweeps
+        *out = p;
+        return LORA_OK;
+    }
     if (dim == 2 && tb2_form(p->form) && !p->odd_cols) {
         // 2-D fusion (stencil2d_tb.cu), 10240^2 on B200, GStencil/s: the cross form runs sweeps of three launches (627 vs
         // 369 unfused); the diamond and pyramid forms sweeps of two (538 vs 370, three: 515; 418 vs 372, three: 318)
@@ -490,6 +511,28 @@ static int step_unfused(lora_plan_t *p, const double *src, double *dst, long lon
         g.vec4 = (lo % 4 == 0) && (reinterpret_cast<uintptr_t>(dst) % 32 == 0);
         g.mirror = mirror_base ? (long long)(mirror_base - dst) : 0;
         e = launch_1d(g, p->w1, st);
+    } else if (p->r2) {
+        if (mirror_base || (ex && (ex->band_lo > 0 || ex->band_hi > 0)))
+            return fail(LORA_ERR_UNSUPPORTED, "the radius-2 3-D shapes run on one GPU (no slab exchange)");
+        Geom3DR2 g;
+        g.in = src;
+        g.out = dst;
+        g.row_pitch = p->padded[2];
+        g.plane_pitch = p->padded[1] * p->padded[2];
+        g.m = (int)p->dims[1];
+        g.n = (int)p->dims[2];
+        g.lo = lo;
+        g.hi = hi;
+        // plane chunks: every chunk re-reads 4 planes of warm-up, so as long as possible -- but at least ~4 CTAs per SM
+        // in the grid (256 threads each), and never more than the z extent of a grid allows
+        const long long per_plane = (long long)((g.n + r2_cols_per_cta() - 1) / r2_cols_per_cta()) *
+                                    ((g.m + r2_rows_per_cta() - 1) / r2_rows_per_cta());
+        long long want = (4LL * p->sm_count + per_plane - 1) / per_plane;  // chunks wanted
+        want = std::max(1LL, std::min(want, (hi - lo + 7) / 8));          // ... of at least 8 planes each
+        long long L = (hi - lo + want - 1) / want;
+        L = std::max(L, (hi - lo + 65534) / 65535);
+        g.planes_per_chunk = (int)std::min<long long>(L, 0x7fffffff);
+        e = launch_3d_r2(p->form, g, p->wr2, st);
     } else if (p->odd_cols) {
         SegCut sc;
         if (int rc = cut_segments(lo, hi, dst, ex, mirror_base, sc)) return rc;
@@ -871,11 +914,10 @@ extern "C" int lora_plan_set_boundary(lora_plan_t *p, int mode) {
                mode != LORA_BOUNDARY_PERIODIC))
         return fail(LORA_ERR_ARG, "bad boundary mode");
     if (mode == LORA_BOUNDARY_PERIODIC) {  // the wrap reads `halo` interior cells behind each face
-        static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
         for (int i = 0; i < p->dim; i++)
-            if (p->dims[i] < halo[p->dim][i])
+            if (p->dims[i] < p->halo[i])
                 return fail(LORA_ERR_UNSUPPORTED, "a periodic boundary needs at least %d cells along axis %d (the storage halo), got %lld",
-                            halo[p->dim][i], i, p->dims[i]);
+                            p->halo[i], i, p->dims[i]);
     }
     p->boundary = mode;
     return LORA_OK;
@@ -886,9 +928,8 @@ extern "C" int lora_plan_boundary(const lora_plan_t *p) { return p ? p->boundary
 // restricted to padded indices [r0, r1) of the outermost axis (the bands of run_host_pipelined)
 static int copy_ring_rows(const lora_plan *p, double *dst, const double *src, long long r0, long long r1, cudaStream_t st,
                           bool lead = true, bool trail = true) {
-    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
     const int dim = p->dim;
-    const long long P0 = p->padded[0], rest = p->elems / P0, h0 = halo[dim][0];
+    const long long P0 = p->padded[0], rest = p->elems / P0, h0 = p->halo[0];
     r0 = std::max(r0, 0LL);
     r1 = std::min(r1, P0);
     if (r0 >= r1) return LORA_OK;
@@ -925,11 +966,10 @@ static int copy_ring(const lora_plan *p, double *dst, const double *src, cudaStr
 }
 // LORA_BOUNDARY_PERIODIC: halo ring of buf <- the periodic image of buf's interior (boundary.cu), innermost axis first
 static int wrap_ring(const lora_plan *p, double *buf, cudaStream_t st) {
-    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
     long long inner = 1;
     for (int ax = p->dim - 1; ax >= 0; ax--) {
         const long long line = p->padded[ax] * inner;  // doubles in one padded line of this axis
-        CU_TRY(launch_wrap_axis(buf, p->elems / line, p->dims[ax], halo[p->dim][ax], inner, p->sm_count, st));
+        CU_TRY(launch_wrap_axis(buf, p->elems / line, p->dims[ax], p->halo[ax], inner, p->sm_count, st));
         inner = line;
     }
     return LORA_OK;
@@ -937,9 +977,8 @@ static int wrap_ring(const lora_plan *p, double *buf, cudaStream_t st) {
 extern "C" int lora_plan_wrap_ring(lora_plan_t *p, double *buf, void *stream) {
     if (!p || !buf) return fail(LORA_ERR_ARG, "null argument");
     if (int rc = check_device(p)) return rc;
-    static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
     for (int i = 0; i < p->dim; i++)
-        if (p->dims[i] < halo[p->dim][i]) return fail(LORA_ERR_UNSUPPORTED, "grid thinner than its storage halo along axis %d", i);
+        if (p->dims[i] < p->halo[i]) return fail(LORA_ERR_UNSUPPORTED, "grid thinner than its storage halo along axis %d", i);
     return wrap_ring(p, buf, static_cast<cudaStream_t>(stream));
 }
 
@@ -1294,18 +1333,24 @@ extern "C" int lora_decompose_2d(int shape, int mode, const double *params49, lo
 }
 
 extern "C" int lora_reference_table(int shape, double *table_out) {
-    if (!table_out || shape_dim(shape) == 0) return fail(LORA_ERR_ARG, "bad argument");
+    if (!table_out || (shape_dim(shape) == 0 && !shape_is_r2(shape))) return fail(LORA_ERR_ARG, "bad argument");
     reference_table(shape, table_out);
     return LORA_OK;
 }
 
 extern "C" int lora_effective_weights(int shape, int mode, const double *params, double *w) {
     if (!w) return fail(LORA_ERR_ARG, "null argument");
-    double table[49];
+    double table[125];
     if (!params) {
-        if (shape_dim(shape) == 0) return fail(LORA_ERR_ARG, "unknown shape %d", shape);
+        if (shape_dim(shape) == 0 && !shape_is_r2(shape)) return fail(LORA_ERR_ARG, "unknown shape %d", shape);
         reference_table(shape, table);
         params = table;
+    }
+    if (shape_is_r2(shape)) {
+        Decomp3DR2 d;
+        decompose_3d_r2(shape, params, d);
+        std::memcpy(w, d.w, sizeof d.w);
+        return LORA_OK;
     }
     switch (shape_dim(shape)) {
         case 1: {
@@ -1609,7 +1654,6 @@ static void run_host_pipelined(lora_plan *p, const double *in, double *out, int 
     const size_t bytes = (size_t)p->elems * sizeof(double);
     const long long rows = p->padded[0], rest = p->elems / p->padded[0];
     const long long h0 = (p->padded[0] - p->dims[0]) / 2, n0 = p->dims[0];
-    static const int radius0[4] = {0, 4, 3, 1};
     std::lock_guard<std::mutex> lk(g_ws_mutex);
     ws_reserve(2, bytes);
     double *b0 = g_ws[0], *b1 = g_ws[1];
@@ -1620,7 +1664,7 @@ static void run_host_pipelined(lora_plan *p, const double *in, double *out, int 
     if (pair_sweeps(p))
         for (int tb : tbs) npairs += tb == 2;
     long long rmax = 0;
-    for (int tb : tbs) rmax = std::max(rmax, (long long)radius0[p->dim] * tb);
+    for (int tb : tbs) rmax = std::max(rmax, (long long)p->radius0 * tb);
     // few, large bands: every band is swept launch by launch, and launches over a few hundred rows fill the GPU badly
     // (10240^2 x 100 launches: 12 bands -> 45 ms of launches, the whole grid at once 28 ms); about 200 MB per band, at
     // most 6, leaves a quarter to a sixth of one copy exposed at either end
@@ -1802,6 +1846,10 @@ extern "C" void lora_gpu_run_host(int shape, int mode, const double *in, double 
     g_last_gpus = 1;
     std::vector<int> devices;
     const int k = wanted_gpus(devices);
+    if (k > 1 && shape_is_r2(shape)) {
+        fail(LORA_ERR_UNSUPPORTED, "the radius-2 3-D shapes run on one GPU (LORA_NGPU / lora_set_gpus asked for %d)", k);
+        die_plan("slabs");
+    }
     if (k > 1 && shape_dim(shape) != 0 && dims && in && out && times >= 0 &&
         run_host_multi_gpu(devices, shape, mode, in, out, params, times, dims)) {
         g_total_ms = std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t_begin).count() / 1e3;
@@ -1844,6 +1892,14 @@ extern "C" void lora_gpu_box_2d3r(const double *in, double *out, const double *p
 extern "C" void lora_gpu_box_3d1r(const double *in, double *out, const double *params, int times, int h, int m, int n) {
     const long long d[3] = {h, m, n};
     lora_gpu_run_host(LORA_BOX3D1R, LORA_WEIGHTS_REFERENCE, in, out, params, times, d);
+}
+extern "C" void lora_gpu_box_3d2r(const double *in, double *out, const double *params, int times, int h, int m, int n) {
+    const long long d[3] = {h, m, n};
+    lora_gpu_run_host(LORA_BOX3D2R, LORA_WEIGHTS_GENERAL, in, out, params, times, d);
+}
+extern "C" void lora_gpu_star_3d2r(const double *in, double *out, const double *params, int times, int h, int m, int n) {
+    const long long d[3] = {h, m, n};
+    lora_gpu_run_host(LORA_STAR3D2R, LORA_WEIGHTS_GENERAL, in, out, params, times, d);
 }
 extern "C" void lora_gpu_star_3d1r(const double *in, double *out, const double *params, int times, int h, int m, int n) {
     const long long d[3] = {h, m, n};

@@ -429,10 +429,10 @@ extern "C" void lora_slabset_destroy(lora_slabset_t *set) {
 extern "C" int lora_slabset_create(lora_slabset_t **out, int shape, int mode, const double *params,
                                    const long long *global_dims, int ndev, const int *devices) {
     if (!out || !global_dims || ndev < 1) return lora_fail(LORA_ERR_ARG, "bad argument");
+    const int dim = shape_dim(shape);  // 0 for the radius-2 3-D shapes too: one GPU only (stencil3d_r2.cu)
+    if (dim == 0) return lora_fail(LORA_ERR_ARG, "unknown shape %d (slabs cut the reference's eight shapes)", shape);
     int have = 0;
     SL_TRY(cudaGetDeviceCount(&have));
-    const int dim = shape_dim(shape);
-    if (dim == 0) return lora_fail(LORA_ERR_ARG, "unknown shape %d", shape);
     static const int halo[4][3] = {{0, 0, 0}, {4, 0, 0}, {4, 4, 0}, {1, 2, 4}};
     lora_slabset *set = new lora_slabset;
     set->dim = dim, set->ndev = ndev, set->shape = shape;

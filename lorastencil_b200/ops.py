@@ -76,10 +76,23 @@ def gpu_star_3d1r(in_, out, params, times, input_h, input_m, input_n):
                  (input_h, input_m, input_n))
 
 
+def gpu_box_3d2r(in_, out, params, times, input_h, input_m, input_n):
+    """Radius-2 box (125 weights) -- not in the reference; arrays of (h+4, m+4, n+8) doubles."""
+    return _call("gpu_box_3d2r", 125, (input_h + 4, input_m + 4, input_n + 8), in_, out, params, times,
+                 (input_h, input_m, input_n))
+
+
+def gpu_star_3d2r(in_, out, params, times, input_h, input_m, input_n):
+    """Radius-2 13-point star (125 weights, off-axis entries zero) -- not in the reference; (h+4, m+4, n+8) doubles."""
+    return _call("gpu_star_3d2r", 125, (input_h + 4, input_m + 4, input_n + 8), in_, out, params, times,
+                 (input_h, input_m, input_n))
+
+
 # CLI shape name -> operator, as dispatched by the reference drivers
 # (src/1d/main.cu:126-133, src/2d/main.cu:268-280, src/3d/main.cu:192-199)
 BY_SHAPE = {"1d1r": gpu_1d1r, "1d2r": gpu_1d2r, "star2d1r": gpu_star_2d1r, "star2d3r": gpu_star_2d3r,
-            "box2d1r": gpu_box_2d3r, "box2d3r": gpu_box_2d3r, "box3d1r": gpu_box_3d1r, "star3d1r": gpu_star_3d1r}
+            "box2d1r": gpu_box_2d3r, "box2d3r": gpu_box_2d3r, "box3d1r": gpu_box_3d1r, "star3d1r": gpu_star_3d1r,
+            "box3d2r": gpu_box_3d2r, "star3d2r": gpu_star_3d2r}  # the last two: new, not reference operators
 
 
 def run_host(shape: str, in_, out, params, times: int, dims, mode: int = _lib.WEIGHTS_REFERENCE):
@@ -88,7 +101,7 @@ def run_host(shape: str, in_, out, params, times: int, dims, mode: int = _lib.WE
     sid = _lib.SHAPE_IDS[shape]
     pin, _ = _ptr(in_)
     pout, _ = _ptr(out)
-    p = _params(params, {1: 9, 2: 49, 3: 27}[len(dims)])
+    p = _params(params, _lib.nparams(shape))
     d = (c_longlong * 3)(*[int(x) for x in dims], *([0] * (3 - len(dims))))
     L.lora_gpu_run_host(sid, int(mode), pin, pout, p.ctypes.data_as(POINTER(c_double)), int(times), d)
     return out

@@ -13,7 +13,7 @@ MAX_TB_1D = 15     # deepest temporal block of the 1-D kernel (kMaxTb1 in csrc/k
 DEFAULT_TB_1D = 15  # kDefaultTb1
 BOUNDARY_NAMES = ["reference", "dirichlet", "zero", "periodic"]
 FORM_NAMES = {0: "taps9", 1: "cross", 2: "pyramid", 3: "diamond", 4: "direct49", 5: "sep3", 6: "star7", 7: "direct27",
-              8: "pyramid_pruned", 9: "rank2", 10: "rank3"}
+              8: "pyramid_pruned", 9: "rank2", 10: "rank3", 11: "star13", 12: "hsep5", 13: "direct125"}
 
 
 def _dp(a: np.ndarray):
@@ -23,8 +23,7 @@ def _dp(a: np.ndarray):
 def reference_table(shape: str) -> np.ndarray:
     """The weight table the reference CLI passes for ``shape``."""
     sid = _lib.SHAPE_IDS[shape]
-    n = 9 if sid < 2 else (49 if sid < 6 else 27)
-    out = np.zeros(n, dtype=np.float64)
+    out = np.zeros(_lib.nparams(shape), dtype=np.float64)
     _lib.check(_lib.lib().lora_reference_table(sid, _dp(out)), "lora_reference_table")
     return out
 
@@ -32,8 +31,7 @@ def reference_table(shape: str) -> np.ndarray:
 def effective_weights(shape: str, mode: int = _lib.WEIGHTS_REFERENCE, params=None) -> np.ndarray:
     """Direct-tap weights a plan built from (shape, mode, params) applies."""
     sid = _lib.SHAPE_IDS[shape]
-    n = 9 if sid < 2 else (49 if sid < 6 else 27)
-    out = np.zeros(n, dtype=np.float64)
+    out = np.zeros(_lib.nparams(shape), dtype=np.float64)
     p = None if params is None else np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
     _lib.check(_lib.lib().lora_effective_weights(sid, int(mode), None if p is None else _dp(p), _dp(out)),
                "lora_effective_weights")
@@ -62,7 +60,9 @@ class Plan:
         self.shape = shape
         self.dims = tuple(int(d) for d in dims)
         self.dim = len(self.dims)
-        self.padded_shape = tuple(d + 2 * h for d, h in zip(self.dims, HALO[self.dim]))
+        if len(_lib.halo_of(shape)) != self.dim:
+            raise ValueError(f"{shape} takes {len(_lib.halo_of(shape))} sizes, got {self.dims}")
+        self.padded_shape = tuple(d + 2 * h for d, h in zip(self.dims, _lib.halo_of(shape)))
         self._h = c_void_p()
         p = None if params is None else np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
         d = (c_longlong * 3)(*self.dims, *([0] * (3 - self.dim)))
@@ -76,7 +76,7 @@ class Plan:
         self.shape = shape
         self.dims = tuple(int(d) for d in dims)
         self.dim = len(self.dims)
-        self.padded_shape = tuple(d + 2 * h for d, h in zip(self.dims, HALO[self.dim]))
+        self.padded_shape = tuple(d + 2 * h for d, h in zip(self.dims, _lib.halo_of(shape)))
         self._h = c_void_p(handle)
         self._borrowed = True
         return self

@@ -6,8 +6,8 @@ for callers whose grids already live in HBM:
 
     out = torch.ops.lorastencil.stencil2d(x, "box2d3r", times, params=None, mode=0, boundary=0)
 
-``x``: contiguous float64 CUDA tensor of the PADDED shape (1-D ``n+8``; 2-D ``(m+8, n+8)``; 3-D ``(h+2, m+4, n+8)``),
-halo included.  Returns a new tensor of the same shape holding the whole padded buffer ``times % 2`` of the reference's
+``x``: contiguous float64 CUDA tensor of the PADDED shape (1-D ``n+8``; 2-D ``(m+8, n+8)``; 3-D ``(h+2, m+4, n+8)``;
+the radius-2 extensions ``box3d2r`` / ``star3d2r``: ``(h+4, m+4, n+8)`` and 125 weights), halo included.  Returns a new tensor of the same shape holding the whole padded buffer ``times % 2`` of the reference's
 ping-pong (S2/S3: halo = the caller's for even ``times``, zero for odd).  ``params``: 9 / 49 / 27 weights (None = the
 reference CLI's table for the shape); ``mode``: 0 = what the reference GPU operator does with ``params``, 1 = every
 weight honoured; ``boundary``: 0 = the reference's ping-pong halo (S2), 1 = Dirichlet (the caller's halo at every
@@ -25,7 +25,8 @@ from . import _lib
 from .plan import BOUNDARY_NAMES, HALO, Plan
 
 _PLANS: dict = {}
-_DIM_SHAPES = {1: ("1d1r", "1d2r"), 2: ("star2d1r", "box2d1r", "star2d3r", "box2d3r"), 3: ("box3d1r", "star3d1r")}
+_DIM_SHAPES = {1: ("1d1r", "1d2r"), 2: ("star2d1r", "box2d1r", "star2d3r", "box2d3r"),
+               3: ("box3d1r", "star3d1r", "box3d2r", "star3d2r")}
 
 
 def _plan_for(x: torch.Tensor, dim: int, shape: str, params: Optional[torch.Tensor], mode: int) -> Plan:
@@ -33,7 +34,7 @@ def _plan_for(x: torch.Tensor, dim: int, shape: str, params: Optional[torch.Tens
         raise ValueError(f"stencil{dim}d: shape must be one of {_DIM_SHAPES[dim]}, got {shape!r}")
     if x.dim() != dim or x.dtype != torch.float64 or not x.is_contiguous():
         raise TypeError(f"stencil{dim}d: expected a contiguous float64 tensor with {dim} dimension(s) (padded grid)")
-    dims = tuple(int(s) - 2 * h for s, h in zip(x.shape, HALO[dim]))
+    dims = tuple(int(s) - 2 * h for s, h in zip(x.shape, _lib.halo_of(shape)))
     if min(dims) < 1:
         raise ValueError(f"stencil{dim}d: padded shape {tuple(x.shape)} leaves no interior")
     p = None if params is None else np.ascontiguousarray(params.detach().cpu().numpy().astype(np.float64).reshape(-1))

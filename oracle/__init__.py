@@ -56,7 +56,8 @@ def dim_of(shape: str) -> int:
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
-    if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")):
+    so, src = os.path.join(_HERE, "liboracle.so"), os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
 
 
@@ -83,7 +84,9 @@ def lib() -> ctypes.CDLL:
         L.oracle_run_1d.argtypes = [dp, dp, dp, c_int, c_longlong]
         L.oracle_run_2d.argtypes = [dp, dp, dp, c_int, c_longlong, c_longlong]
         L.oracle_run_3d.argtypes = [dp, dp, dp, c_int, c_longlong, c_longlong, c_longlong]
-        for f in (L.oracle_run_1d, L.oracle_run_2d, L.oracle_run_3d):
+        L.oracle_step_3d_r2.argtypes = [dp, dp, dp, c_longlong, c_longlong, c_longlong]
+        L.oracle_run_3d_r2.argtypes = [dp, dp, dp, c_int, c_longlong, c_longlong, c_longlong]
+        for f in (L.oracle_run_1d, L.oracle_run_2d, L.oracle_run_3d, L.oracle_run_3d_r2):
             f.restype = c_int
         _LIB = L
     return _LIB
@@ -141,6 +144,56 @@ def run(shape_or_dim, a: np.ndarray, params: np.ndarray, times: int, out: np.nda
         rc = L.oracle_run_3d(_p(a), _p(out), _p(params), times, a.shape[0] - 2 * h[0], a.shape[1] - 2 * h[1],
                              a.shape[2] - 2 * h[2])
     if rc != 0:
+        raise MemoryError("oracle work buffers")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# radius-2 3-D shapes (box3d2r / star3d2r): NOT in the reference; checker of the product's extension
+# --------------------------------------------------------------------------------------------
+HALO_R2 = (2, 2, 4)
+R2_SHAPES = ("box3d2r", "star3d2r")
+
+
+def padded_shape_r2(dims) -> tuple:
+    return tuple(d + 2 * k for d, k in zip(dims, HALO_R2))
+
+
+def reference_params_r2(shape: str) -> np.ndarray:
+    """The default tables of the product for these shapes (include/lorastencil.h: lora_reference_table), restated."""
+    if shape == "box3d2r":
+        a = np.array([1.0, 2.0, 3.0, 2.0, 1.0])
+        return np.einsum("i,j,k->ijk", a, a, a).reshape(-1)
+    if shape == "star3d2r":
+        w = np.zeros((5, 5, 5))
+        for d, v in ((0, 3.0), (1, 2.0), (2, 1.0)):
+            for ax in range(3):
+                for sgn in (-1, 1):
+                    idx = [2, 2, 2]
+                    idx[ax] += sgn * d
+                    w[tuple(idx)] = v
+        return w.reshape(-1)
+    raise ValueError(shape)
+
+
+def step_r2(a: np.ndarray, params: np.ndarray) -> np.ndarray:
+    """One direct-tap step over the interior of a (h+4, m+4, n+8) array: a zero array with the interior written."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    assert a.ndim == 3 and params.size == 125
+    out = np.zeros_like(a)
+    lib().oracle_step_3d_r2(_p(a), _p(out), _p(params), a.shape[0], a.shape[1], a.shape[2])
+    return out
+
+
+def run_r2(a: np.ndarray, params: np.ndarray, times: int) -> np.ndarray:
+    """``times`` launches with the gpu_* buffer semantics (S2/S3) on the radius-2 layout."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    assert a.ndim == 3 and params.size == 125
+    out = np.zeros_like(a)
+    h, m, n = (s - 2 * k for s, k in zip(a.shape, HALO_R2))
+    if lib().oracle_run_3d_r2(_p(a), _p(out), _p(params), int(times), h, m, n) != 0:
         raise MemoryError("oracle work buffers")
     return out
 

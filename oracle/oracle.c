@@ -165,3 +165,39 @@ int oracle_run_3d(const double *in, double *out, const double *param, int times,
     i64 total = dims[0] * dims[1] * dims[2];
     return run_generic(in, out, total, total, times, step3, param, dims);
 }
+
+/* ---- radius-2 3-D shapes (box3d2r / star3d2r) -- NOT in the reference (src/3d/3d_utils.h:39-42 stops at radius 1;
+ * SURVEY.md section 8(f)-4).  The same direct-tap protocol as test_cpu (src/3d/main.cu:33-68) widened to a
+ * 5 x 5 x 5 window, on the product's layout for these shapes: (h+4) x (m+4) x (n+8), interior origin [2][2][4];
+ * 125 weights [(dh+2)*25 + (dr+2)*5 + dc+2], summed left to right.  Parity of this function is pinned by
+ * tests/test_r2.py against scipy.ndimage.correlate, not by any reference vector ("unpinned by the reference"). */
+void oracle_step_3d_r2(const double *in, double *out, const double *param, i64 heights, i64 rows, i64 cols) {
+#pragma omp parallel for schedule(static)
+    for (i64 h = 2; h < heights - 2; h++) {
+        for (i64 r = 2; r < rows - 2; r++) {
+            for (i64 c = 4; c < cols - 4; c++) {
+                double acc = 0.0;
+                int first = 1;
+                for (int dh = -2; dh <= 2; dh++)
+                    for (int dr = -2; dr <= 2; dr++)
+                        for (int dc = -2; dc <= 2; dc++) {
+                            double p = param[(dh + 2) * 25 + (dr + 2) * 5 + (dc + 2)] *
+                                       in[((h + dh) * rows + (r + dr)) * cols + (c + dc)];
+                            if (first) { acc = p; first = 0; } else acc = acc + p;
+                        }
+                out[(h * rows + r) * cols + c] = acc;
+            }
+        }
+    }
+}
+
+static void step3r2(const double *a, double *b, const double *p, const i64 *d) {
+    oracle_step_3d_r2(a, b, p, d[0], d[1], d[2]);
+}
+
+/* the S2 / S3 buffer semantics of the gpu_* operators (src/3d/gpu_box.cu:190-223) on that layout */
+int oracle_run_3d_r2(const double *in, double *out, const double *param, int times, i64 h, i64 m, i64 n) {
+    i64 dims[3] = {h + 4, m + 4, n + 8};
+    i64 total = dims[0] * dims[1] * dims[2];
+    return run_generic(in, out, total, total, times, step3r2, param, dims);
+}

@@ -44,7 +44,8 @@ def test_shape_names_of_each_driver():
 
 @pytest.mark.parametrize("exe,args,count", [("lorastencil_1d", ["1d2r", "1024", "2"], 9),
                                             ("lorastencil_2d", ["box2d3r", "64", "64", "2"], 49),
-                                            ("lorastencil_3d", ["box3d1r", "8", "8", "64", "2"], 27)])
+                                            ("lorastencil_3d", ["box3d1r", "8", "8", "64", "2"], 27),
+                                            ("lorastencil_3d", ["star3d2r", "8", "8", "64", "2"], 125)])
 def test_weight_file_errors(tmp_path, exe, args, count):
     """--weights FILE is validated before any CUDA call: a missing file, a short table and a non-number each give
     'Invalid argument: ...' on stderr and return 1, like the reference's own argument errors (src/2d/main.cu:128-131)."""
@@ -68,7 +69,8 @@ def test_weight_file_errors(tmp_path, exe, args, count):
 @pytest.mark.parametrize("exe,args,count", [("lorastencil_1d", ["1d1r", "5000", "3"], 9),
                                             ("lorastencil_2d", ["star2d1r", "96", "130", "3"], 49),
                                             ("lorastencil_2d", ["box2d3r", "64", "64", "2"], 49),
-                                            ("lorastencil_3d", ["star3d1r", "9", "16", "64", "3"], 27)])
+                                            ("lorastencil_3d", ["star3d1r", "9", "16", "64", "3"], 27),
+                                            ("lorastencil_3d", ["box3d2r", "9", "16", "64", "3"], 125)])
 def test_weight_file_is_honoured(tmp_path, exe, args, count):
     """A caller's table (dense, asymmetric, no zero anywhere) from a file: the --check protocol of the reference
     (one direct-tap CPU step with EVERY weight against one launch, src/2d/main.cu:282-328) finds no mismatch."""
@@ -79,4 +81,16 @@ def test_weight_file_is_honoured(tmp_path, exe, args, count):
     r = run(exe, *args, "--weights", str(f), "--check")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert f"INFO: weights = {f} ({count} values, every one honoured)" in r.stdout
+    assert "Correct!" in r.stdout and "naive = " not in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,info", [("box3d2r", "box_3d2r"), ("star3d2r", "star_3d2r")])
+def test_radius2_shapes_pass_the_check_protocol(shape, info):
+    """The radius-2 extensions through the same driver: INFO line, banner, one direct-tap CPU step (5x5x5 window)
+    against one launch."""
+    r = run("lorastencil_3d", shape, "12", "10", "130", "4", "--check")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f"INFO: shape = {info}, h = 12, m = 10, n = 130, times = 4" in r.stdout
+    assert f"LoRAStencil(3D {info}): " in r.stdout and "GStencil/s = " in r.stdout
     assert "Correct!" in r.stdout and "naive = " not in r.stdout

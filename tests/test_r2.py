@@ -1,0 +1,150 @@
+"""Radius-2 3-D shapes box3d2r / star3d2r (the reference's shape list ends at radius 1,
+src/3d/3d_utils.h:39-42, so there is no reference vector for them).
+
+CPU: the checker (oracle.step_r2 / run_r2: the test_cpu protocol of src/3d/main.cu:33-68 on a 5x5x5 window, with the
+S2 / S3 buffer semantics of src/3d/gpu_box.cu:190-223) is pinned against an independent implementation,
+scipy.ndimage.correlate; the host decomposition picks its form by structure and reports the taps it applies.
+GPU: the drop-in operators, the plan API and torch.ops against the checker."""
+import numpy as np
+import pytest
+
+import lorastencil_b200 as ls
+import oracle
+from lorastencil_b200 import _lib, ops
+from lorastencil_b200.plan import effective_weights, reference_table
+
+RTOL = 1e-12
+INNER = (slice(2, -2), slice(2, -2), slice(4, -4))
+
+
+def tables(rng):
+    """(name, shape, table, expected form)"""
+    star = np.zeros((5, 5, 5))
+    for ax in range(3):
+        for d in (-2, -1, 1, 2):
+            idx = [2, 2, 2]
+            idx[ax] += d
+            star[tuple(idx)] = rng.uniform(-1, 1)
+    star[2, 2, 2] = rng.uniform(-1, 1)
+    hsep = np.einsum("i,jk->ijk", rng.uniform(-1, 1, 5), rng.uniform(-1, 1, (5, 5)))
+    dense = rng.uniform(-1, 1, (5, 5, 5))
+    return [("default box", "box3d2r", oracle.reference_params_r2("box3d2r"), "hsep5"),
+            ("default star", "star3d2r", oracle.reference_params_r2("star3d2r"), "star13"),
+            ("general star", "star3d2r", star.reshape(-1), "star13"),
+            ("rank 1 along h", "box3d2r", hsep.reshape(-1), "hsep5"),
+            ("dense", "box3d2r", dense.reshape(-1), "direct125"),
+            ("dense through the star entry point", "star3d2r", dense.reshape(-1), "direct125")]
+
+
+@pytest.mark.parametrize("dims", [(6, 7, 9), (1, 1, 1), (3, 2, 64)])
+def test_checker_equals_scipy_correlation(dims):
+    from scipy import ndimage
+    rng = np.random.default_rng(1)
+    for _, shape, w, _ in tables(rng):
+        wi = np.round(8 * w)  # integers: every sum is exact, so the comparison can be ==
+        a = rng.integers(0, 100, oracle.padded_shape_r2(dims)).astype(np.float64)
+        out = oracle.step_r2(a, wi)
+        ref = ndimage.correlate(a, wi.reshape(5, 5, 5), mode="constant")
+        assert np.array_equal(out[INNER], ref[INNER])
+        ring = out.copy()
+        ring[INNER] = 0
+        assert not ring.any()  # interior only
+    # S2 / S3: launch i reads buf[i % 2]; buffer 1 starts as zeros; the result is the whole padded buf[times % 2]
+    w = oracle.reference_params_r2("star3d2r")
+    a = rng.integers(0, 100, oracle.padded_shape_r2(dims)).astype(np.float64)
+    b = [a.copy(), np.zeros_like(a)]
+    for i in range(4):
+        assert np.array_equal(oracle.run_r2(a, w, i), b[i % 2])
+        b[(i + 1) % 2][INNER] = oracle.step_r2(b[i % 2], w)[INNER]
+
+
+def test_default_tables_match_the_checker_restatement():
+    for shape in oracle.R2_SHAPES:
+        assert np.array_equal(reference_table(shape), oracle.reference_params_r2(shape))
+        assert _lib.nparams(shape) == 125 and _lib.halo_of(shape) == oracle.HALO_R2
+
+
+def test_every_weight_is_honoured_in_both_modes():
+    rng = np.random.default_rng(2)
+    for name, shape, w, form in tables(rng):
+        for mode in (ls.WEIGHTS_REFERENCE, ls.WEIGHTS_GENERAL):
+            eff = effective_weights(shape, mode, w)
+            assert eff.shape == (125,)
+            assert np.abs(eff - w).max() <= 64 * 2.3e-16 * np.abs(w).max(), name
+            if form != "hsep5":
+                assert np.array_equal(eff, w), name  # only the rank-1 form re-multiplies its factors
+
+
+def test_reference_only_entry_points_refuse_the_new_shapes():
+    """Slabs (and everything else that asks shape_dim) do not know these shapes: an error, not a wrong layout."""
+    from ctypes import POINTER, byref, c_double, c_longlong, c_void_p
+    L = _lib.lib()
+    out = c_void_p()
+    d = (c_longlong * 3)(8, 8, 8)
+    rc = L.lora_slabset_create(byref(out), _lib.SHAPE_IDS["box3d2r"], 0, None, d, 2, None)
+    assert rc == 1 and not out.value and b"unknown shape" in L.lora_last_error()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(12, 10, 64), (1, 1, 1), (5, 9, 31), (40, 33, 130), (70, 6, 300)])
+def test_drop_in_operators_match_the_checker(dims):
+    rng = np.random.default_rng(7)
+    ops.set_verbose(False)
+    for name, shape, w, _ in tables(rng):
+        a = rng.uniform(-1, 1, oracle.padded_shape_r2(dims))
+        for times in (0, 1, 2, 5):
+            out = np.full_like(a, -7.0)
+            ops.BY_SHAPE[shape](a, out, w, times, *dims)
+            ref = oracle.run_r2(a, w, times)
+            assert np.abs(out - ref).max() <= RTOL * max(np.abs(ref).max(), 1e-300), (name, dims, times)
+
+
+@pytest.mark.gpu
+def test_integer_data_is_exact_for_the_first_launches():
+    """Small-integer data and the default tables: every sum is exact in FP64 whatever its order (as for the reference's
+    own shapes) -- bit-identical to the checker."""
+    dims = (20, 16, 128)
+    ops.set_verbose(False)
+    for shape, upto in (("box3d2r", 4), ("star3d2r", 8)):
+        a = np.random.default_rng(3).integers(0, 100, oracle.padded_shape_r2(dims)).astype(np.float64)
+        w = oracle.reference_params_r2(shape)
+        for times in range(1, upto + 1):
+            out = np.zeros_like(a)
+            ops.BY_SHAPE[shape](a, out, w, times, *dims)
+            assert np.array_equal(out, oracle.run_r2(a, w, times)), (shape, times)
+
+
+@pytest.mark.gpu
+def test_plan_api_ranges_boundaries_and_torch_op():
+    import torch
+    import lorastencil_b200.torch_ops  # noqa: F401
+    rng = np.random.default_rng(11)
+    dims = (30, 20, 66)
+    a = rng.uniform(-1, 1, oracle.padded_shape_r2(dims))
+    for shape in oracle.R2_SHAPES:
+        w = oracle.reference_params_r2(shape)
+        plan = ls.Plan(shape, dims)
+        assert plan.padded_shape == a.shape and plan.temporal_block == 1
+        assert plan.describe.startswith("3d radius-2")
+        # one launch cut into plane ranges == one launch over everything
+        src, whole, parts = torch.from_numpy(a).cuda(), plan.new_buffer(), plan.new_buffer()
+        plan.step(src, whole)
+        for lo, hi in ((0, 7), (7, 8), (8, 30)):
+            plan.step(src, parts, lo, hi)
+        torch.cuda.synchronize()
+        assert torch.equal(whole, parts)
+        assert np.abs(whole.cpu().numpy() - oracle.step_r2(a, w)).max() <= RTOL * np.abs(a).max() * np.abs(w).sum()
+        # fused sweeps do not exist for these shapes
+        plan.temporal_block = 2
+        assert plan.temporal_block == 1
+        # periodic boundary on the radius-2 layout
+        plan.boundary = "periodic"
+        got = plan.run(torch.from_numpy(a).cuda(), plan.new_buffer(), 3).cpu().numpy()
+        cur = np.pad(a[INNER], [(2, 2), (2, 2), (4, 4)], mode="wrap")
+        for _ in range(3):
+            cur = np.pad(oracle.step_r2(cur, w)[INNER], [(2, 2), (2, 2), (4, 4)], mode="wrap")
+        assert np.abs(got - cur).max() <= RTOL * np.abs(cur).max()
+        # torch op, reference halo semantics
+        y = torch.ops.lorastencil.stencil3d(torch.from_numpy(a).cuda(), shape, 4)
+        ref = oracle.run_r2(a, w, 4)
+        assert np.abs(y.cpu().numpy() - ref).max() <= RTOL * np.abs(ref).max()
