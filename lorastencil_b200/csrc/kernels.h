@@ -281,9 +281,7 @@ struct WeightsR2 {
     double q[25];   // HSEP5: in-plane table, w[dh][dr][dc] = a[dh + 2] * q[(dr + 2) * 5 + dc + 2]
     double a[5];
 };
-cudaError_t launch_3d_r2(int form, const Geom3DR2 &g, const WeightsR2 &w, cudaStream_t s);
-int r2_rows_per_cta();
-int r2_cols_per_cta();
+cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count, cudaStream_t s);  // picks planes_per_chunk
 
 // periodic halo ring (boundary.cu): one axis of an array seen as [outer][len + 2 halo][inner]
 cudaError_t launch_wrap_axis(double *buf, long long outer, long long len, int halo, long long inner, int sm_count,

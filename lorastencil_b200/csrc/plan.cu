@@ -523,16 +523,8 @@ static int step_unfused(lora_plan_t *p, const double *src, double *dst, long lon
         g.n = (int)p->dims[2];
         g.lo = lo;
         g.hi = hi;
-        // plane chunks: every chunk re-reads 4 planes of warm-up, so as long as possible -- but at least ~4 CTAs per SM
-        // in the grid (256 threads each), and never more than the z extent of a grid allows
-        const long long per_plane = (long long)((g.n + r2_cols_per_cta() - 1) / r2_cols_per_cta()) *
-                                    ((g.m + r2_rows_per_cta() - 1) / r2_rows_per_cta());
-        long long want = (4LL * p->sm_count + per_plane - 1) / per_plane;  // chunks wanted
-        want = std::max(1LL, std::min(want, (hi - lo + 7) / 8));          // ... of at least 8 planes each
-        long long L = (hi - lo + want - 1) / want;
-        L = std::max(L, (hi - lo + 65534) / 65535);
-        g.planes_per_chunk = (int)std::min<long long>(L, 0x7fffffff);
-        e = launch_3d_r2(p->form, g, p->wr2, st);
+        g.planes_per_chunk = 0;  // chosen by the launcher
+        e = launch_3d_r2(p->form, g, p->wr2, p->sm_count, st);
     } else if (p->odd_cols) {
         SegCut sc;
         if (int rc = cut_segments(lo, hi, dst, ex, mirror_base, sc)) return rc;

@@ -17,6 +17,8 @@
 //   DIRECT125  125 FMA: five in-plane sums, one per accumulator
 // In-plane neighbours come through L1 (25 loads per cell and plane, 5 x 5 threads share them); no shared memory, no
 // barriers, so rows / columns outside the grid simply retire.  A chunk of planes costs 4 extra plane reads of warm-up.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "../../include/lorastencil.h"
@@ -25,10 +27,13 @@ namespace lora {
 
 namespace {
 
-constexpr int kR2Cols = 128;  // threads along the columns (one cell each)
+constexpr int kR2Cols = 128;  // threads along the columns
 constexpr int kR2Rows = 2;    // rows per CTA
 
-template <int FORM>
+// One cell per thread.  UNROLL = 1: plain loads, one plane per trip (variant 0).  UNROLL = 4: read-only loads
+// (LDG.CONSTANT), no aliasing between the two buffers, several planes per trip so that the loads of the next planes may
+// be issued ahead of this plane's store (variant 1; the 125-tap form stays at one plane per trip: two need 249 registers).
+template <int FORM, int UNROLL>
 __global__ void __launch_bounds__(kR2Cols * kR2Rows)
 k_stencil3d_r2(const __grid_constant__ Geom3DR2 g, const __grid_constant__ WeightsR2 w) {
     const int c = blockIdx.x * kR2Cols + threadIdx.x;
@@ -38,21 +43,23 @@ k_stencil3d_r2(const __grid_constant__ Geom3DR2 g, const __grid_constant__ Weigh
     const long long q_hi = min(q_lo + (long long)g.planes_per_chunk, g.hi);       // one past the last
     // cell (plane p, r, c) of the interior sits at padded (p + 2, r + 2, c + 4)
     const long long cell = (long long)(r + 2) * g.row_pitch + 4 + c;
-    const double *in = g.in + cell;
-    double *out = g.out + cell;
+    const double *__restrict__ in = g.in + cell;
+    double *__restrict__ out = g.out + cell;
+    auto ld = [](const double *q) { return UNROLL > 1 ? __ldg(q) : *q; };
 
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // acc[k]: output plane p - 2 + k while plane p is being pushed
+#pragma unroll(FORM == LORA_FORM_DIRECT125 ? 1 : UNROLL)
     for (long long p = q_lo - 2; p <= q_hi + 1; p++) {
         const double *pl = in + (p + 2) * g.plane_pitch;
         if (FORM == LORA_FORM_STAR13) {
-            const double ctr = pl[0];
+            const double ctr = ld(pl);
             double t = w.w[62] * ctr;  // (0, 0, 0)
 #pragma unroll
             for (int d = 1; d <= 2; d++) {
-                t = fma(w.w[62 - d], pl[-d], t);                      // (0, 0, -d)
-                t = fma(w.w[62 + d], pl[d], t);                       // (0, 0, +d)
-                t = fma(w.w[62 - 5 * d], pl[-d * g.row_pitch], t);    // (0, -d, 0)
-                t = fma(w.w[62 + 5 * d], pl[d * g.row_pitch], t);     // (0, +d, 0)
+                t = fma(w.w[62 - d], ld(pl - d), t);                      // (0, 0, -d)
+                t = fma(w.w[62 + d], ld(pl + d), t);                      // (0, 0, +d)
+                t = fma(w.w[62 - 5 * d], ld(pl - d * g.row_pitch), t);    // (0, -d, 0)
+                t = fma(w.w[62 + 5 * d], ld(pl + d * g.row_pitch), t);    // (0, +d, 0)
             }
             acc[2] += t;
             // plane p is plane q + dh of output q = p - dh: tap (dh, 0, 0) = w[62 + 25 dh], accumulator k = 2 - dh
@@ -65,7 +72,7 @@ k_stencil3d_r2(const __grid_constant__ Geom3DR2 g, const __grid_constant__ Weigh
 #pragma unroll
             for (int dr = -2; dr <= 2; dr++)
 #pragma unroll
-                for (int dc = -2; dc <= 2; dc++) v[(dr + 2) * 5 + dc + 2] = pl[dr * g.row_pitch + dc];
+                for (int dc = -2; dc <= 2; dc++) v[(dr + 2) * 5 + dc + 2] = ld(pl + dr * g.row_pitch + dc);
             if (FORM == LORA_FORM_HSEP5) {
                 double t = w.q[0] * v[0];
 #pragma unroll
@@ -92,25 +99,153 @@ k_stencil3d_r2(const __grid_constant__ Geom3DR2 g, const __grid_constant__ Weigh
     }
 }
 
-}  // namespace
+// Variant 2: TWO adjacent cells per thread (even column counts, 16-byte aligned buffers).  A row of the neighbourhood is
+// columns c-2 .. c+3 = three aligned 128-bit loads for two cells instead of five 64-bit loads per cell; the in-plane
+// sums of the one-cell kernel are bound by exactly that -- L1 wavefronts (25 unaligned 256-byte warp loads per cell
+// and plane) -- and every weight fetched feeds two FMAs.
+template <int FORM>
+__global__ void __launch_bounds__(kR2Cols * kR2Rows)
+k_stencil3d_r2_pair(const __grid_constant__ Geom3DR2 g, const __grid_constant__ WeightsR2 w) {
+    const int c = 2 * (blockIdx.x * kR2Cols + threadIdx.x);  // cells c and c + 1; n is even, so both or neither exist
+    const int r = blockIdx.y * kR2Rows + threadIdx.y;
+    if (c >= g.n || r >= g.m) return;
+    const long long q_lo = g.lo + (long long)blockIdx.z * g.planes_per_chunk;
+    const long long q_hi = min(q_lo + (long long)g.planes_per_chunk, g.hi);
+    const long long cell = (long long)(r + 2) * g.row_pitch + 4 + c;  // padded column c + 4 is even: 16-byte aligned
+    const double *__restrict__ in = g.in + cell;
+    double *__restrict__ out = g.out + cell;
+    auto ld2 = [](const double *q) { return __ldg(reinterpret_cast<const double2 *>(q)); };
 
-cudaError_t launch_3d_r2(int form, const Geom3DR2 &g, const WeightsR2 &w, cudaStream_t s) {
-    if (g.hi <= g.lo) return cudaSuccess;
-    const long long chunks = (g.hi - g.lo + g.planes_per_chunk - 1) / g.planes_per_chunk;
-    const long long by = (g.m + kR2Rows - 1) / kR2Rows;
-    if (chunks > 65535 || by > 65535) return cudaErrorInvalidConfiguration;
-    const dim3 grid((unsigned)((g.n + kR2Cols - 1) / kR2Cols), (unsigned)by, (unsigned)chunks);
-    const dim3 block(kR2Cols, kR2Rows);
-    switch (form) {
-        case LORA_FORM_STAR13: k_stencil3d_r2<LORA_FORM_STAR13><<<grid, block, 0, s>>>(g, w); break;
-        case LORA_FORM_HSEP5: k_stencil3d_r2<LORA_FORM_HSEP5><<<grid, block, 0, s>>>(g, w); break;
-        case LORA_FORM_DIRECT125: k_stencil3d_r2<LORA_FORM_DIRECT125><<<grid, block, 0, s>>>(g, w); break;
-        default: return cudaErrorInvalidValue;
+    double acc0[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, acc1[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // cell c / cell c + 1
+    for (long long p = q_lo - 2; p <= q_hi + 1; p++) {
+        const double *pl = in + (p + 2) * g.plane_pitch;
+        if (FORM == LORA_FORM_STAR13) {
+            const double2 a = ld2(pl - 2), b = ld2(pl), d = ld2(pl + 2);  // columns (c-2, c-1), (c, c+1), (c+2, c+3)
+            double t0 = w.w[62] * b.x, t1 = w.w[62] * b.y;
+            t0 = fma(w.w[61], a.y, t0);  // (0, 0, -1)
+            t1 = fma(w.w[61], b.x, t1);
+            t0 = fma(w.w[63], b.y, t0);  // (0, 0, +1)
+            t1 = fma(w.w[63], d.x, t1);
+            t0 = fma(w.w[60], a.x, t0);  // (0, 0, -2)
+            t1 = fma(w.w[60], a.y, t1);
+            t0 = fma(w.w[64], d.x, t0);  // (0, 0, +2)
+            t1 = fma(w.w[64], d.y, t1);
+#pragma unroll
+            for (int k = 1; k <= 2; k++) {
+                const double2 up = ld2(pl - k * g.row_pitch), dn = ld2(pl + k * g.row_pitch);
+                t0 = fma(w.w[62 - 5 * k], up.x, t0);  // (0, -k, 0)
+                t1 = fma(w.w[62 - 5 * k], up.y, t1);
+                t0 = fma(w.w[62 + 5 * k], dn.x, t0);  // (0, +k, 0)
+                t1 = fma(w.w[62 + 5 * k], dn.y, t1);
+            }
+            acc0[2] += t0;
+            acc1[2] += t1;
+            acc0[0] = fma(w.w[62 + 50], b.x, acc0[0]);  // tap (dh, 0, 0) into accumulator k = 2 - dh
+            acc1[0] = fma(w.w[62 + 50], b.y, acc1[0]);
+            acc0[1] = fma(w.w[62 + 25], b.x, acc0[1]);
+            acc1[1] = fma(w.w[62 + 25], b.y, acc1[1]);
+            acc0[3] = fma(w.w[62 - 25], b.x, acc0[3]);
+            acc1[3] = fma(w.w[62 - 25], b.y, acc1[3]);
+            acc0[4] = fma(w.w[62 - 50], b.x, acc0[4]);
+            acc1[4] = fma(w.w[62 - 50], b.y, acc1[4]);
+        } else {
+            double v[5][6];  // v[dr + 2][j] = column c - 2 + j: cell c reads j = dc + 2, cell c + 1 reads j = dc + 3
+#pragma unroll
+            for (int dr = -2; dr <= 2; dr++) {
+                const double *row = pl + dr * g.row_pitch;
+                const double2 a = ld2(row - 2), b = ld2(row), d = ld2(row + 2);
+                v[dr + 2][0] = a.x, v[dr + 2][1] = a.y, v[dr + 2][2] = b.x;
+                v[dr + 2][3] = b.y, v[dr + 2][4] = d.x, v[dr + 2][5] = d.y;
+            }
+            if (FORM == LORA_FORM_HSEP5) {
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 5; i++)
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        t0 = fma(w.q[i * 5 + j], v[i][j], t0);
+                        t1 = fma(w.q[i * 5 + j], v[i][j + 1], t1);
+                    }
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    acc0[k] = fma(w.a[4 - k], t0, acc0[k]);
+                    acc1[k] = fma(w.a[4 - k], t1, acc1[k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const double *wk = w.w + (4 - k) * 25;
+                    double t0 = acc0[k], t1 = acc1[k];
+#pragma unroll
+                    for (int i = 0; i < 5; i++)
+#pragma unroll
+                        for (int j = 0; j < 5; j++) {
+                            t0 = fma(wk[i * 5 + j], v[i][j], t0);
+                            t1 = fma(wk[i * 5 + j], v[i][j + 1], t1);
+                        }
+                    acc0[k] = t0;
+                    acc1[k] = t1;
+                }
+            }
+        }
+        if (p - 2 >= q_lo) st_global_v2(out + p * g.plane_pitch, acc0[0], acc1[0]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc0[k] = acc0[k + 1], acc1[k] = acc1[k + 1];
+        acc0[4] = 0.0;
+        acc1[4] = 0.0;
     }
+}
+
+// which kernel: 0 = one cell per thread, plain loads (the first version); 1 = read-only loads, four planes per trip;
+// 2 = two cells per thread (needs an even column count and 16-byte aligned buffers, else 1).  LORA_R2_VARIANT overrides
+// the default (tuning / the parity tests run every variant).
+constexpr int kDefaultVariant = 0;
+
+template <int FORM>
+cudaError_t launch_form(int variant, dim3 grid, dim3 block, const Geom3DR2 &g, const WeightsR2 &w, cudaStream_t s) {
+    if (variant == 2)
+        k_stencil3d_r2_pair<FORM><<<grid, block, 0, s>>>(g, w);
+    else if (variant == 1)
+        k_stencil3d_r2<FORM, 4><<<grid, block, 0, s>>>(g, w);
+    else
+        k_stencil3d_r2<FORM, 1><<<grid, block, 0, s>>>(g, w);
     return cudaGetLastError();
 }
 
-int r2_rows_per_cta() { return kR2Rows; }
-int r2_cols_per_cta() { return kR2Cols; }
+}  // namespace
+
+// g.planes_per_chunk is chosen here: every chunk of planes re-reads 4 planes of warm-up, so chunks as long as possible
+// -- but enough of them that the grid is many waves deep (about 32 CTAs of 256 threads per SM: 5 to 8 are resident, and
+// with one chunk a 512^3 grid is 1.4 waves, a third of the GPU idle in the second), at least 16 planes each, and never
+// more chunks than the z extent of a grid allows
+cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count, cudaStream_t s) {
+    const long long planes = g.hi - g.lo;
+    if (planes <= 0) return cudaSuccess;
+    int variant = kDefaultVariant;
+    if (const char *e = getenv("LORA_R2_VARIANT")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 2) variant = v;
+    }
+    const bool pair_ok = g.n % 2 == 0 && reinterpret_cast<uintptr_t>(g.in) % 16 == 0 && reinterpret_cast<uintptr_t>(g.out) % 16 == 0;
+    if (variant == 2 && !pair_ok) variant = 1;
+    const int cols_per_cta = kR2Cols * (variant == 2 ? 2 : 1);
+    const long long bx = (g.n + cols_per_cta - 1) / cols_per_cta, by = (g.m + kR2Rows - 1) / kR2Rows;
+    if (by > 65535) return cudaErrorInvalidConfiguration;
+    long long want = (32LL * sm_count + bx * by - 1) / (bx * by);  // chunks wanted
+    want = want < 1 ? 1 : want;
+    if (want > (planes + 15) / 16) want = (planes + 15) / 16;
+    long long L = (planes + want - 1) / want;
+    if (L < (planes + 65534) / 65535) L = (planes + 65534) / 65535;
+    g.planes_per_chunk = (int)(L > 0x7fffffffLL ? 0x7fffffffLL : L);
+    const long long chunks = (planes + g.planes_per_chunk - 1) / g.planes_per_chunk;
+    const dim3 grid((unsigned)bx, (unsigned)by, (unsigned)chunks);
+    const dim3 block(kR2Cols, kR2Rows);
+    switch (form) {
+        case LORA_FORM_STAR13: return launch_form<LORA_FORM_STAR13>(variant, grid, block, g, w, s);
+        case LORA_FORM_HSEP5: return launch_form<LORA_FORM_HSEP5>(variant, grid, block, g, w, s);
+        case LORA_FORM_DIRECT125: return launch_form<LORA_FORM_DIRECT125>(variant, grid, block, g, w, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 }  // namespace lora

@@ -85,9 +85,14 @@ def test_reference_only_entry_points_refuse_the_new_shapes():
     assert rc == 1 and not out.value and b"unknown shape" in L.lora_last_error()
 
 
+VARIANTS = ["0", "1", "2"]  # csrc/stencil3d_r2.cu: one cell per thread / + read-only loads, 4 planes per trip / two cells
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("dims", [(12, 10, 64), (1, 1, 1), (5, 9, 31), (40, 33, 130), (70, 6, 300)])
-def test_drop_in_operators_match_the_checker(dims):
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("dims", [(12, 10, 64), (1, 1, 1), (5, 9, 31), (40, 33, 130), (70, 6, 300), (100, 4, 2)])
+def test_drop_in_operators_match_the_checker(dims, variant, monkeypatch):
+    monkeypatch.setenv("LORA_R2_VARIANT", variant)  # read at every launch
     rng = np.random.default_rng(7)
     ops.set_verbose(False)
     for name, shape, w, _ in tables(rng):
@@ -100,9 +105,11 @@ def test_drop_in_operators_match_the_checker(dims):
 
 
 @pytest.mark.gpu
-def test_integer_data_is_exact_for_the_first_launches():
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_integer_data_is_exact_for_the_first_launches(variant, monkeypatch):
     """Small-integer data and the default tables: every sum is exact in FP64 whatever its order (as for the reference's
     own shapes) -- bit-identical to the checker."""
+    monkeypatch.setenv("LORA_R2_VARIANT", variant)
     dims = (20, 16, 128)
     ops.set_verbose(False)
     for shape, upto in (("box3d2r", 4), ("star3d2r", 8)):
@@ -115,8 +122,13 @@ def test_integer_data_is_exact_for_the_first_launches():
 
 
 @pytest.mark.gpu
-def test_plan_api_ranges_boundaries_and_torch_op():
+@pytest.mark.parametrize("variant", VARIANTS + [None])
+def test_plan_api_ranges_boundaries_and_torch_op(variant, monkeypatch):
     import torch
+    if variant is None:
+        monkeypatch.delenv("LORA_R2_VARIANT", raising=False)  # the default kernel
+    else:
+        monkeypatch.setenv("LORA_R2_VARIANT", variant)
     import lorastencil_b200.torch_ops  # noqa: F401
     rng = np.random.default_rng(11)
     dims = (30, 20, 66)
