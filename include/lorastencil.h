@@ -316,7 +316,8 @@ enum {
     LORA_FORM_RANK3 = 10,     /* 2-D: sum of 3 such terms: 42 taps */
     LORA_FORM_STAR13 = 11,    /* 3-D radius 2: 13 taps */
     LORA_FORM_HSEP5 = 12,     /* 3-D radius 2: a(h) (x) Q(m, n), rank 1 along the plane axis, any in-plane 5 x 5 table: 30 taps */
-    LORA_FORM_DIRECT125 = 13  /* 3-D radius 2: all 125 taps */
+    LORA_FORM_DIRECT125 = 13, /* 3-D radius 2: all 125 taps */
+    LORA_FORM_SEP5 = 14       /* 3-D radius 2: a(h) (x) b(m) (x) c(n), rank 1 along every axis: 15 taps */
 };
 
 typedef struct {

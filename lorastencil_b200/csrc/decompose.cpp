@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace lora {
@@ -544,6 +545,10 @@ bool decompose_3d(int shape, int mode, const double *params, Decomp3D &d) {
 // 3-D radius 2 (no reference counterpart: src/3d/3d_utils.h:39-42 stops at radius 1).  Every weight is honoured; the
 // form is what the STRUCTURE of the table allows: 13-point star, rank 1 along the plane axis, or all 125 taps.
 // ---------------------------------------------------------------------------------------------
+// whether a fully separable table takes the SEP5 kernel (k_stencil3d_r2_sep) or stays with HSEP5: on -- 195 against 179
+// GStencil/s for the default box table at 512^3 (profiles/r2_extensions_sep5.json); LORA_R2_SEP5=0|1 overrides
+constexpr bool kDefaultSep5 = true;
+
 bool decompose_3d_r2(int shape, const double *params, Decomp3DR2 &d) {
     if (!shape_is_r2(shape)) return false;
     d = Decomp3DR2();
@@ -607,6 +612,48 @@ bool decompose_3d_r2(int shape, const double *params, Decomp3DR2 &d) {
             d.recon_err = best_err;
             d.macs = 30;
             d.desc = "3d radius-2 a(h) x Q(m,n): rank 1 along the plane axis, 25 + 5 taps";
+            // ... and Q itself rank 1, b (x) c through its largest entry (same scaling rule)?  Then 5 + 5 + 5 taps.
+            bool sep5 = kDefaultSep5;
+            if (const char *e = getenv("LORA_R2_SEP5")) sep5 = atoi(e) != 0;
+            int qb = 0;
+            for (int i = 1; i < 25; i++)
+                if (std::fabs(q[i]) > std::fabs(q[qb])) qb = i;
+            if (sep5 && std::fabs(q[qb]) > 0) {
+                const int r0 = qb / 5, c0 = qb % 5;
+                double smin2 = std::fabs(q[qb]);
+                for (int i = 0; i < 5; i++) {
+                    const double v = std::fabs(q[i * 5 + c0]);
+                    if (v > 0 && v < smin2) smin2 = v;
+                }
+                const double cand2[3] = {smin2, q[qb], 1.0};
+                double err2 = -1, b[5], c[5];
+                for (double sc : cand2) {
+                    double tb[5], tc[5], err = 0;
+                    for (int i = 0; i < 5; i++) tb[i] = q[i * 5 + c0] / sc;
+                    for (int j = 0; j < 5; j++) tc[j] = q[r0 * 5 + j] * sc / q[qb];
+                    for (int h = 0; h < 5; h++)
+                        for (int i = 0; i < 5; i++)
+                            for (int j = 0; j < 5; j++)
+                                err = std::max(err, std::fabs(a[h] * (tb[i] * tc[j]) - params[h * 25 + i * 5 + j]));
+                    if (err2 < 0 || err < err2) {
+                        err2 = err;
+                        std::memcpy(b, tb, sizeof b);
+                        std::memcpy(c, tc, sizeof c);
+                    }
+                    if (err == 0) break;
+                }
+                if (err2 <= tol) {
+                    d.form = LORA_FORM_SEP5;
+                    std::memcpy(d.b, b, sizeof b);
+                    std::memcpy(d.c, c, sizeof c);
+                    for (int h = 0; h < 5; h++)
+                        for (int i = 0; i < 5; i++)
+                            for (int j = 0; j < 5; j++) d.w[h * 25 + i * 5 + j] = d.a[h] * (d.b[i] * d.c[j]);
+                    d.recon_err = err2;
+                    d.macs = 15;
+                    d.desc = "3d radius-2 separable a(h) x b(m) x c(n): rank 1 along every axis, 5 + 5 + 5 taps";
+                }
+            }
             return true;
         }
     }

@@ -50,6 +50,7 @@ struct Decomp3DR2 {
     double w[125] = {};   // effective taps [(dh+2)*25 + (dr+2)*5 + dc+2] (== the table: every weight is honoured)
     double q[25] = {};    // HSEP5: w[dh][dr][dc] = a[dh+2] * q[(dr+2)*5 + dc+2]
     double a[5] = {};
+    double b[5] = {}, c[5] = {};  // SEP5: q = b (x) c
     double recon_err = 0.0;
     int macs = 125;
     std::string desc;
@@ -69,6 +70,6 @@ void reference_table(int shape, double *out);
 bool decompose_1d(int shape, int mode, const double *params, Decomp1D &d);
 bool decompose_2d(int shape, int mode, const double *params, Decomp2D &d);
 bool decompose_3d(int shape, int mode, const double *params, Decomp3D &d);
-bool decompose_3d_r2(int shape, const double *params, Decomp3DR2 &d);
+bool decompose_3d_r2(int shape, const double *params, Decomp3DR2 &d);  // LORA_R2_SEP5=0|1 overrides the SEP5 default
 
 }  // namespace lora

@@ -280,6 +280,7 @@ struct WeightsR2 {
     double w[125];  // [(dh + 2) * 25 + (dr + 2) * 5 + dc + 2]: every form's effective taps (STAR13 / DIRECT125 read these)
     double q[25];   // HSEP5: in-plane table, w[dh][dr][dc] = a[dh + 2] * q[(dr + 2) * 5 + dc + 2]
     double a[5];
+    double b[5], c[5];  // SEP5: q[(dr + 2) * 5 + dc + 2] = b[dr + 2] * c[dc + 2]
 };
 cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count, cudaStream_t s);  // picks planes_per_chunk
 

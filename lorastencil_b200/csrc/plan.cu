@@ -203,6 +203,8 @@ extern "C" int lora_plan_create(lora_plan_t **out, int shape, int mode, const do
         std::memcpy(p->wr2.w, d.w, sizeof d.w);
         std::memcpy(p->wr2.q, d.q, sizeof d.q);
         std::memcpy(p->wr2.a, d.a, sizeof d.a);
+        std::memcpy(p->wr2.b, d.b, sizeof d.b);
+        std::memcpy(p->wr2.c, d.c, sizeof d.c);
         p->form = d.form;
         p->desc = d.desc;
     } else if (dim == 1) {

@@ -15,8 +15,11 @@
 //   HSEP5    30 FMA: w[dh][dr][dc] = a[dh] * Q[dr][dc] (rank 1 along the plane axis, ANY in-plane 5 x 5 table Q):
 //            one in-plane sum T = Q . plane, then a[dh] * T into the five accumulators
 //   DIRECT125  125 FMA: five in-plane sums, one per accumulator
-// In-plane neighbours come through L1 (25 loads per cell and plane, 5 x 5 threads share them); no shared memory, no
-// barriers, so rows / columns outside the grid simply retire.  A chunk of planes costs 4 extra plane reads of warm-up.
+//   SEP5     15 FMA: a[dh] * b[dr] * c[dc] (rank 1 along every axis): see k_stencil3d_r2_sep
+// In-plane neighbours come through L1; no shared memory, no barriers, so rows / columns outside the grid simply retire.
+// A chunk of planes costs 4 extra plane reads of warm-up.  Measured on B200 at 512^3 (profiles/r2_extensions_*.json):
+// STAR13 225, SEP5 195, HSEP5 179, DIRECT125 57 GStencil/s -- first versions, short of memory-level parallelism (one
+// dependent chain of planes per thread), see DESIGN.md section 2.5.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -196,10 +199,60 @@ k_stencil3d_r2_pair(const __grid_constant__ Geom3DR2 g, const __grid_constant__ 
     }
 }
 
-// which kernel: 0 = one cell per thread, plain loads (the first version); 1 = read-only loads, four planes per trip;
-// 2 = two cells per thread (needs an even column count and 16-byte aligned buffers, else 1).  LORA_R2_VARIANT overrides
-// the default (tuning / the parity tests run every variant).
-constexpr int kDefaultVariant = 0;
+// Fully separable tables, w[dh][dr][dc] = a[dh] b[dr] c[dc] (form SEP5: the default box3d2r table is one): 15 FMA and
+// FIVE loads per cell and plane instead of 25.  A lane owns one column: it sums its column over the five rows with b
+// (five aligned, fully coalesced loads), takes the row sums of the two columns either side from its neighbour lanes by
+// shuffle and combines them with c, then pushes a[dh] * t into the five accumulators.  Lanes 0, 1, 30, 31 of a warp only
+// feed their neighbours: a warp stores 28 columns and adjacent warps overlap by 4 (12.5 % redundant loads -- against
+// five times fewer loads overall).
+constexpr int kSepOut = 28;  // columns a warp stores
+
+__global__ void __launch_bounds__(kR2Cols * kR2Rows)
+k_stencil3d_r2_sep(const __grid_constant__ Geom3DR2 g, const __grid_constant__ WeightsR2 w) {
+    const int lane = threadIdx.x & 31;
+    const int wbase = (blockIdx.x * (kR2Cols / 32) + (threadIdx.x >> 5)) * kSepOut;  // first column this warp stores
+    const int r = blockIdx.y * kR2Rows + threadIdx.y;
+    if (wbase >= g.n || r >= g.m) return;  // warp-uniform: a warp is 32 consecutive x of one y
+    const int c = wbase - 2 + lane;        // this lane's column; -2 .. n + 1 are cells of the padded row
+    const int cl = min(c, g.n + 1);        // lanes beyond that re-read the row's last halo cell (feeds no stored column)
+    const bool owner = lane >= 2 && lane < 2 + kSepOut && c < g.n;
+    const long long q_lo = g.lo + (long long)blockIdx.z * g.planes_per_chunk;
+    const long long q_hi = min(q_lo + (long long)g.planes_per_chunk, g.hi);
+    const long long row0 = (long long)(r + 2) * g.row_pitch + 4;
+    const double *__restrict__ in = g.in + row0 + cl;
+    double *__restrict__ out = g.out + row0 + c;
+    constexpr unsigned kFull = 0xffffffffu;
+
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (long long p = q_lo - 2; p <= q_hi + 1; p++) {
+        const double *pl = in + (p + 2) * g.plane_pitch;
+        double s = w.b[0] * __ldg(pl - 2 * g.row_pitch);
+        s = fma(w.b[1], __ldg(pl - g.row_pitch), s);
+        s = fma(w.b[2], __ldg(pl), s);
+        s = fma(w.b[3], __ldg(pl + g.row_pitch), s);
+        s = fma(w.b[4], __ldg(pl + 2 * g.row_pitch), s);
+        double t = w.c[2] * s;
+        t = fma(w.c[0], __shfl_up_sync(kFull, s, 2), t);    // column c - 2
+        t = fma(w.c[1], __shfl_up_sync(kFull, s, 1), t);    // column c - 1
+        t = fma(w.c[3], __shfl_down_sync(kFull, s, 1), t);  // column c + 1
+        t = fma(w.c[4], __shfl_down_sync(kFull, s, 2), t);  // column c + 2
+#pragma unroll
+        for (int k = 0; k < 5; k++) acc[k] = fma(w.a[4 - k], t, acc[k]);  // dh = 2 - k
+        if (owner && p - 2 >= q_lo) out[p * g.plane_pitch] = acc[0];
+        acc[0] = acc[1];
+        acc[1] = acc[2];
+        acc[2] = acc[3];
+        acc[3] = acc[4];
+        acc[4] = 0.0;
+    }
+}
+
+// which kernel for the other forms: 0 = one cell per thread, plain loads (the first version); 1 = read-only loads, four
+// planes per trip; 2 = two cells per thread (needs an even column count and 16-byte aligned buffers, else 0).  Measured
+// at 512^3 (profiles/r2_extensions_variants.json), GStencil/s for variants 0 / 1 / 2: 13-point 206 / 216 / 221, rank 1
+// along the plane axis 126 / 86 / 178, 125 taps 29 / 29 / 55.  LORA_R2_VARIANT overrides the default (the parity tests
+// run every variant).
+constexpr int kDefaultVariant = 2;
 
 template <int FORM>
 cudaError_t launch_form(int variant, dim3 grid, dim3 block, const Geom3DR2 &g, const WeightsR2 &w, cudaStream_t s) {
@@ -227,8 +280,8 @@ cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count,
         if (v >= 0 && v <= 2) variant = v;
     }
     const bool pair_ok = g.n % 2 == 0 && reinterpret_cast<uintptr_t>(g.in) % 16 == 0 && reinterpret_cast<uintptr_t>(g.out) % 16 == 0;
-    if (variant == 2 && !pair_ok) variant = 1;
-    const int cols_per_cta = kR2Cols * (variant == 2 ? 2 : 1);
+    if (variant == 2 && !pair_ok) variant = 0;
+    const int cols_per_cta = form == LORA_FORM_SEP5 ? (kR2Cols / 32) * kSepOut : kR2Cols * (variant == 2 ? 2 : 1);
     const long long bx = (g.n + cols_per_cta - 1) / cols_per_cta, by = (g.m + kR2Rows - 1) / kR2Rows;
     if (by > 65535) return cudaErrorInvalidConfiguration;
     long long want = (32LL * sm_count + bx * by - 1) / (bx * by);  // chunks wanted
@@ -241,6 +294,9 @@ cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count,
     const dim3 grid((unsigned)bx, (unsigned)by, (unsigned)chunks);
     const dim3 block(kR2Cols, kR2Rows);
     switch (form) {
+        case LORA_FORM_SEP5:
+            k_stencil3d_r2_sep<<<grid, block, 0, s>>>(g, w);
+            return cudaGetLastError();
         case LORA_FORM_STAR13: return launch_form<LORA_FORM_STAR13>(variant, grid, block, g, w, s);
         case LORA_FORM_HSEP5: return launch_form<LORA_FORM_HSEP5>(variant, grid, block, g, w, s);
         case LORA_FORM_DIRECT125: return launch_form<LORA_FORM_DIRECT125>(variant, grid, block, g, w, s);

@@ -13,7 +13,7 @@ MAX_TB_1D = 15     # deepest temporal block of the 1-D kernel (kMaxTb1 in csrc/k
 DEFAULT_TB_1D = 15  # kDefaultTb1
 BOUNDARY_NAMES = ["reference", "dirichlet", "zero", "periodic"]
 FORM_NAMES = {0: "taps9", 1: "cross", 2: "pyramid", 3: "diamond", 4: "direct49", 5: "sep3", 6: "star7", 7: "direct27",
-              8: "pyramid_pruned", 9: "rank2", 10: "rank3", 11: "star13", 12: "hsep5", 13: "direct125"}
+              8: "pyramid_pruned", 9: "rank2", 10: "rank3", 11: "star13", 12: "hsep5", 13: "direct125", 14: "sep5"}
 
 
 def _dp(a: np.ndarray):

@@ -59,6 +59,16 @@ for name, shape, params in (("star3d2r default (13 taps)", "star3d2r", None), ("
         del plan
         torch.cuda.empty_cache()
 os.environ.pop("LORA_R2_VARIANT", None)
+for sep5 in ("0", "1"):  # the default box table is fully separable: 25 + 5 taps (two cells per thread) vs 5 + 5 + 5
+    os.environ["LORA_R2_SEP5"] = sep5
+    plan = ls.Plan("box3d2r", (512, 512, 512))
+    r = {"case": f"box3d2r default, LORA_R2_SEP5={sep5}", "dims": [512, 512, 512], "launches": args.launches, **timed(plan, args.launches)}
+    r["fixed_16B_roofline_frac"] = round(r["gstencil_best"] / 403.5, 3)
+    rows.append(r)
+    print(json.dumps(r), flush=True)
+    del plan
+    torch.cuda.empty_cache()
+os.environ.pop("LORA_R2_SEP5", None)
 if args.periodic:
     for shape, dims in (("star2d3r", (10240, 10240)), ("box3d1r", (512, 512, 512)), ("1d2r", (1 << 26,))):
         for boundary in ("reference", "periodic"):

@@ -75,6 +75,19 @@ def test_every_weight_is_honoured_in_both_modes():
                 assert np.array_equal(eff, w), name  # only the rank-1 form re-multiplies its factors
 
 
+def test_fully_separable_tables_factor_exactly_when_the_sep5_form_is_on(monkeypatch):
+    """LORA_R2_SEP5=1: a (x) b (x) c tables take the 5 + 5 + 5 form; integer tables factor into integers (exact taps)."""
+    monkeypatch.setenv("LORA_R2_SEP5", "1")
+    w = oracle.reference_params_r2("box3d2r")
+    assert np.array_equal(effective_weights("box3d2r", ls.WEIGHTS_GENERAL, w), w)
+    rng = np.random.default_rng(4)
+    w = np.einsum("i,j,k->ijk", rng.uniform(-1, 1, 5), rng.uniform(-1, 1, 5), rng.uniform(-1, 1, 5)).reshape(-1)
+    assert np.abs(effective_weights("box3d2r", ls.WEIGHTS_GENERAL, w) - w).max() <= 64 * 2.3e-16 * np.abs(w).max()
+    # rank 1 along the plane axis only: stays what it was
+    w = np.einsum("i,jk->ijk", rng.uniform(-1, 1, 5), rng.uniform(-1, 1, (5, 5))).reshape(-1)
+    assert np.abs(effective_weights("box3d2r", ls.WEIGHTS_GENERAL, w) - w).max() <= 64 * 2.3e-16 * np.abs(w).max()
+
+
 def test_reference_only_entry_points_refuse_the_new_shapes():
     """Slabs (and everything else that asks shape_dim) do not know these shapes: an error, not a wrong layout."""
     from ctypes import POINTER, byref, c_double, c_longlong, c_void_p
@@ -160,3 +173,40 @@ def test_plan_api_ranges_boundaries_and_torch_op(variant, monkeypatch):
         y = torch.ops.lorastencil.stencil3d(torch.from_numpy(a).cuda(), shape, 4)
         ref = oracle.run_r2(a, w, 4)
         assert np.abs(y.cpu().numpy() - ref).max() <= RTOL * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(12, 10, 64), (1, 1, 1), (5, 9, 31), (40, 33, 130), (70, 6, 300), (9, 5, 27), (9, 5, 28),
+                                  (9, 5, 29), (6, 3, 112), (6, 3, 113), (20, 16, 128)])
+def test_fully_separable_form(dims, monkeypatch):
+    """LORA_R2_SEP5=1 (csrc/stencil3d_r2.cu: k_stencil3d_r2_sep -- row sums exchanged between lanes by shuffle, warps of 28
+    stored columns): the default box table (exact on integer data) and a random a (x) b (x) c table, column counts
+    around the warp and CTA widths (28, 112)."""
+    import torch
+    monkeypatch.setenv("LORA_R2_SEP5", "1")
+    ops.set_verbose(False)
+    rng = np.random.default_rng(5)
+    plan = ls.Plan("box3d2r", dims)
+    assert "separable a(h) x b(m) x c(n)" in plan.describe
+    w = oracle.reference_params_r2("box3d2r")
+    a = rng.integers(0, 100, oracle.padded_shape_r2(dims)).astype(np.float64)
+    for times in (1, 2, 3, 4):
+        out = np.full_like(a, -7.0)
+        ops.gpu_box_3d2r(a, out, w, times, *dims)
+        assert np.array_equal(out, oracle.run_r2(a, w, times)), (dims, times)
+    ws = np.einsum("i,j,k->ijk", rng.uniform(-1, 1, 5), rng.uniform(-1, 1, 5), rng.uniform(-1, 1, 5)).reshape(-1)
+    af = rng.uniform(-1, 1, a.shape)
+    plan = ls.Plan("box3d2r", dims, params=ws, mode=ls.WEIGHTS_GENERAL)
+    assert "separable a(h) x b(m) x c(n)" in plan.describe
+    for times in (1, 5):
+        got = plan.run(torch.from_numpy(af).cuda(), plan.new_buffer(), times).cpu().numpy()
+        ref = oracle.run_r2(af, ws, times)
+        assert np.abs(got - ref).max() <= RTOL * np.abs(ref).max(), (dims, times)
+    # plane ranges of one launch
+    src, whole, parts = torch.from_numpy(af).cuda(), plan.new_buffer(), plan.new_buffer()
+    plan.step(src, whole)
+    cut = max(1, dims[0] // 3)
+    for lo, hi in ((0, cut), (cut, dims[0])):
+        plan.step(src, parts, lo, hi)
+    torch.cuda.synchronize()
+    assert torch.equal(whole, parts)
