@@ -25,6 +25,10 @@ Numbers on the JSON line:
              fixed-16-B roofline fraction among them.
   parity     (every N) small grids of all shapes through the same slab driver the timed run uses, gathered and compared
              with the CPU oracle on rank 0 -- multi-GPU correctness travels with the scaling record.
+  extensions (N = 1, with `shapes`) the section-8(f)-4 additions, which are not reference shapes and therefore not part
+             of `shapes` / `worst_shape_frac`: the radius-2 3-D shapes star3d2r / box3d2r at 512^3 (device-resident, best
+             and median of 3) and the periodic boundary mode against the reference halo at one launch per step, each with
+             a small-grid comparison against the CPU oracle.  Failure-proof: an exception becomes {"error": ...}.
   scaling_extra  (every N) BASELINE.json configs[4]: box2d1r 40960^2 and box3d1r 1024^3 strong scaling (global grid
              fixed, N slabs), and per-GPU-constant 2-D / 3-D slabs (weak scaling), with the bytes exchanged per step.
 """
@@ -342,6 +346,68 @@ def measure_shape(torch, ls, ops, shape, dims, launches, hbm_gbs, device_index, 
         allc = time_cpu(shape, dims, min_seconds=4.0, max_launches=8)
         row["cpu_baseline"] = {"one_core": one, "all_cores": allc}
     return row
+
+
+def measure_extensions(torch, ls, hbm_gbs):
+    """Rows for the additions beyond the reference's shape list (DESIGN.md sections 2.5 and 4)."""
+    import oracle
+    rows = []
+
+    def timed(plan, launches=6, reps=3):
+        b0 = device_fill(torch, plan.padded_shape, 100, "cuda", 1)
+        b1 = plan.new_buffer()
+        plan.run(b0, b1, 2)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.run(b0, b1, launches)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        cells = float(np.prod(plan.dims))
+        gst = cells * launches / (min(ms) / 1e3) / 1e9
+        return {"launches": launches, "reps": reps, "gstencils": gst,
+                "gstencils_median": cells * launches / (statistics.median(ms) / 1e3) / 1e9,
+                "roofline_frac": gst * 16 / hbm_gbs, "form": plan.describe, "temporal_block": plan.temporal_block}
+
+    rng = np.random.default_rng(2)
+    for shape in ("star3d2r", "box3d2r"):
+        small = (9, 12, 70)
+        a = rng.uniform(-1, 1, oracle.padded_shape_r2(small))
+        w = oracle.reference_params_r2(shape)
+        ps = ls.Plan(shape, small)
+        got = ps.run(torch.from_numpy(a).cuda(), ps.new_buffer(), 3).cpu().numpy()
+        ref = oracle.run_r2(a, w, 3)
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        row = {"what": f"{shape} (radius 2, 125 weights; not a reference shape)", "dims": [512, 512, 512],
+               "parity": {"dims": list(small), "launches": 3, "max_rel_err": err, "ok": err <= 1e-12}}
+        row.update(timed(ls.Plan(shape, (512, 512, 512))))
+        rows.append(row)
+        torch.cuda.empty_cache()
+    for shape, dims, small in (("star2d3r", (10240, 10240), (40, 66)), ("box3d1r", (512, 512, 512), (6, 10, 64))):
+        a = rng.uniform(-1, 1, oracle.padded_shape(shape, small))
+        ps = ls.Plan(shape, small)
+        ps.boundary = "periodic"
+        got = ps.run(torch.from_numpy(a).cuda(), ps.new_buffer(), 3).cpu().numpy()
+        ref = oracle.run_periodic(shape, a, oracle.effective_params(shape), 3)
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        row = {"what": f"{shape}, periodic boundary (one launch per step)", "dims": list(dims),
+               "parity": {"dims": list(small), "launches": 3, "max_rel_err": err, "ok": err <= 1e-12}}
+        for boundary in ("periodic", "reference"):
+            plan = ls.Plan(shape, dims)
+            plan.temporal_block = 1  # like with like: the periodic mode runs one launch per step
+            plan.boundary = boundary
+            t = timed(plan)
+            if boundary == "periodic":
+                row.update(t)
+            else:
+                row["gstencils_reference_halo_unfused"] = t["gstencils"]
+            del plan
+            torch.cuda.empty_cache()
+        rows.append(row)
+    return rows
 
 
 def exchange_bytes_per_step(shape, dims, tb):
@@ -717,6 +783,10 @@ def main():
         worst = min(line["shapes"], key=lambda r: r["roofline_frac"])
         line["worst_shape_frac"] = worst["roofline_frac"]
         line["worst_shape"] = worst["shape"]
+        try:  # additions beyond the reference's shape list: never allowed to cost the line
+            line["extensions"] = measure_extensions(torch, ls, hbm_gbs)
+        except Exception as e:  # noqa: BLE001
+            line["extensions"] = {"error": f"{type(e).__name__}: {e}"}
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
     if world > 1:
