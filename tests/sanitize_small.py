@@ -7,7 +7,8 @@ hunted with canaries instead, tests/test_parity_gpu.py::test_no_write_outside_th
 
 Covers: the drop-in operators of all 8 shapes at ragged sizes, fused 1-D sweeps (every temporal block depth, virtual
 halo, sub-ranges), the chunked copy-overlapped 1-D operator, fused 2-D sweeps (edge strips, narrow grids), general
-weights (direct49 / direct27 forms).  Results are checked against the oracle as well."""
+weights (direct49 / direct27 forms), the radius-2 3-D shapes (every form and kernel variant), the periodic halo
+refresh.  Results are checked against the oracle as well."""
 import os
 import sys
 
@@ -72,4 +73,32 @@ a = np.random.default_rng(7).uniform(-1, 1, (6 + 2, 20 + 4, 64 + 8))
 out = np.zeros_like(a)
 ops.run_host("box3d1r", a, out, w27, 2, (6, 20, 64), mode=ls.WEIGHTS_GENERAL)
 check("box3d1r", out, oracle.run(3, a, w27, 2), "3-D general weights (direct27)")
+
+# radius-2 3-D shapes: every form (13-point, fully separable, rank 1 along h, 125 taps) and every kernel variant
+rng = np.random.default_rng(8)
+dense = rng.uniform(-1, 1, 125)
+hsep = np.einsum("i,jk->ijk", rng.uniform(-1, 1, 5), rng.uniform(-1, 1, (5, 5))).reshape(-1)
+for variant in ("0", "1", "2"):
+    os.environ["LORA_R2_VARIANT"] = variant
+    for shape, w, dims in (("star3d2r", oracle.reference_params_r2("star3d2r"), (9, 7, 130)), ("box3d2r", oracle.reference_params_r2("box3d2r"), (20, 5, 113)),
+                           ("box3d2r", hsep, (6, 9, 31)), ("box3d2r", dense, (17, 3, 64))):
+        a = rng.uniform(-1, 1, oracle.padded_shape_r2(dims))
+        out = np.zeros_like(a)
+        ops.BY_SHAPE[shape](a, out, w, 3, *dims)
+        ref = oracle.run_r2(a, w, 3)
+        err = np.abs(out - ref).max() / np.abs(ref).max()
+        assert err <= RTOL, (shape, dims, variant, err)
+os.environ.pop("LORA_R2_VARIANT")
+print("ok radius-2 shapes, variants 0..2", flush=True)
+
+# periodic boundary: the halo refresh kernel on every layout
+for shape, dims in (("1d2r", (5001,)), ("star2d3r", (33, 71)), ("box2d3r", (40, 66)), ("star3d1r", (5, 9, 31)), ("box3d1r", (6, 10, 64))):
+    a = rng.uniform(-1, 1, oracle.padded_shape(shape, dims))
+    plan = ls.Plan(shape, dims)
+    plan.boundary = "periodic"
+    got = plan.run(torch.from_numpy(a).cuda(), plan.new_buffer(), 4).cpu().numpy()
+    ref = oracle.run_periodic(shape, a, oracle.effective_params(shape), 4)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err <= RTOL, (shape, dims, err)
+print("ok periodic boundary", flush=True)
 print("sanitize_small OK")
