@@ -98,7 +98,7 @@ void lora_gpu_run_host(int shape, int mode, const double *in, double *out, const
  * Returns the previous value.  Also settable with the environment variable LORA_QUIET=1. */
 int lora_set_verbose(int on);
 
-/* milliseconds the last lora_gpu_* call spent in its launch loop (the reference's timed region:
+/* milliseconds the last lora_gpu_* call of the CALLING THREAD spent in its launch loop (the reference's timed region:
  * launches + device sync, src/2d/gpu.cu:408-414), and in the whole call (alloc + H2D + D2H too) */
 double lora_last_loop_ms(void);
 double lora_last_total_ms(void);

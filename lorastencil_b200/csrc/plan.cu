@@ -1374,9 +1374,11 @@ extern "C" int lora_effective_weights(int shape, int mode, const double *params,
 // layer 1: drop-in host operators
 // ---------------------------------------------------------------------------------------------
 static int g_verbose = -1;
-static double g_loop_ms = 0, g_total_ms = 0;
-static int g_chunks = 1;  // chunks the last drop-in call was cut into (1-D copy/compute overlap)
-static int g_bands = 1;   // time-skewed bands of the last call that took the band pipeline (run_host_pipelined)
+// what the last drop-in call ON THIS THREAD measured / chose: concurrent callers (they serialise on the workspace mutex)
+// each read their own figures back
+static thread_local double g_loop_ms = 0, g_total_ms = 0;
+static thread_local int g_chunks = 1;  // chunks the last drop-in call was cut into (1-D copy/compute overlap)
+static thread_local int g_bands = 1;   // time-skewed bands of the last call that took the band pipeline (run_host_pipelined)
 static std::mutex g_ws_mutex;
 static std::vector<double *> g_ws;  // device workspace the drop-in operators cache between calls (equal-sized buffers)
 static size_t g_ws_bytes = 0;
@@ -1800,7 +1802,7 @@ static int wanted_gpus(std::vector<int> &devices) {
     for (int i = 0; i < k; i++) devices.push_back(i);
     return k;
 }
-static int g_last_gpus = 1;
+static thread_local int g_last_gpus = 1;
 extern "C" int lora_last_gpus(void) { return g_last_gpus; }
 
 // The drop-in operator on k GPUs of this process (LORA_NGPU=k): the padded host grid is cut into k slabs along its
