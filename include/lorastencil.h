@@ -296,6 +296,9 @@ int lora_debug_tasks_2dtb_pairs(int m, int n, int lo, int hi, int sm_count, int 
 /* the periodic halo refresh (lora_plan_wrap_ring: same work items, same axis order) applied to a HOST array of the padded
  * size of a dim-D grid with interior sizes dims[0..dim) */
 int lora_debug_wrap_ring_host(int dim, const long long *dims, double *buf);
+/* launch geometry of the radius-2 3-D kernels for an h x m x n grid: out4 = {grid.x, grid.y, plane chunks, planes per
+ * chunk}; form = LORA_FORM_STAR13 | HSEP5 | DIRECT125 | SEP5, variant = LORA_R2_VARIANT (0..2) */
+int lora_debug_r2_grid(int form, int variant, long long h, int m, int n, int sm_count, long long *out4);
 
 /* ------------------------------------------------------------------------------------------
  * Layer 3: host low-rank decomposition (inspection / tests)

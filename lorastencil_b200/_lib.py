@@ -37,7 +37,7 @@ C_ABI_SYMBOLS = (
     "lora_plan_padded_elems", "lora_plan_step", "lora_plan_run", "lora_plan_set_temporal_block",
     "lora_plan_temporal_block", "lora_plan_set_boundary", "lora_plan_boundary", "lora_plan_wrap_ring", "lora_plan_step_fused", "lora_plan_step_mirror", "lora_plan_step_fused_mirror",
     "lora_peer_alloc", "lora_peer_free", "lora_peer_open", "lora_peer_close", "lora_stream_write_flag",
-    "lora_stream_wait_flag_geq", "lora_debug_temporal_schedule", "lora_debug_pair_schedule", "lora_debug_tasks_2dtb", "lora_debug_tasks_2dtb_pairs", "lora_debug_wrap_ring_host", "lora_debug_tb2_probe", "lora_plan_launch_count", "lora_plan_describe",
+    "lora_stream_wait_flag_geq", "lora_debug_temporal_schedule", "lora_debug_pair_schedule", "lora_debug_tasks_2dtb", "lora_debug_tasks_2dtb_pairs", "lora_debug_wrap_ring_host", "lora_debug_r2_grid", "lora_debug_tb2_probe", "lora_plan_launch_count", "lora_plan_describe",
     "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
     "lora_set_gpus", "lora_last_gpus",
     "lora_slab_create", "lora_slab_destroy", "lora_slab_info", "lora_slab_buffer", "lora_slab_export",
@@ -157,6 +157,8 @@ def lib() -> ctypes.CDLL:
     L.lora_debug_tasks_2dtb_pairs.restype = c_int
     L.lora_debug_wrap_ring_host.argtypes = [c_int, POINTER(c_longlong), POINTER(c_double)]
     L.lora_debug_wrap_ring_host.restype = c_int
+    L.lora_debug_r2_grid.argtypes = [c_int, c_int, c_longlong, c_int, c_int, c_int, POINTER(c_longlong)]
+    L.lora_debug_r2_grid.restype = c_int
     L.lora_plan_launch_count.argtypes = [c_void_p]
     L.lora_plan_launch_count.restype = c_longlong
     L.lora_plan_describe.argtypes = [c_void_p]

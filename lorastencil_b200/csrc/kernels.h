@@ -283,6 +283,9 @@ struct WeightsR2 {
     double b[5], c[5];  // SEP5: q[(dr + 2) * 5 + dc + 2] = b[dr + 2] * c[dc + 2]
 };
 cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count, cudaStream_t s);  // picks planes_per_chunk
+long long r2_planes_per_chunk(long long planes, long long ctas_per_plane, int sm_count);
+int r2_cols_per_cta(int form, int variant);
+int r2_rows_per_cta();
 
 // periodic halo ring (boundary.cu): one axis of an array seen as [outer][len + 2 halo][inner]
 cudaError_t launch_wrap_axis(double *buf, long long outer, long long len, int halo, long long inner, int sm_count,

@@ -996,6 +996,20 @@ extern "C" int lora_debug_wrap_ring_host(int dim, const long long *dims, double 
     return LORA_OK;
 }
 
+// the launch geometry of the radius-2 3-D kernels for planes [0, h) of an h x m x n grid (stencil3d_r2.cu), for the CPU
+// tests: out4 = {grid.x, grid.y, plane chunks, planes per chunk}; no CUDA call
+extern "C" int lora_debug_r2_grid(int form, int variant, long long h, int m, int n, int sm_count, long long *out4) {
+    if (!out4 || h <= 0 || m <= 0 || n <= 0 || sm_count <= 0 || variant < 0 || variant > 2) return fail(LORA_ERR_ARG, "bad argument");
+    if (form != LORA_FORM_STAR13 && form != LORA_FORM_HSEP5 && form != LORA_FORM_DIRECT125 && form != LORA_FORM_SEP5)
+        return fail(LORA_ERR_ARG, "not a radius-2 form: %d", form);
+    const int cols = r2_cols_per_cta(form, variant), rows = r2_rows_per_cta();
+    out4[0] = (n + cols - 1) / cols;
+    out4[1] = (m + rows - 1) / rows;
+    out4[3] = r2_planes_per_chunk(h, out4[0] * out4[1], sm_count);
+    out4[2] = (h + out4[3] - 1) / out4[3];
+    return LORA_OK;
+}
+
 // for the slab driver (exchange.h): the ring of a slab's local array -- the side halo of every local row / plane, and the
 // leading / trailing halo rows only where the slab ends the grid
 int lora_plan_copy_ring(lora_plan_t *p, double *dst, const double *src, int lead, int trail, void *stream) {

@@ -267,10 +267,25 @@ cudaError_t launch_form(int variant, dim3 grid, dim3 block, const Geom3DR2 &g, c
 
 }  // namespace
 
-// g.planes_per_chunk is chosen here: every chunk of planes re-reads 4 planes of warm-up, so chunks as long as possible
-// -- but enough of them that the grid is many waves deep (about 32 CTAs of 256 threads per SM: 5 to 8 are resident, and
-// with one chunk a 512^3 grid is 1.4 waves, a third of the GPU idle in the second), at least 16 planes each, and never
-// more chunks than the z extent of a grid allows
+// Planes per chunk: every chunk of planes re-reads 4 planes of warm-up, so chunks as long as possible -- but enough of
+// them that the grid is many waves deep (about 32 CTAs of 256 threads per SM: 5 to 8 are resident, and with one chunk a
+// 512^3 grid is 1.4 waves, a third of the GPU idle in the second), never more than ceil(planes / 16) of them, nor more than
+// the z extent of a grid allows.  ctas_per_plane = CTAs one plane of one chunk takes.
+long long r2_planes_per_chunk(long long planes, long long ctas_per_plane, int sm_count) {
+    long long want = (32LL * sm_count + ctas_per_plane - 1) / ctas_per_plane;  // chunks wanted
+    want = want < 1 ? 1 : want;
+    if (want > (planes + 15) / 16) want = (planes + 15) / 16;
+    long long L = (planes + want - 1) / want;
+    if (L < (planes + 65534) / 65535) L = (planes + 65534) / 65535;
+    return L > 0x7fffffffLL ? 0x7fffffffLL : L;
+}
+
+// columns one CTA stores: 128 (one cell per thread), 256 (two cells), 112 (SEP5: 4 warps of 28)
+int r2_cols_per_cta(int form, int variant) {
+    return form == LORA_FORM_SEP5 ? (kR2Cols / 32) * kSepOut : kR2Cols * (variant == 2 ? 2 : 1);
+}
+int r2_rows_per_cta() { return kR2Rows; }
+
 cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count, cudaStream_t s) {
     const long long planes = g.hi - g.lo;
     if (planes <= 0) return cudaSuccess;
@@ -281,15 +296,10 @@ cudaError_t launch_3d_r2(int form, Geom3DR2 g, const WeightsR2 &w, int sm_count,
     }
     const bool pair_ok = g.n % 2 == 0 && reinterpret_cast<uintptr_t>(g.in) % 16 == 0 && reinterpret_cast<uintptr_t>(g.out) % 16 == 0;
     if (variant == 2 && !pair_ok) variant = 0;
-    const int cols_per_cta = form == LORA_FORM_SEP5 ? (kR2Cols / 32) * kSepOut : kR2Cols * (variant == 2 ? 2 : 1);
+    const int cols_per_cta = r2_cols_per_cta(form, variant);
     const long long bx = (g.n + cols_per_cta - 1) / cols_per_cta, by = (g.m + kR2Rows - 1) / kR2Rows;
     if (by > 65535) return cudaErrorInvalidConfiguration;
-    long long want = (32LL * sm_count + bx * by - 1) / (bx * by);  // chunks wanted
-    want = want < 1 ? 1 : want;
-    if (want > (planes + 15) / 16) want = (planes + 15) / 16;
-    long long L = (planes + want - 1) / want;
-    if (L < (planes + 65534) / 65535) L = (planes + 65534) / 65535;
-    g.planes_per_chunk = (int)(L > 0x7fffffffLL ? 0x7fffffffLL : L);
+    g.planes_per_chunk = (int)r2_planes_per_chunk(planes, bx * by, sm_count);
     const long long chunks = (planes + g.planes_per_chunk - 1) / g.planes_per_chunk;
     const dim3 grid((unsigned)bx, (unsigned)by, (unsigned)chunks);
     const dim3 block(kR2Cols, kR2Rows);

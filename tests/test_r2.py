@@ -88,6 +88,25 @@ def test_fully_separable_tables_factor_exactly_when_the_sep5_form_is_on(monkeypa
     assert np.abs(effective_weights("box3d2r", ls.WEIGHTS_GENERAL, w) - w).max() <= 64 * 2.3e-16 * np.abs(w).max()
 
 
+def test_launch_geometry_covers_every_plane_in_deep_grids():
+    """Host planning of the radius-2 launches (csrc/stencil3d_r2.cu: r2_planes_per_chunk): chunks cover all planes, none
+    is empty, never more than ceil(h / 16) of them, about 32 CTAs per SM when the grid allows, z <= 65535."""
+    from ctypes import c_longlong
+    L = _lib.lib()
+    out = (c_longlong * 4)()
+    cols = {(11, 0): 128, (11, 2): 256, (12, 1): 128, (13, 2): 256, (14, 0): 112, (14, 2): 112}
+    for (form, variant), c in cols.items():
+        for h, m, n in ((512, 512, 512), (1, 1, 1), (17, 3, 64), (1024, 1024, 1024), (100000, 2, 2), (3000000, 1, 1), (40, 33, 130)):
+            assert L.lora_debug_r2_grid(form, variant, h, m, n, 148, out) == 0
+            gx, gy, chunks, per = list(out)
+            assert gx == -(-n // c) and gy == -(-m // 2)
+            assert 1 <= chunks <= 65535 and (chunks - 1) * per < h <= chunks * per  # every plane, no empty chunk
+            assert 2 * per >= min(h, 16)  # never more than ceil(h / 16) chunks: a chunk re-reads 4 planes of warm-up
+            if h >= 64 and gx * gy * (h // 16) >= 32 * 148:
+                assert gx * gy * chunks >= 0.5 * 32 * 148, (form, variant, h, m, n)
+    assert L.lora_debug_r2_grid(5, 0, 8, 8, 8, 148, out) != 0  # not a radius-2 form
+
+
 def test_reference_only_entry_points_refuse_the_new_shapes():
     """Slabs (and everything else that asks shape_dim) do not know these shapes: an error, not a wrong layout."""
     from ctypes import POINTER, byref, c_double, c_longlong, c_void_p
