@@ -157,12 +157,17 @@ int lora_plan_run(lora_plan_t *plan, double *buf0, double *buf1, int times, void
 
 /* Temporal blocking (new; the reference launches one kernel per time step).  lora_plan_run fuses up to
  * `tb` consecutive launches into one sweep that keeps the intermediate grids on chip; results are
- * bit-identical to unfused launches, halo semantics (S2) included.  Default: 15 (the maximum) for the 1-D
- * shapes (or the environment variable LORA_TB).  2-D: 3 launches can be fused (tb >= 3 selects it, anything less
- * means one launch per step); default 3 for the cross and diamond forms, 1 for the FP64-bound pyramid / direct
- * forms (environment variable LORA_TB2=3|1).  For large cross / diamond grids the default is only provisional: the first
- * lora_plan_run times 3 single launches against 1 fused sweep on a scratch grid of the same width and keeps the winner
- * (cached per form, size and device; an explicit lora_plan_set_temporal_block or LORA_TB2 is final).  3-D: always 1.  */
+ * bit-identical to unfused launches, halo semantics (S2) included.
+ * 1-D: tb = 1..15, default 15 (environment variable LORA_TB).
+ * 2-D: sweeps of 3 launches (tb >= 3; every low-rank form) or of 2 (tb == 2; every form but the cross), anything else
+ * means one launch per step; default 3 for the cross form, 2 for the diamond and pyramid forms, 1 for the direct /
+ * rank-2 / rank-3 forms and for odd column counts (environment variable LORA_TB2=3|2|1).  For large cross grids the
+ * default is only provisional: the first lora_plan_run times 3 single launches against 1 fused sweep on a scratch grid
+ * of the same width and keeps the winner (cached per form, size and device; an explicit lora_plan_set_temporal_block
+ * or LORA_TB2 is final).
+ * 3-D: sweeps of 2 launches (tb >= 2) for the 7-point and separable forms, default on (LORA_TB3=1 turns it off); the
+ * 27-tap form, odd column counts and the radius-2 shapes run one launch per step.
+ * lora_plan_temporal_block returns what lora_plan_run will fuse. */
 int lora_plan_set_temporal_block(lora_plan_t *plan, int tb);
 int lora_plan_temporal_block(const lora_plan_t *plan);
 
@@ -185,9 +190,11 @@ int lora_plan_boundary(const lora_plan_t *plan);
 int lora_plan_wrap_ring(lora_plan_t *plan, double *buf, void *stream);
 
 /* One FUSED launch of `tb` time steps over interior range [lo, hi) of the outermost axis.
- * 2-D (tb = 1 or 3): rows [lo, hi); the ring of src must be the one its time parity calls for (caller's halo at even
- * `launches_before`, zeros at odd -- what the ping-pong gives when every sweep advances an odd number of steps),
- * halo_src is required, virt_lo / virt_hi say whether the rows above 0 / below m are the global halo ring.
+ * 2-D (tb = 1, 3, or 2 for the diamond / pyramid forms): rows [lo, hi); the ring of src must be the one its time parity
+ * calls for (caller's halo at even `launches_before`, zeros at odd -- what the ping-pong gives when every sweep advances
+ * an odd number of steps; sweeps of 2 all start at even times, which is why lora_plan_run lends buffer 1 the caller's
+ * ring while they run), halo_src is required, virt_lo / virt_hi say whether the rows above 0 / below m are the global
+ * halo ring.  3-D sweeps of 2 launches are issued by lora_plan_run and the slab drivers only (this entry point: 1-D, 2-D).
  * 1-D (tb = 1..15): reads src[lo - 4 tb, hi + 4 tb) clipped to the array, writes dst[lo, hi).  `launches_before` = time steps
  * already applied to src (its parity selects the halo each level sees).  virt_lo / virt_hi: that end of
  * the array is an end of the global line, whose halo cells are virtual -- caller's halo (read from the

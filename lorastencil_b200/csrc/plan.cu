@@ -805,7 +805,7 @@ static int step_fused_impl(lora_plan_t *p, const double *src, double *dst, const
         return fail(LORA_ERR_UNSUPPORTED, "a periodic boundary refreshes the halo ring before every launch: no fused sweeps");
     if (p->dim == 2)
         return step_fused_2d(p, src, dst, halo_src, lo, hi, tb, launches_before, virt_lo, virt_hi, ex, mirror_base, stream);
-    if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "temporal blocking is implemented for the 1-D and 2-D shapes");
+    if (p->dim != 1) return fail(LORA_ERR_UNSUPPORTED, "this entry point fuses 1-D and 2-D launches; 3-D sweeps of two are issued by lora_plan_run and the slab drivers");
     if (tb < 1 || tb > kMaxTb1) return fail(LORA_ERR_ARG, "temporal block must be 1..%d", kMaxTb1);
     if (lo < 0 || hi > p->dims[0] || lo > hi) return fail(LORA_ERR_ARG, "bad range [%lld, %lld)", lo, hi);
     if ((virt_lo || virt_hi) && !halo_src) return fail(LORA_ERR_ARG, "virtual halo needs halo_src");
