@@ -105,3 +105,33 @@ def test_periodic_general_weights_and_wrap_ring_on_its_own():
     plan.wrap_ring(c[1])
     torch.cuda.synchronize()
     assert np.array_equal(c[1].cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("shape,dims", [("1d2r", (257,)), ("star2d1r", (12, 20)), ("box2d3r", (9, 16)), ("box3d1r", (5, 6, 12))])
+def test_periodic_checker_is_shift_invariant_and_linear(shape, dims):
+    """Size-independent properties of a stencil on a torus: rolling the interior rolls the result; the operator is linear.
+    (Integer data and weights: both hold exactly.)"""
+    rng = np.random.default_rng(21)
+    d = len(dims)
+    inner = tuple(slice(h, -h) for h in oracle.HALO[d])
+    w = np.round(rng.uniform(-3, 3, oracle.reference_params(shape).size))
+
+    def padded(interior):
+        a = np.zeros(oracle.padded_shape(shape, dims))
+        a[inner] = interior
+        return a
+
+    x = rng.integers(0, 50, dims).astype(np.float64)
+    y = rng.integers(0, 50, dims).astype(np.float64)
+    fx = oracle.run_periodic(shape, padded(x), w, 3)[inner]
+    fy = oracle.run_periodic(shape, padded(y), w, 3)[inner]
+    shift = tuple(int(s) for s in rng.integers(1, 5, d))
+    rolled = oracle.run_periodic(shape, padded(np.roll(x, shift, axis=tuple(range(d)))), w, 3)[inner]
+    assert np.array_equal(rolled, np.roll(fx, shift, axis=tuple(range(d))))
+    assert np.array_equal(oracle.run_periodic(shape, padded(2 * x - 3 * y), w, 3)[inner], 2 * fx - 3 * fy)
+    # the caller's halo values are never read
+    junk = padded(x)
+    ring = np.ones_like(junk, dtype=bool)
+    ring[inner] = False
+    junk[ring] = 1e30
+    assert np.array_equal(oracle.run_periodic(shape, junk, w, 3)[inner], fx)
