@@ -344,6 +344,17 @@ typedef struct {
 /* factor a 7x7 weight table; shape picks the reference quirks when mode == REFERENCE */
 int lora_decompose_2d(int shape, int mode, const double *params49, lora_decomp2d_t *out);
 
+/* structure found in a 125-weight table of a radius-2 3-D shape (every weight is honoured whatever the form) */
+typedef struct {
+    int form;          /* LORA_FORM_STAR13 | LORA_FORM_SEP5 | LORA_FORM_HSEP5 | LORA_FORM_DIRECT125 */
+    double a[5];       /* HSEP5 / SEP5: profile along the plane axis, index dh+2 */
+    double b[5], c[5]; /* SEP5: profiles along rows / columns */
+    double q[25];      /* HSEP5 / SEP5: the in-plane table (SEP5: == b (x) c) */
+    double recon_err;  /* max |factors multiplied out - table| (0 for STAR13 / DIRECT125) */
+    int macs_per_cell; /* 13 | 15 | 30 | 125 */
+} lora_decomp3d_r2_t;
+int lora_decompose_3d_r2(int shape, const double *params125, lora_decomp3d_r2_t *out);
+
 /* the weight table the reference CLI passes for `shape` (src/1d/main.cu:77-78, src/2d/main.cu:139-195,
  * src/3d/main.cu:112-125): 9 / 49 / 27 doubles; for the radius-2 shapes our own default, 125 doubles (box3d2r:
  * [1,2,3,2,1] (x) [1,2,3,2,1] (x) [1,2,3,2,1]; star3d2r: centre 3, arms 2 then 1) */

@@ -16,7 +16,7 @@ shared library is missing or no CUDA device is present.
 from ._lib import (SHAPES, SHAPE_IDS, WEIGHTS_GENERAL, WEIGHTS_REFERENCE, LoraError, build, lib, lib_path,
                    library_built)
 from . import ops
-from .plan import Plan, decompose_2d, effective_weights, reference_table
+from .plan import Plan, decompose_2d, decompose_3d_r2, effective_weights, reference_table
 
 __all__ = ["SHAPES", "SHAPE_IDS", "WEIGHTS_GENERAL", "WEIGHTS_REFERENCE", "LoraError", "build", "lib", "lib_path",
-           "library_built", "ops", "Plan", "decompose_2d", "effective_weights", "reference_table"]
+           "library_built", "ops", "Plan", "decompose_2d", "decompose_3d_r2", "effective_weights", "reference_table"]

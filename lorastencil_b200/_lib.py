@@ -38,7 +38,7 @@ C_ABI_SYMBOLS = (
     "lora_plan_temporal_block", "lora_plan_set_boundary", "lora_plan_boundary", "lora_plan_wrap_ring", "lora_plan_step_fused", "lora_plan_step_mirror", "lora_plan_step_fused_mirror",
     "lora_peer_alloc", "lora_peer_free", "lora_peer_open", "lora_peer_close", "lora_stream_write_flag",
     "lora_stream_wait_flag_geq", "lora_debug_temporal_schedule", "lora_debug_pair_schedule", "lora_debug_tasks_2dtb", "lora_debug_tasks_2dtb_pairs", "lora_debug_wrap_ring_host", "lora_debug_r2_grid", "lora_debug_tb2_probe", "lora_plan_launch_count", "lora_plan_describe",
-    "lora_last_error", "lora_decompose_2d", "lora_reference_table", "lora_effective_weights",
+    "lora_last_error", "lora_decompose_2d", "lora_decompose_3d_r2", "lora_reference_table", "lora_effective_weights",
     "lora_set_gpus", "lora_last_gpus",
     "lora_slab_create", "lora_slab_destroy", "lora_slab_info", "lora_slab_buffer", "lora_slab_export",
     "lora_slab_connect_ipc", "lora_slab_connect_local", "lora_slab_reset", "lora_slab_sweep", "lora_slab_run",
@@ -61,6 +61,11 @@ class LoraError(RuntimeError):
 class Decomp2D(Structure):
     _fields_ = [("form", c_int), ("nterms", c_int), ("vert", c_double * 7 * 3), ("horiz", c_double * 7 * 3),
                 ("centre", c_double), ("residual", c_double * 8), ("recon_err", c_double), ("macs_per_cell", c_int)]
+
+
+class Decomp3DR2(Structure):
+    _fields_ = [("form", c_int), ("a", c_double * 5), ("b", c_double * 5), ("c", c_double * 5), ("q", c_double * 25),
+                ("recon_err", c_double), ("macs_per_cell", c_int)]
 
 
 def lib_path() -> str:
@@ -159,6 +164,8 @@ def lib() -> ctypes.CDLL:
     L.lora_debug_wrap_ring_host.restype = c_int
     L.lora_debug_r2_grid.argtypes = [c_int, c_int, c_longlong, c_int, c_int, c_int, POINTER(c_longlong)]
     L.lora_debug_r2_grid.restype = c_int
+    L.lora_decompose_3d_r2.argtypes = [c_int, dp, POINTER(Decomp3DR2)]
+    L.lora_decompose_3d_r2.restype = c_int
     L.lora_plan_launch_count.argtypes = [c_void_p]
     L.lora_plan_launch_count.restype = c_longlong
     L.lora_plan_describe.argtypes = [c_void_p]

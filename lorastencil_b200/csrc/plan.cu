@@ -1340,6 +1340,20 @@ extern "C" int lora_decompose_2d(int shape, int mode, const double *params49, lo
     return LORA_OK;
 }
 
+extern "C" int lora_decompose_3d_r2(int shape, const double *params125, lora_decomp3d_r2_t *out) {
+    if (!params125 || !out) return fail(LORA_ERR_ARG, "null argument");
+    Decomp3DR2 d;
+    if (!decompose_3d_r2(shape, params125, d)) return fail(LORA_ERR_ARG, "shape %d is not a radius-2 3-D shape", shape);
+    out->form = d.form;
+    std::memcpy(out->a, d.a, sizeof d.a);
+    std::memcpy(out->b, d.b, sizeof d.b);
+    std::memcpy(out->c, d.c, sizeof d.c);
+    std::memcpy(out->q, d.q, sizeof d.q);
+    out->recon_err = d.recon_err;
+    out->macs_per_cell = d.macs;
+    return LORA_OK;
+}
+
 extern "C" int lora_reference_table(int shape, double *table_out) {
     if (!table_out || (shape_dim(shape) == 0 && !shape_is_r2(shape))) return fail(LORA_ERR_ARG, "bad argument");
     reference_table(shape, table_out);

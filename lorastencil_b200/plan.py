@@ -50,6 +50,17 @@ def decompose_2d(shape: str, params, mode: int = _lib.WEIGHTS_GENERAL) -> dict:
             "macs_per_cell": d.macs_per_cell}
 
 
+def decompose_3d_r2(shape: str, params) -> dict:
+    """Structure the host finds in a 125-weight table of a radius-2 3-D shape (layer 3)."""
+    d = _lib.Decomp3DR2()
+    p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
+    if p.size != 125:
+        raise ValueError(f"expected 125 weights, got {p.size}")
+    _lib.check(_lib.lib().lora_decompose_3d_r2(_lib.SHAPE_IDS[shape], _dp(p), byref(d)), "lora_decompose_3d_r2")
+    return {"form": FORM_NAMES[d.form], "a": np.array(list(d.a)), "b": np.array(list(d.b)), "c": np.array(list(d.c)),
+            "q": np.array(list(d.q)).reshape(5, 5), "recon_err": d.recon_err, "macs_per_cell": d.macs_per_cell}
+
+
 class Plan:
     """A device-resident stencil plan: weights factored on the host once, launches on CUDA tensors.
 

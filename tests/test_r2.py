@@ -75,6 +75,40 @@ def test_every_weight_is_honoured_in_both_modes():
                 assert np.array_equal(eff, w), name  # only the rank-1 form re-multiplies its factors
 
 
+def test_form_follows_the_structure_of_the_table(monkeypatch):
+    """decompose_3d_r2 (csrc/decompose.cpp): 13-point star / fully separable / rank 1 along the plane axis / 125 taps."""
+    from lorastencil_b200.plan import decompose_3d_r2
+    monkeypatch.delenv("LORA_R2_SEP5", raising=False)
+    rng = np.random.default_rng(6)
+    for name, shape, w, form in tables(rng):
+        d = decompose_3d_r2(shape, w)
+        want = {"default box": "sep5"}.get(name, form)  # fully separable tables take the shuffle kernel by default
+        assert d["form"] == want, name
+        assert d["macs_per_cell"] == {"star13": 13, "sep5": 15, "hsep5": 30, "direct125": 125}[want]
+    # the default box factors into the integers it was made of: exact taps, exact first launches
+    d = decompose_3d_r2("box3d2r", oracle.reference_params_r2("box3d2r"))
+    for k in "abc":
+        assert np.array_equal(d[k], [1, 2, 3, 2, 1]), k
+    assert d["recon_err"] == 0.0 and np.array_equal(d["q"], np.outer(d["b"], d["c"]))
+    # one off-axis weight ends the star; one perturbed entry ends the separability
+    w = oracle.reference_params_r2("star3d2r").copy()
+    w[0] = 0.5
+    assert decompose_3d_r2("star3d2r", w)["form"] == "direct125"
+    w = oracle.reference_params_r2("box3d2r").copy()
+    w[7] += 1.0
+    assert decompose_3d_r2("box3d2r", w)["form"] == "direct125"
+    # a (x) Q with Q of rank 2: rank 1 along the plane axis only
+    q = np.outer([1, 2, 3, 2, 1], [1, 2, 3, 2, 1]) + np.outer([1, 0, 0, 0, 1], [0, 1, 0, 1, 0])
+    w = np.einsum("i,jk->ijk", [1.0, 2, 4, 2, 1], q).reshape(-1)
+    d = decompose_3d_r2("box3d2r", w)
+    assert d["form"] == "hsep5" and d["recon_err"] == 0.0 and np.array_equal(np.einsum("i,jk->ijk", d["a"], d["q"]).reshape(-1), w)
+    # LORA_R2_SEP5=0 keeps separable tables on the two-cells-per-thread kernel
+    monkeypatch.setenv("LORA_R2_SEP5", "0")
+    assert decompose_3d_r2("box3d2r", oracle.reference_params_r2("box3d2r"))["form"] == "hsep5"
+    with pytest.raises(_lib.LoraError):
+        decompose_3d_r2("box3d1r", np.zeros(125))
+
+
 def test_fully_separable_tables_factor_exactly_when_the_sep5_form_is_on(monkeypatch):
     """LORA_R2_SEP5=1: a (x) b (x) c tables take the 5 + 5 + 5 form; integer tables factor into integers (exact taps)."""
     monkeypatch.setenv("LORA_R2_SEP5", "1")
